@@ -1,0 +1,463 @@
+// Persistent, warp-specialised bf16 GEMM for sm_100a:  D[lane, col] = sum_k X[lane, k] * Y[col, k]
+//   * operands staged by TMA (cp.async.bulk.tensor, 128-B swizzle) into a multi-stage shared-memory ring,
+//   * products issued by ONE thread with tcgen05.mma (UMMA 128 x BN x 16, kind::f16, fp32 accumulate),
+//   * accumulators live in TMEM (two buffers, so the epilogue of tile i overlaps the main loop of tile i+1),
+//   * epilogue warps read TMEM with tcgen05.ld and apply the fused epilogue (bias / GELU / residual / SwiGLU).
+// Both operands are K-major ("TN" GEMM), which is exactly nn.Linear: activations [M,K] and weights [N,K].
+//
+// Replaces the cuBLAS calls underneath the reference's nn.Linear layers:
+//   SigLIP q/k/v/out/fc1/fc2, patch-embed-as-GEMM, mm_projector (video_head_live_llava_qwen.py:90-98),
+//   Qwen2 q/k/v/o/gate/up/down (video_head_live_llava_qwen.py:141-150).
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <cstdio>
+#include <cstring>
+
+namespace mmd {
+
+static thread_local std::string g_gemm_err;
+const char* gemm_last_error() { return g_gemm_err.c_str(); }
+
+constexpr int BM = 128;        // UMMA M: TMEM lanes
+constexpr int BK = 64;         // bf16 elements per k-block = one 128-B swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
+constexpr int SMEM_BUDGET = 227 * 1024;
+
+struct GemmKernelParams {
+  int x_rows, y_rows;
+  int x_tiles, y_tiles;
+  int k_splits, kb_per_split, kb_total;
+  const float* bias;
+  void* out;
+  long long ldo;
+  long long split_stride;
+};
+
+template <int BN, bool DUAL>
+struct GemmCfg {
+  static constexpr int X_BYTES = BM * BK * 2;                      // 16 KB
+  static constexpr int Y_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = X_BYTES * (DUAL ? 2 : 1) + Y_BYTES;
+  static constexpr int ACC_COLS = BN * (DUAL ? 2 : 1);
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;                   // double-buffered accumulator
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - 1024 /*align slack*/ - BAR_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static_assert(TMEM_COLS <= 512, "TMEM overflow");
+  static_assert(STAGES >= 3, "pipeline too shallow");
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // 0.5 x (1 + tanh( sqrt(2/pi) (x + 0.044715 x^3) ))  -- SigLIP "gelu_pytorch_tanh"
+  const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  return 0.5f * x * (1.0f + t);
+}
+__device__ __forceinline__ float gelu_erf_f(float x) {  // nn.GELU() default used by mm_projector (mlp2x_gelu)
+  return 0.5f * x * (1.0f + erff(x * 0.7071067811865476f));
+}
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x) {
+  if constexpr (ACT == ACT_GELU_TANH) return gelu_tanh_f(x);
+  if constexpr (ACT == ACT_GELU_ERF) return gelu_erf_f(x);
+  return x;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int BN, bool DUAL, int EPI, int ACT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
+                    const __grid_constant__ CUtensorMap tmY, const GemmKernelParams p) {
+  using Cfg = GemmCfg<BN, DUAL>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int total_tiles = p.x_tiles * p.y_tiles * p.k_splits;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmY);
+    if constexpr (DUAL) tma_prefetch_desc(&tmX2);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int ks = tile % p.k_splits;
+        const int rest = tile / p.k_splits;
+        const int xt = rest % p.x_tiles, yt = rest / p.x_tiles;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sX = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sY = sX + Cfg::X_BYTES * (DUAL ? 2 : 1);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          tma_load_2d(sX, &tmX, full_bar(stage), kb * BK, xt * BM);
+          if constexpr (DUAL) tma_load_2d(sX + Cfg::X_BYTES, &tmX2, full_bar(stage), kb * BK, xt * BM);
+          tma_load_2d(sY, &tmY, full_bar(stage), kb * BK, yt * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int ks = tile % p.k_splits;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::ACC_COLS;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sX = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sY = sX + Cfg::X_BYTES * (DUAL ? 2 : 1);
+          const uint64_t dX = umma_desc_k_sw128(sX);
+          const uint64_t dY = umma_desc_k_sw128(sY);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
+            // advancing K inside the 128-B swizzle atom = +32 B on the start address (encoded >> 4)
+            umma_f16(d_tmem, dX + 2u * k, dY + 2u * k, idesc, accum);
+            if constexpr (DUAL) {
+              const uint64_t dX2 = umma_desc_k_sw128(sX + Cfg::X_BYTES);
+              umma_f16(d_tmem + BN, dX2 + 2u * k, dY + 2u * k, idesc, accum);
+            }
+          }
+          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (TMEM -> registers -> global) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int lane_row = q * 32 + (int)lane_id();
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int ks = tile % p.k_splits;
+      const int rest = tile / p.k_splits;
+      const int xt = rest % p.x_tiles, yt = rest / p.x_tiles;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_COLS;
+      const int xi = xt * BM + lane_row;  // index along X rows (TMEM lane)
+      const int y0 = yt * BN;             // first index along Y rows (TMEM column 0)
+
+      if constexpr (EPI == EPI_BF16 || EPI == EPI_RESID_F32 || EPI == EPI_F32) {
+        // normal orientation: lane = output row m, columns = n (contiguous in memory)
+        const bool row_ok = xi < p.x_rows;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (y0 + c0 >= p.y_rows) break;  // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + c0, v);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int n = y0 + c0 + g * 8;
+              if (n < p.y_rows) {  // y_rows % 8 == 0 is enforced by the launcher
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+                if (p.bias != nullptr) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                }
+                if constexpr (EPI == EPI_BF16) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) f[j] = apply_act<ACT>(f[j]);
+                  uint4 o;
+                  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+                  o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+                  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)xi * p.ldo + n;
+                  *reinterpret_cast<uint4*>(dst) = o;
+                } else {
+                  float* dst = reinterpret_cast<float*>(p.out) + (long long)xi * p.ldo + n;
+                  float4 r0, r1;
+                  if constexpr (EPI == EPI_RESID_F32) {
+                    r0 = *reinterpret_cast<const float4*>(dst);
+                    r1 = *reinterpret_cast<const float4*>(dst + 4);
+                  } else {
+                    r0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    r1 = r0;
+                  }
+                  r0.x += f[0]; r0.y += f[1]; r0.z += f[2]; r0.w += f[3];
+                  r1.x += f[4]; r1.y += f[5]; r1.z += f[6]; r1.w += f[7];
+                  *reinterpret_cast<float4*>(dst) = r0;
+                  *reinterpret_cast<float4*>(dst + 4) = r1;
+                }
+              }
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_T_F32) {
+        // swap-AB: lane = n (weight row), column = token. Lanes of a warp write 32 consecutive n -> 128-B stores.
+        const bool n_ok = xi < p.x_rows;
+        float* plane = reinterpret_cast<float*>(p.out) + (long long)ks * p.split_stride;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (y0 + c0 >= p.y_rows) break;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + c0, v);
+          tmem_ld_wait();
+          if (n_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int tok = y0 + c0 + j;
+              if (tok < p.y_rows) plane[(long long)tok * p.ldo + xi] = __uint_as_float(v[j]);
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_T_SWIGLU) {
+        const bool n_ok = xi < p.x_rows;
+        __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          if (y0 + c0 >= p.y_rows) break;
+          uint32_t g[16], u[16];
+          tmem_ld_32x32b_x16(t_row + c0, g);
+          tmem_ld_32x32b_x16(t_row + BN + c0, u);
+          tmem_ld_wait();
+          if (n_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int tok = y0 + c0 + j;
+              if (tok < p.y_rows) {
+                const float gv = __uint_as_float(g[j]);
+                const float uv = __uint_as_float(u[j]);
+                const float s = gv / (1.0f + __expf(-gv));
+                outp[(long long)tok * p.ldo + xi] = __float2bfloat16_rn(s * uv);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Host side: tensor-map cache and dispatch
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct MapKey {
+  const void* ptr; int rows; int K; long long ld; int box_rows;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && K == o.K && ld == o.ld && box_rows == o.box_rows;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h ^= (size_t)k.rows * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= (size_t)k.K * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+    h ^= (size_t)k.ld * 0x165667B19E3779F9ull + (h << 6) + (h >> 2);
+    h ^= (size_t)k.box_rows + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+
+struct GemmContext {
+  int device = 0;
+  int num_sms = 148;
+  PFN_encodeTiled encode = nullptr;
+  std::mutex mu;
+  std::unordered_map<MapKey, CUtensorMap, MapKeyHash> maps;
+};
+
+GemmContext* gemm_context_create(int device) {
+  auto* c = new GemmContext();
+  c->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    g_gemm_err = "cudaGetDeviceProperties failed";
+    delete c;
+    return nullptr;
+  }
+  c->num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr) {
+    g_gemm_err = "cuTensorMapEncodeTiled entry point not found";
+    delete c;
+    return nullptr;
+  }
+  c->encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  return c;
+}
+void gemm_context_destroy(GemmContext* c) { delete c; }
+
+static int get_map(GemmContext* c, const void* ptr, int rows, int K, long long ld, int box_rows, CUtensorMap* out) {
+  MapKey key{ptr, rows, K, ld, box_rows};
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto it = c->maps.find(key);
+    if (it != c->maps.end()) { *out = it->second; return 0; }
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * 2) % 16 != 0) {
+    g_gemm_err = "gemm operand must be 16-B aligned with a 16-B aligned row stride";
+    return -2;
+  }
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = c->encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%lld box=%d", (int)r, rows, K, ld, box_rows);
+    g_gemm_err = buf;
+    return -3;
+  }
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->maps.size() > 65536) c->maps.clear();
+    c->maps.emplace(key, m);
+  }
+  *out = m;
+  return 0;
+}
+
+int gemm_effective_splits(int K, int k_splits) {
+  const int kb_total = (K + BK - 1) / BK;
+  if (k_splits < 1) k_splits = 1;
+  if (k_splits > kb_total) k_splits = kb_total;
+  const int per = (kb_total + k_splits - 1) / k_splits;
+  return (kb_total + per - 1) / per;
+}
+
+template <int BN, bool DUAL, int EPI, int ACT>
+static int launch_cfg(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, DUAL>;
+  auto kern = gemm_tcgen05_kernel<BN, DUAL, EPI, ACT>;
+  static bool attr_set = false;  // per instantiation
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { g_gemm_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -4; }
+    attr_set = true;
+  }
+  CUtensorMap tmX, tmX2, tmY;
+  int rc;
+  if ((rc = get_map(c, a.X, a.x_rows, a.K, a.ldx, BM, &tmX)) != 0) return rc;
+  if (DUAL) { if ((rc = get_map(c, a.X2, a.x_rows, a.K, a.ldx, BM, &tmX2)) != 0) return rc; }
+  else tmX2 = tmX;
+  if ((rc = get_map(c, a.Y, a.y_rows, a.K, a.ldy, BN, &tmY)) != 0) return rc;
+
+  GemmKernelParams p;
+  p.x_rows = a.x_rows; p.y_rows = a.y_rows;
+  p.x_tiles = (a.x_rows + BM - 1) / BM;
+  p.y_tiles = (a.y_rows + BN - 1) / BN;
+  p.kb_total = (a.K + BK - 1) / BK;
+  const int splits = (EPI == EPI_T_F32) ? gemm_effective_splits(a.K, a.k_splits) : 1;
+  p.k_splits = splits;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.split_stride = a.split_stride;
+  const long long tiles = (long long)p.x_tiles * p.y_tiles * p.k_splits;
+  int max_ctas = a.max_ctas > 0 ? a.max_ctas : c->num_sms;
+  const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
+  if (grid <= 0) return 0;
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmX, tmX2, tmY, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_gemm_err = std::string("gemm launch: ") + cudaGetErrorString(e); return -5; }
+  return 0;
+}
+
+template <int EPI, int ACT>
+static int launch_normal(GemmContext* c, const GemmArgs& a, cudaStream_t s) {
+  if (a.y_rows % 8 != 0) { g_gemm_err = "normal-orientation GEMM needs N % 8 == 0"; return -2; }
+  if (a.y_rows <= 128) return launch_cfg<128, false, EPI, ACT>(c, a, s);
+  return launch_cfg<256, false, EPI, ACT>(c, a, s);
+}
+
+int gemm_launch(GemmContext* c, const GemmArgs& a, cudaStream_t s) {
+  if (c == nullptr) { g_gemm_err = "null gemm context"; return -1; }
+  if (a.X == nullptr || a.Y == nullptr || a.out == nullptr || a.x_rows <= 0 || a.y_rows <= 0 || a.K <= 0) {
+    g_gemm_err = "gemm: null pointer or non-positive shape";
+    return -2;
+  }
+  if (a.K % 8 != 0) { g_gemm_err = "gemm: K must be a multiple of 8 (16-B rows for TMA)"; return -2; }
+  switch (a.epi) {
+    case EPI_BF16:
+      if (a.act == ACT_NONE) return launch_normal<EPI_BF16, ACT_NONE>(c, a, s);
+      if (a.act == ACT_GELU_TANH) return launch_normal<EPI_BF16, ACT_GELU_TANH>(c, a, s);
+      if (a.act == ACT_GELU_ERF) return launch_normal<EPI_BF16, ACT_GELU_ERF>(c, a, s);
+      break;
+    case EPI_RESID_F32: return launch_normal<EPI_RESID_F32, ACT_NONE>(c, a, s);
+    case EPI_F32: return launch_normal<EPI_F32, ACT_NONE>(c, a, s);
+    case EPI_T_F32:
+      if (a.y_rows <= 64) return launch_cfg<64, false, EPI_T_F32, ACT_NONE>(c, a, s);
+      if (a.y_rows <= 128) return launch_cfg<128, false, EPI_T_F32, ACT_NONE>(c, a, s);
+      return launch_cfg<256, false, EPI_T_F32, ACT_NONE>(c, a, s);
+    case EPI_T_SWIGLU:
+      if (a.X2 == nullptr) { g_gemm_err = "swiglu gemm needs X2"; return -2; }
+      if (a.y_rows <= 64) return launch_cfg<64, true, EPI_T_SWIGLU, ACT_NONE>(c, a, s);
+      return launch_cfg<128, true, EPI_T_SWIGLU, ACT_NONE>(c, a, s);
+    default: break;
+  }
+  g_gemm_err = "gemm: unknown epilogue/activation";
+  return -2;
+}
+
+}  // namespace mmd

@@ -1,0 +1,47 @@
+// Host-side interface of the tcgen05 GEMM (see gemm.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace mmd {
+
+// Epilogue selector.
+//  "Normal" orientation: X = activations [M,K] (TMEM lanes = rows m), Y = weights [N,K] (TMEM columns = n).
+//  "T" (swap-AB) orientation: X = weights [N,K] (TMEM lanes = n), Y = activations [M,K] (columns = token m);
+//  used when M is small so the 128-wide UMMA M dimension is filled by weight rows and HBM streaming of the
+//  weights is spread over all SMs with split-K.
+enum GemmEpi : int {
+  EPI_BF16 = 0,      // out_bf16[m, n] = act(acc + bias[n])
+  EPI_RESID_F32 = 1, // out_f32[m, n] += acc + bias[n]            (fp32 residual stream, in place)
+  EPI_T_F32 = 2,     // out_f32[split][m, n] = acc                (split-K partial planes, no bias)
+  EPI_T_SWIGLU = 3,  // out_bf16[m, n] = silu(acc_gate) * acc_up  (two X operands: gate rows, up rows)
+  EPI_F32 = 4,       // out_f32[m, n] = acc + bias[n]
+};
+enum GemmAct : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2 };
+
+struct GemmArgs {
+  const __nv_bfloat16* X = nullptr;   // [x_rows, K], row stride ldx (elements)
+  const __nv_bfloat16* X2 = nullptr;  // second lane operand (EPI_T_SWIGLU: up_proj rows), same shape as X
+  const __nv_bfloat16* Y = nullptr;   // [y_rows, K], row stride ldy
+  int x_rows = 0, y_rows = 0, K = 0;
+  int64_t ldx = 0, ldy = 0;
+  int epi = EPI_BF16, act = ACT_NONE;
+  const float* bias = nullptr;        // may be null
+  void* out = nullptr;
+  int64_t ldo = 0;                    // output row stride (elements)
+  int k_splits = 1;                   // only EPI_T_F32
+  int64_t split_stride = 0;           // elements between partial planes
+  int max_ctas = 0;                   // 0 = number of SMs
+};
+
+struct GemmContext;  // tensor-map cache + device properties
+GemmContext* gemm_context_create(int device);
+void gemm_context_destroy(GemmContext*);
+// Returns 0 on success, negative on bad arguments / CUDA error; message via gemm_last_error().
+int gemm_launch(GemmContext*, const GemmArgs&, cudaStream_t stream);
+const char* gemm_last_error();
+// Effective number of split-K planes the launch will write for (K, requested splits).
+int gemm_effective_splits(int K, int k_splits);
+
+}  // namespace mmd

@@ -1,0 +1,59 @@
+"""Thin Python wrappers over the C ABI (tensor -> pointer marshalling only; no arithmetic happens here)."""
+import torch
+
+from . import _lib
+from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_T_F32, EPI_T_SWIGLU)
+
+
+def _chk2d(t, dtype):
+    assert t.is_cuda and t.dtype == dtype and t.dim() == 2 and t.stride(1) == 1, (t.shape, t.dtype, t.stride())
+
+
+def gemm(x, w, *, bias=None, act=ACT_NONE, out=None, epi=EPI_BF16):
+    """Normal orientation: out[M,N] = epi(x[M,K] @ w[N,K]^T + bias)."""
+    _chk2d(x, torch.bfloat16)
+    _chk2d(w, torch.bfloat16)
+    M, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        assert epi in (EPI_BF16, EPI_F32)
+        out = torch.empty(M, N, device=x.device, dtype=torch.bfloat16 if epi == EPI_BF16 else torch.float32)
+    lib = _lib.load()
+    rc = lib.mmd_gemm_bf16(_lib.context(x.device.index), epi, act, x.data_ptr(), 0, M, x.stride(0), w.data_ptr(), N,
+                           w.stride(0), K, _lib.ptr(bias), out.data_ptr(), out.stride(0), 1, 0, _lib.stream_ptr())
+    _lib.check(rc, "mmd_gemm_bf16")
+    return out
+
+
+def gemm_t_partials(x, w, k_splits, out=None):
+    """Swap-AB split-K: returns fp32 partial planes [splits, M, N] of x[M,K] @ w[N,K]^T."""
+    _chk2d(x, torch.bfloat16)
+    _chk2d(w, torch.bfloat16)
+    M, K = x.shape
+    N = w.shape[0]
+    lib = _lib.load()
+    splits = lib.mmd_gemm_splits(K, k_splits)
+    if out is None:
+        out = torch.empty(splits, M, N, device=x.device, dtype=torch.float32)
+    rc = lib.mmd_gemm_bf16(_lib.context(x.device.index), EPI_T_F32, ACT_NONE, w.data_ptr(), 0, N, w.stride(0),
+                           x.data_ptr(), M, x.stride(0), K, 0, out.data_ptr(), out.stride(1), k_splits, out.stride(0),
+                           _lib.stream_ptr())
+    _lib.check(rc, "mmd_gemm_bf16(T_F32)")
+    return out
+
+
+def gemm_t_swiglu(x, w_gate, w_up, out=None):
+    """Swap-AB fused SwiGLU: out[M,N] = silu(x @ w_gate^T) * (x @ w_up^T), bf16."""
+    _chk2d(x, torch.bfloat16)
+    _chk2d(w_gate, torch.bfloat16)
+    _chk2d(w_up, torch.bfloat16)
+    M, K = x.shape
+    N = w_gate.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=torch.bfloat16)
+    lib = _lib.load()
+    rc = lib.mmd_gemm_bf16(_lib.context(x.device.index), EPI_T_SWIGLU, ACT_NONE, w_gate.data_ptr(), w_up.data_ptr(), N,
+                           w_gate.stride(0), x.data_ptr(), M, x.stride(0), K, 0, out.data_ptr(), out.stride(0), 1, 0,
+                           _lib.stream_ptr())
+    _lib.check(rc, "mmd_gemm_bf16(T_SWIGLU)")
+    return out

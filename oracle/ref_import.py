@@ -1,0 +1,165 @@
+"""TEST INFRASTRUCTURE ONLY — imports the reference's OWN model class from /root/reference through three shims.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this package.
+This module works only where /root/reference exists (the authoring container); it is used to (1) validate the
+restatement in oracle/restate.py and (2) generate the golden vectors under tests/golden/ (oracle/make_golden.py).
+
+Shims (none of them touches the arithmetic of the reference files):
+  1. `peft`  — absent here; models/modeling_live.py:3 imports LoraConfig/get_peft_model/PeftModel at module import.
+  2. `llava.model.llava_arch.LlavaMetaModel` — LLaVA-NeXT is an unpinned git dependency (README.md:31-36) that is not
+     vendored.  The stub restates what its published code does for `llava-onevision-qwen2-7b-ov`:
+       * SigLipVisionTower: SigLIP-so400m/14@384 vision model with the LAST encoder layer deleted and head=Identity;
+         forward returns hidden_states[-1], i.e. the output of the 26th layer BEFORE post_layernorm
+         [recalled from llava/model/multimodal_encoder/siglip_encoder.py, unpinned];
+       * mm_projector 'mlp2x_gelu': Linear(1152,3584) -> nn.GELU() -> Linear(3584,3584)
+         [recalled from llava/model/multimodal_projector/builder.py, unpinned].
+  3. transformers 5.x guard: video_head_live_llava_qwen.py:73 sets `config.rope_scaling = None`, which on the
+     installed transformers 5.5 wipes `rope_parameters`; the guard ignores that one assignment.
+"""
+import importlib.machinery
+import os
+import sys
+import types
+
+import torch
+from torch import nn
+
+REFERENCE_ROOT = os.environ.get("MMDUET_REFERENCE", "/root/reference")
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "models"))
+
+
+class _SigLipTowerStub(nn.Module):
+    """Restates LLaVA-NeXT's SigLipVisionTower.forward for a batched tensor input."""
+
+    def __init__(self, vision_cfg):
+        super().__init__()
+        from transformers import SiglipVisionModel
+        self.vision_tower = SiglipVisionModel(vision_cfg)
+        del self.vision_tower.vision_model.encoder.layers[-1:]
+        self.vision_tower.vision_model.head = nn.Identity()
+        self.vision_tower.requires_grad_(False)
+        self.num_patches_per_side = vision_cfg.image_size // vision_cfg.patch_size
+        self.image_processor = None
+
+    def forward(self, images):
+        vm = self.vision_tower.vision_model
+        x = vm.embeddings(images.to(dtype=vm.embeddings.patch_embedding.weight.dtype))
+        out = vm.encoder(inputs_embeds=x)
+        return out.last_hidden_state.to(images.dtype)  # pre-post_layernorm, all patch tokens
+
+
+def _install_stubs():
+    if "peft" not in sys.modules:
+        peft = types.ModuleType("peft")
+        peft.__spec__ = importlib.machinery.ModuleSpec("peft", None)
+
+        class _Unavailable:
+            def __init__(self, *a, **k):
+                raise RuntimeError("peft is not installed; the oracle runs without LoRA")
+
+            @classmethod
+            def from_pretrained(cls, *a, **k):
+                raise RuntimeError("peft is not installed; the oracle runs without LoRA")
+
+        peft.LoraConfig = _Unavailable
+        peft.PeftModel = _Unavailable
+        peft.get_peft_model = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("peft is not installed"))
+        sys.modules["peft"] = peft
+
+    if "llava.model.llava_arch" not in sys.modules:
+        llava = types.ModuleType("llava")
+        llava.__path__ = []
+        llava_model = types.ModuleType("llava.model")
+        llava_model.__path__ = []
+        arch = types.ModuleType("llava.model.llava_arch")
+
+        class LlavaMetaModel:
+            def __init__(self, config):
+                super().__init__(config)
+                vcfg = getattr(config, "oracle_vision_config", None)
+                if vcfg is None:
+                    raise RuntimeError("config.oracle_vision_config (SiglipVisionConfig) must be set for the stub")
+                self.vision_tower = _SigLipTowerStub(vcfg)
+                self.mm_projector = nn.Sequential(
+                    nn.Linear(vcfg.hidden_size, config.hidden_size), nn.GELU(),
+                    nn.Linear(config.hidden_size, config.hidden_size))
+
+            def get_vision_tower(self):
+                return self.vision_tower
+
+        arch.LlavaMetaModel = LlavaMetaModel
+        sys.modules["llava"] = llava
+        sys.modules["llava.model"] = llava_model
+        sys.modules["llava.model.llava_arch"] = arch
+
+    if "models" not in sys.modules or not getattr(sys.modules["models"], "__oracle_shim__", False):
+        pkg = types.ModuleType("models")
+        pkg.__path__ = [os.path.join(REFERENCE_ROOT, "models")]
+        pkg.__oracle_shim__ = True
+        sys.modules["models"] = pkg
+        sub = types.ModuleType("models.live_llava")
+        sub.__path__ = [os.path.join(REFERENCE_ROOT, "models", "live_llava")]
+        sys.modules["models.live_llava"] = sub
+
+
+def import_reference():
+    """Returns the reference modules (vision_live, modeling_live, video_head_live_llava_qwen)."""
+    if not reference_available():
+        raise RuntimeError(f"{REFERENCE_ROOT} is not present (it never is on the GPU box)")
+    _install_stubs()
+    import importlib
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        vl = importlib.import_module("models.vision_live")
+        ml = importlib.import_module("models.modeling_live")
+        vh = importlib.import_module("models.live_llava.video_head_live_llava_qwen")
+    cfg_cls = vh.VideoHeadLiveLlavaQwenConfig
+    if not getattr(cfg_cls, "__oracle_rope_guard__", False):
+        orig_setattr = cfg_cls.__setattr__
+
+        def guarded(self, key, value):
+            if key == "rope_scaling" and value is None:
+                return  # shim 3
+            return orig_setattr(self, key, value)
+
+        cfg_cls.__setattr__ = guarded
+        cfg_cls.__oracle_rope_guard__ = True
+    return vl, ml, vh
+
+
+def build_reference_model(arch, state_dict=None, dtype=torch.float32, seed=1234):
+    """Instantiates the reference's VideoHeadLiveLlavaQwenForCausalLM (random init or from `state_dict`).
+
+    `arch` is an oracle.arch.Arch.  Returns the nn.Module in eval mode on CPU."""
+    from transformers import SiglipVisionConfig
+    _, _, vh = import_reference()
+    vcfg = SiglipVisionConfig(hidden_size=arch.vit_dim, intermediate_size=arch.vit_mlp,
+                              num_hidden_layers=arch.vit_layers_total, num_attention_heads=arch.vit_heads,
+                              image_size=arch.image_size, patch_size=arch.patch_size,
+                              hidden_act="gelu_pytorch_tanh", layer_norm_eps=1e-6)
+    cfg = vh.VideoHeadLiveLlavaQwenConfig(
+        hidden_size=arch.hidden, intermediate_size=arch.mlp, num_hidden_layers=arch.layers,
+        num_attention_heads=arch.q_heads, num_key_value_heads=arch.kv_heads, vocab_size=arch.vocab,
+        rms_norm_eps=arch.rms_eps, rope_theta=arch.rope_theta, max_position_embeddings=arch.max_pos,
+        tie_word_embeddings=False, attn_implementation="sdpa",
+        video_pooling_stride=arch.pool_stride, frame_num_tokens=arch.frame_tokens,
+        frame_resolution=arch.image_size)
+    cfg.mm_spatial_pool_mode = arch.pool_mode
+    cfg.oracle_vision_config = vcfg
+    torch.manual_seed(seed)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = vh.VideoHeadLiveLlavaQwenForCausalLM(cfg)
+    if state_dict is not None:
+        missing, unexpected = model.load_state_dict(state_dict, strict=False)
+        missing = [m for m in missing if "post_layernorm" not in m and "position_ids" not in m]
+        if missing or unexpected:
+            raise RuntimeError(f"state_dict mismatch: missing={missing[:5]} unexpected={unexpected[:5]}")
+    model = model.to(dtype).eval()
+    model.requires_grad_(False)
+    return model
