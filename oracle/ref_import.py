@@ -157,7 +157,9 @@ def build_reference_model(arch, state_dict=None, dtype=torch.float32, seed=1234)
         model = vh.VideoHeadLiveLlavaQwenForCausalLM(cfg)
     if state_dict is not None:
         missing, unexpected = model.load_state_dict(state_dict, strict=False)
-        missing = [m for m in missing if "post_layernorm" not in m and "position_ids" not in m]
+        # `vision_encoder.*` aliases `model.vision_tower.*` (video_head_live_llava_qwen.py:82: same module, second name)
+        missing = [m for m in missing if "post_layernorm" not in m and "position_ids" not in m
+                   and not m.startswith("vision_encoder.")]
         if missing or unexpected:
             raise RuntimeError(f"state_dict mismatch: missing={missing[:5]} unexpected={unexpected[:5]}")
     model = model.to(dtype).eval()
