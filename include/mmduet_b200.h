@@ -2,11 +2,14 @@
  *
  * The reference (yellow-binary-tree/MMDuet) is pure Python and has no FFI; its boundary is the Python surface in
  * models/vision_live.py, models/modeling_live.py, models/live_llava/video_head_live_llava_qwen.py and
- * test/inference.py.  The functions below are what a ctypes binding underneath that surface calls; each one names
- * the reference call site whose arithmetic it replaces.  Conventions: every pointer is a caller-owned CUDA device
- * pointer unless stated otherwise, sizes/strides are int64_t in ELEMENTS, `stream` is a cudaStream_t passed as
- * void*, calls are asynchronous with respect to the host, and the return value is 0 on success or a negative
- * MMD_ERR_* code with a thread-local message available from mmd_last_error().  There is no CPU fallback.
+ * test/inference.py.  The functions below are what a ctypes binding underneath that surface calls (see
+ * INTEGRATION.md); each one names the reference call site whose arithmetic it replaces.
+ *
+ * Conventions: every pointer is a caller-owned CUDA DEVICE pointer unless marked "host"; sizes/strides are in
+ * ELEMENTS; `stream` is a cudaStream_t passed as void*; calls are asynchronous with respect to the host, allocate
+ * nothing on the device (the caller provides workspaces sized by the *_workspace_bytes functions) and never
+ * synchronise; the return value is 0 or a negative MMD_ERR_* code with a thread-local message available from
+ * mmd_last_error().  There is no CPU fallback: mmd_create fails on anything that is not an sm_100 device.
  */
 #ifndef MMDUET_B200_H_
 #define MMDUET_B200_H_
@@ -23,36 +26,182 @@ extern "C" {
 
 #define MMD_OK 0
 #define MMD_ERR_ARG (-2)
+#define MMD_ERR_WORKSPACE (-3)
 #define MMD_ERR_CUDA (-5)
+
+#define MMD_DT_U8 0
+#define MMD_DT_BF16 1
+#define MMD_DT_F32 2
+
+#define MMD_PAGE_TOKENS 64 /* tokens per KV page */
 
 typedef struct mmd_ctx mmd_ctx;
 
 MMD_API const char* mmd_version(void);
 MMD_API const char* mmd_last_error(void);
-/* One context per device/process; fails (NULL) on anything that is not sm_100. */
 MMD_API mmd_ctx* mmd_create(int device);
 MMD_API void mmd_destroy(mmd_ctx*);
+MMD_API int mmd_num_sms(mmd_ctx*);
 
-/* epilogue / activation selectors of mmd_gemm_bf16 */
-#define MMD_EPI_BF16 0
-#define MMD_EPI_RESID_F32 1
-#define MMD_EPI_T_F32 2
-#define MMD_EPI_T_SWIGLU 3
-#define MMD_EPI_F32 4
+/* ---------------------------------------------------------------------------------------------------------------
+ * GEMM (tcgen05.mma, TMA operands, TMEM accumulators) — every nn.Linear on the path.
+ * D[i, j] = sum_k X[i, k] * Y[j, k], bf16 operands (both K-major), fp32 accumulation.
+ * Normal epilogues: X = activations [M,K], Y = weights [N,K], out[M,N].  T epilogues (swap-AB for small M): X (and
+ * X2) = weights [N,K], Y = activations [M,K], out[M,N]; MMD_EPI_T_F32 writes split-K fp32 planes `split_stride`
+ * elements apart (mmd_gemm_splits gives the effective plane count for a requested split).
+ * Replaces cuBLAS under: SigLIP q/k/v/out/fc1/fc2 + patch-embed Conv2d (video_head_live_llava_qwen.py:96-98),
+ * mm_projector (:90-91), Qwen2 q/k/v/o/gate/up/down + lm_head (:141-155).
+ * ------------------------------------------------------------------------------------------------------------- */
+#define MMD_EPI_BF16 0      /* out_bf16 = act(acc + bias[n])                       */
+#define MMD_EPI_RESID_F32 1 /* out_f32 += acc + bias[n]      (fp32 residual stream) */
+#define MMD_EPI_T_F32 2     /* out_f32[split][m][n] = acc                          */
+#define MMD_EPI_T_SWIGLU 3  /* out_bf16[m][n] = silu(acc_gate) * acc_up            */
+#define MMD_EPI_F32 4       /* out_f32 = acc + bias[n]                             */
 #define MMD_ACT_NONE 0
 #define MMD_ACT_GELU_TANH 1
 #define MMD_ACT_GELU_ERF 2
-
-/* D[i, j] = sum_k X[i, k] * Y[j, k], bf16 operands (both K-major), fp32 accumulation in TMEM (tcgen05.mma).
- * Replaces every nn.Linear on the path (cuBLAS in the reference): SigLIP q/k/v/out/fc1/fc2 and the patch-embed
- * Conv2d as a GEMM (video_head_live_llava_qwen.py:96-98), mm_projector (:90-91) and the Qwen2 projections
- * (:141-150).  Normal epilogues: X = activations [M,K], Y = weights [N,K], out[M,N].  T epilogues (swap-AB for small
- * M): X (and X2) = weights [N,K], Y = activations [M,K], out[M,N]; MMD_EPI_T_F32 writes `k_splits` fp32 partial
- * planes `split_stride` elements apart (see mmd_gemm_splits for the effective plane count). */
 MMD_API int mmd_gemm_bf16(mmd_ctx*, int epi, int act, const void* X, const void* X2, int64_t x_rows, int64_t ldx,
-                  const void* Y, int64_t y_rows, int64_t ldy, int64_t K, const float* bias, void* out, int64_t ldo,
-                  int k_splits, int64_t split_stride, void* stream);
+                          const void* Y, int64_t y_rows, int64_t ldy, int64_t K, const float* bias, void* out,
+                          int64_t ldo, int k_splits, int64_t split_stride, void* stream);
 MMD_API int mmd_gemm_splits(int64_t K, int k_splits);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Building-block kernels (exported so that tests can check each against the oracle).
+ * ------------------------------------------------------------------------------------------------------------- */
+/* Patch im2col (+ optional (x/255-0.5)/0.5): pixels [T,3,img,img] (u8/bf16/f32) -> A bf16 [T*G*G, k_pad].
+ * SiglipVisionEmbeddings Conv2d (TF:models/siglip/modeling_siglip.py:124-130); models/vision_live.py:13. */
+MMD_API int mmd_im2col(const void* pixels, int px_dtype, int normalize, void* A, int T, int img, int patch, int k_pad,
+                       void* stream);
+/* LayerNorm over fp32 rows -> bf16 (or fp32) rows; SiglipEncoderLayer layer_norm1/2, post_layernorm. */
+MMD_API int mmd_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_f32, int64_t rows,
+                          int D, float eps, void* stream);
+/* Fused SigLIP attention on packed qkv bf16 [T*S, 3*H*dh] -> out bf16 [T*S, H*dh]
+ * (TF:models/siglip/modeling_siglip.py:252-330). */
+MMD_API int mmd_vit_attention(const void* qkv, void* out, int T, int S, int H, int dh, void* stream);
+/* resid += sum of split-K planes; out = RMSNorm(resid) * w (bf16 and/or fp32) — Qwen2DecoderLayer residual adds and
+ * Qwen2RMSNorm (TF:models/qwen2/modeling_qwen2.py:249-310).  w == NULL: reduction only. */
+MMD_API int mmd_resid_add_rmsnorm(float* resid, const float* partial, int n_planes, int64_t plane_stride, const float* w,
+                                  void* out_bf16, float* out_f32, int64_t rows, int H, float eps, void* stream);
+/* q/k/v bias + RoPE + KV append into the paged pool (TF:models/qwen2/modeling_qwen2.py:127-146,215-233;
+ * TF:cache_utils.py:119-120). */
+MMD_API int mmd_qkv_finish(const float* partial, int n_planes, int64_t plane_stride, const float* bias,
+                           const float* rope_cos, const float* rope_sin, const int* tok_pos, const int* tok_slot,
+                           void* q_out, void* kv_layer, int M, int Hq, int Hkv, int dh, void* stream);
+/* Chunked-prefill attention over the paged KV pool (see mmd_step for stream_desc / block_tables).
+ * o_part: fp32 [n_splits, total_q*Hq, dh]; ml_part: fp32 [n_splits, total_q*Hq, 2]; out bf16 [total_q, Hq*dh]. */
+MMD_API int mmd_kv_attention(mmd_ctx*, const void* q, const void* kv_layer, const int* stream_desc, const int* block_tables,
+                             int n_streams, int max_n_q, int total_q, int max_kv_len, float* o_part, float* ml_part,
+                             void* out, int Hq, int Hkv, int dh, int n_splits /* 0 = auto */, void* stream);
+MMD_API int mmd_kv_attention_splits(mmd_ctx*, int max_n_q, int Hq, int Hkv, int n_streams, int max_kv_len);
+/* Tap pooling (bilinear / average weights or max) — video_head_live_llava_qwen.py:100-119, vision_live.py:19-25. */
+MMD_API int mmd_tap_pool(const void* in, int in_dtype, void* out, int out_dtype, const int* tap_idx, const float* tap_w,
+                         int T, int n_in, int n_out, int max_taps, int D, int maxpool, void* stream);
+/* informative/relevance heads + sigmoid score on selected rows (video_head_live_llava_qwen.py:160-161;
+ * test/inference.py:243-244).  head_w fp32 [4,H] = {inf0, inf1, rel0, rel1}. */
+MMD_API int mmd_heads(const float* hidden_f32, const int* rows, const float* head_w, float* logits_out, float* scores_out,
+                      int n_rows, int H, void* stream);
+/* Greedy token pick with the HF repetition penalty (models/modeling_live.py:51-77). */
+MMD_API int mmd_argmax(const float* logits, int64_t V, const int64_t* penal_ids, int n_penal, float penalty,
+                       int64_t* out_id, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * SigLIP tower (a1/a2): patch embed -> n_layers x {LN, QKV, attention, out-proj, LN, fc1+GELU(tanh), fc2} with an fp32
+ * residual stream.  Output: the fp32 residual [T*S, dim] BEFORE post_layernorm (llava path,
+ * video_head_live_llava_qwen.py:96-98); the legacy entry (models/vision_live.py:11-31) applies post_ln + pooling on top.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* ln1_w; const float* ln1_b;
+  const void* qkv_w;  const float* qkv_b;   /* bf16 [3*dim, dim] (q;k;v stacked), fp32 [3*dim] */
+  const void* out_w;  const float* out_b;   /* bf16 [dim, dim] */
+  const float* ln2_w; const float* ln2_b;
+  const void* fc1_w;  const float* fc1_b;   /* bf16 [mlp, dim] */
+  const void* fc2_w;  const float* fc2_b;   /* bf16 [dim, mlp] */
+} mmd_vit_layer;
+
+typedef struct {
+  int image_size, patch_size, dim, heads, mlp, n_layers, k_pad;
+  const void* patch_w;              /* bf16 [dim, k_pad]: Conv2d weight flattened (c, py, px), zero padded */
+  const float* patch_b;             /* fp32 [dim] */
+  const float* pos_emb;             /* fp32 [S, dim] */
+  const mmd_vit_layer* layers;      /* HOST array of n_layers entries */
+} mmd_vit_weights;
+
+MMD_API int64_t mmd_vit_workspace_bytes(const mmd_vit_weights*, int T);
+MMD_API int mmd_vit_forward(mmd_ctx*, const mmd_vit_weights*, const void* pixels, int px_dtype, int normalize, int T,
+                            float* resid_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * mm_projector + GELU + spatial pooling (a2): gathers the source tokens the pooling reads (169 of 729 for the
+ * bilinear 27->7 resize), Linear1 + erf-GELU, Linear2 with an fp32 epilogue, then the tap pooling (bilinear / average
+ * weights or max) in fp32 and a single rounding to bf16.
+ * video_head_live_llava_qwen.py:90-91 (connector), :100-119 (post_projector_pooling).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int vit_dim, hidden, n_src_tokens /* S */, n_gather, n_out, max_taps, maxpool;
+  const void* w1; const float* b1;   /* bf16 [hidden, vit_dim] */
+  const void* w2; const float* b2;   /* bf16 [hidden, hidden]  */
+  const int* gather_idx;             /* int32 [n_gather]: source token of each gathered row */
+  const int* tap_idx;                /* int32 [n_out, max_taps]: index INTO THE GATHERED set, -1 = end */
+  const float* tap_w;                /* fp32 [n_out, max_taps] */
+} mmd_projector_weights;
+
+MMD_API int64_t mmd_projector_workspace_bytes(const mmd_projector_weights*, int T);
+MMD_API int mmd_projector_pool(mmd_ctx*, const mmd_projector_weights*, const float* vit_resid, int T, void* out_bf16,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Decoder step (a4/a5/a7): embed/concat -> n_layers x {RMSNorm, QKV(+bias,RoPE,KV append), KV-append attention, o_proj,
+ * RMSNorm, SwiGLU MLP} -> final RMSNorm -> informative/relevance heads (+ lm_head on requested rows only).
+ * VideoHeadLiveLlavaQwenForCausalLM.forward (video_head_live_llava_qwen.py:121-205) as driven by
+ * LiveInferForBenchmark._encode_frame/_encode_query (test/inference.py:221-255).  Several streams (videos) and several
+ * frames per stream can share one step (varlen), weights are read once per step.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* ln1_w;                /* input_layernorm fp32 [H] */
+  const void* qkv_w; const float* qkv_b; /* bf16 [(Hq+2Hkv)*dh, H] (q;k;v stacked), fp32 */
+  const void* o_w;                   /* bf16 [H, Hq*dh] */
+  const float* ln2_w;                /* post_attention_layernorm */
+  const void* gate_w; const void* up_w;  /* bf16 [mlp, H] */
+  const void* down_w;                /* bf16 [H, mlp] */
+} mmd_dec_layer;
+
+typedef struct {
+  int hidden, n_layers, q_heads, kv_heads, head_dim, mlp, vocab, max_pos;
+  float rms_eps;
+  const mmd_dec_layer* layers;       /* HOST array */
+  const float* final_norm_w;         /* fp32 [H] */
+  const void* embed;                 /* bf16 [vocab, H] */
+  const void* lm_head;               /* bf16 [vocab, H] (may be NULL when no lm rows are ever requested) */
+  const float* heads_w;              /* fp32 [4, H] */
+  const float* rope_cos; const float* rope_sin; /* fp32 [max_pos, dh/2] */
+} mmd_dec_weights;
+
+typedef struct {
+  void* pool;                        /* bf16 [n_layers][n_pages][2][kv_heads][MMD_PAGE_TOKENS][head_dim] */
+  int64_t layer_stride;              /* elements between layers */
+  int n_pages;
+} mmd_kv_pool;
+
+typedef struct {
+  int n_tokens;                      /* rows of this step (all streams packed) */
+  const int* src_row;                /* int32 [n_tokens]: >= 0 embedding id; < 0 row -(v+1) of frame_tokens */
+  const void* frame_tokens;          /* bf16 [*, H] (output of mmd_projector_pool) */
+  const int* tok_pos;                /* int32 [n_tokens] RoPE position */
+  const int* tok_slot;               /* int32 [n_tokens] physical KV slot = page*MMD_PAGE_TOKENS + offset */
+  int n_streams;
+  const int* stream_desc;            /* int32 [n_streams,4] {q_start, n_q, kv_len(after append), table_off} */
+  const int* block_tables;           /* int32 page ids */
+  int max_n_q, max_kv_len;           /* host copies of the maxima over streams (grid sizing) */
+  int n_score_rows; const int* score_rows;   /* rows at which the heads are evaluated */
+  float* head_logits_out;            /* fp32 [n_score_rows,4] */
+  float* scores_out;                 /* fp32 [n_score_rows,2] {informative_score, relevance_score} */
+  int n_lm_rows; const int* lm_rows; /* rows that need lm_head (query / generation steps), 0 on frame steps */
+  float* lm_logits_out;              /* fp32 [n_lm_rows, vocab] */
+} mmd_step;
+
+MMD_API int64_t mmd_decoder_workspace_bytes(mmd_ctx*, const mmd_dec_weights*, int max_tokens, int max_lm_rows);
+MMD_API int mmd_decoder_step(mmd_ctx*, const mmd_dec_weights*, const mmd_kv_pool*, const mmd_step*, void* workspace,
+                             int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

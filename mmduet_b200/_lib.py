@@ -21,6 +21,50 @@ _lib = None
 _lock = threading.Lock()
 _ctx = {}
 
+PAGE_TOKENS = 64
+DT_U8, DT_BF16, DT_F32 = 0, 1, 2
+c_float_p = ctypes.c_void_p  # device pointers travel as integers
+
+
+class VitLayer(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "out_w", "out_b", "ln2_w", "ln2_b",
+                                        "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+class VitWeights(ctypes.Structure):
+    _fields_ = [(n, c_int) for n in ("image_size", "patch_size", "dim", "heads", "mlp", "n_layers", "k_pad")] + \
+               [("patch_w", c_void_p), ("patch_b", c_void_p), ("pos_emb", c_void_p), ("layers", ctypes.POINTER(VitLayer))]
+
+
+class ProjectorWeights(ctypes.Structure):
+    _fields_ = [(n, c_int) for n in ("vit_dim", "hidden", "n_src_tokens", "n_gather", "n_out", "max_taps", "maxpool")] + \
+               [(n, c_void_p) for n in ("w1", "b1", "w2", "b2", "gather_idx", "tap_idx", "tap_w")]
+
+
+class DecLayer(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("ln1_w", "qkv_w", "qkv_b", "o_w", "ln2_w", "gate_w", "up_w", "down_w")]
+
+
+class DecWeights(ctypes.Structure):
+    _fields_ = [(n, c_int) for n in ("hidden", "n_layers", "q_heads", "kv_heads", "head_dim", "mlp", "vocab", "max_pos")] + \
+               [("rms_eps", c_float), ("layers", ctypes.POINTER(DecLayer))] + \
+               [(n, c_void_p) for n in ("final_norm_w", "embed", "lm_head", "heads_w", "rope_cos", "rope_sin")]
+
+
+class KvPool(ctypes.Structure):
+    _fields_ = [("pool", c_void_p), ("layer_stride", c_int64), ("n_pages", c_int)]
+
+
+class Step(ctypes.Structure):
+    _fields_ = [("n_tokens", c_int), ("src_row", c_void_p), ("frame_tokens", c_void_p), ("tok_pos", c_void_p),
+                ("tok_slot", c_void_p), ("n_streams", c_int), ("stream_desc", c_void_p), ("block_tables", c_void_p),
+                ("max_n_q", c_int), ("max_kv_len", c_int), ("n_score_rows", c_int), ("score_rows", c_void_p),
+                ("head_logits_out", c_void_p), ("scores_out", c_void_p), ("n_lm_rows", c_int), ("lm_rows", c_void_p),
+                ("lm_logits_out", c_void_p)]
+
+
+P = ctypes.POINTER
+
 # name -> (restype, argtypes); every symbol include/mmduet_b200.h declares must be listed here
 SIGNATURES = {
     "mmd_version": (ctypes.c_char_p, []),
@@ -30,6 +74,28 @@ SIGNATURES = {
     "mmd_gemm_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64,
                               c_int64, c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p]),
     "mmd_gemm_splits": (c_int, [c_int64, c_int]),
+    "mmd_num_sms": (c_int, [c_void_p]),
+    "mmd_im2col": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mmd_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_float, c_void_p]),
+    "mmd_vit_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mmd_resid_add_rmsnorm": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                      c_float, c_void_p]),
+    "mmd_qkv_finish": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mmd_kv_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mmd_kv_attention_splits": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int]),
+    "mmd_tap_pool": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                             c_int, c_void_p]),
+    "mmd_heads": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mmd_argmax": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    "mmd_vit_workspace_bytes": (c_int64, [P(VitWeights), c_int]),
+    "mmd_vit_forward": (c_int, [c_void_p, P(VitWeights), c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int64,
+                                c_void_p]),
+    "mmd_projector_workspace_bytes": (c_int64, [P(ProjectorWeights), c_int]),
+    "mmd_projector_pool": (c_int, [c_void_p, P(ProjectorWeights), c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mmd_decoder_workspace_bytes": (c_int64, [c_void_p, P(DecWeights), c_int, c_int]),
+    "mmd_decoder_step": (c_int, [c_void_p, P(DecWeights), P(KvPool), P(Step), c_void_p, c_int64, c_void_p]),
 }
 
 

@@ -1,18 +1,91 @@
-// C-ABI of libmmduet_b200.so (declared in include/mmduet_b200.h).
+// C-ABI of libmmduet_b200.so (declared in include/mmduet_b200.h): argument checking, workspace carving and the launch
+// sequences of the SigLIP tower, the projector/pool stage and the decoder step.
 #include "../../include/mmduet_b200.h"
 #include "gemm.cuh"
+#include "kernels.cuh"
 
 #include <string>
 
 namespace {
 thread_local std::string g_err;
-void set_err(const std::string& s) { g_err = s; }
+int fail(int code, const std::string& s) { g_err = s; return code; }
+
+struct Bump {  // 256-B aligned bump allocator over the caller's workspace
+  uint8_t* base; int64_t cap; int64_t off = 0; bool ok = true;
+  Bump(void* b, int64_t c) : base(static_cast<uint8_t*>(b)), cap(c) {}
+  template <typename T> T* take(int64_t n_elems) {
+    const int64_t bytes = (n_elems * (int64_t)sizeof(T) + 255) & ~int64_t(255);
+    if (base != nullptr && off + bytes > cap) ok = false;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 }  // namespace
 
 struct mmd_ctx {
   int device;
+  int num_sms;
   mmd::GemmContext* gemm;
 };
+
+#define CHECK_CTX(c) do { if ((c) == nullptr) return fail(MMD_ERR_ARG, "null context"); } while (0)
+#define RUN(expr, what) do { int rc_ = (expr); if (rc_ != 0) return fail(rc_, std::string(what) + ": " + mmd::gemm_last_error()); } while (0)
+#define RUNK(expr, what) do { int rc_ = (expr); if (rc_ != 0) return fail(rc_, std::string(what) + ": bad arguments"); } while (0)
+
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MMD_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return 0;
+}
+
+// split-K choice for the swap-AB (weight-streaming) GEMMs: fill the SMs, few waves, not too many partial planes
+static int choose_splits(int num_sms, int N, int K, int M) {
+  const int bn = M <= 64 ? 64 : (M <= 128 ? 128 : 256);
+  const int tiles = ((N + 127) / 128) * ((M + bn - 1) / bn);
+  const int kb = (K + 63) / 64;
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= 8 && s <= kb; ++s) {
+    const int eff = mmd::gemm_effective_splits(K, s);
+    if (eff != s) continue;
+    const int per = (kb + s - 1) / s;
+    const long long units = (long long)tiles * s;
+    const long long waves = (units + num_sms - 1) / num_sms;
+    const double cost = (double)waves * (per + 6.0) + 0.5 * s;  // 6 k-blocks of fixed per-tile overhead, plane traffic
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  return best;
+}
+
+static int gemm_T_partials(mmd_ctx* c, const void* act, int M, const void* w, int N, int K, int splits, float* planes,
+                           cudaStream_t s, int* eff_out) {
+  mmd::GemmArgs a;
+  a.X = static_cast<const __nv_bfloat16*>(w); a.x_rows = N; a.ldx = K;
+  a.Y = static_cast<const __nv_bfloat16*>(act); a.y_rows = M; a.ldy = K;
+  a.K = K; a.epi = mmd::EPI_T_F32; a.out = planes; a.ldo = N; a.k_splits = splits; a.split_stride = (int64_t)M * N;
+  *eff_out = mmd::gemm_effective_splits(K, splits);
+  return mmd::gemm_launch(c->gemm, a, s);
+}
+
+static int gemm_normal(mmd_ctx* c, const void* act, int M, const void* w, int N, int K, int64_t lda, int epi, int actfn,
+                       const float* bias, void* out, int64_t ldo, cudaStream_t s) {
+  mmd::GemmArgs a;
+  a.X = static_cast<const __nv_bfloat16*>(act); a.x_rows = M; a.ldx = lda;
+  a.Y = static_cast<const __nv_bfloat16*>(w); a.y_rows = N; a.ldy = K;
+  a.K = K; a.epi = epi; a.act = actfn; a.bias = bias; a.out = out; a.ldo = ldo;
+  return mmd::gemm_launch(c->gemm, a, s);
+}
+
+__global__ void gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict__ rows,
+                                        __nv_bfloat16* __restrict__ dst, int H8) {
+  const uint4* s = reinterpret_cast<const uint4*>(src + (long long)rows[blockIdx.x] * H8 * 8);
+  uint4* d = reinterpret_cast<uint4*>(dst + (long long)blockIdx.x * H8 * 8);
+  for (int c = threadIdx.x; c < H8; c += blockDim.x) d[c] = s[c];
+}
 
 extern "C" {
 
@@ -20,17 +93,18 @@ const char* mmd_version(void) { return "mmduet_b200 0.1 (sm_100a)"; }
 const char* mmd_last_error(void) { return g_err.c_str(); }
 
 mmd_ctx* mmd_create(int device) {
-  if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice failed"); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { g_err = "cudaSetDevice failed"; return nullptr; }
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { set_err("cudaGetDeviceProperties failed"); return nullptr; }
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { g_err = "cudaGetDeviceProperties failed"; return nullptr; }
   if (prop.major != 10) {
-    set_err("mmduet_b200 needs an sm_100a (B200) device; found sm_" + std::to_string(prop.major * 10 + prop.minor));
+    g_err = "mmduet_b200 needs an sm_100a (B200) device; found sm_" + std::to_string(prop.major * 10 + prop.minor);
     return nullptr;
   }
   mmd::GemmContext* g = mmd::gemm_context_create(device);
-  if (g == nullptr) { set_err(mmd::gemm_last_error()); return nullptr; }
+  if (g == nullptr) { g_err = mmd::gemm_last_error(); return nullptr; }
   mmd_ctx* c = new mmd_ctx();
   c->device = device;
+  c->num_sms = prop.multiProcessorCount;
   c->gemm = g;
   return c;
 }
@@ -41,10 +115,12 @@ void mmd_destroy(mmd_ctx* c) {
   delete c;
 }
 
+int mmd_num_sms(mmd_ctx* c) { return c ? c->num_sms : 0; }
+
 int mmd_gemm_bf16(mmd_ctx* c, int epi, int act, const void* X, const void* X2, int64_t x_rows, int64_t ldx,
                   const void* Y, int64_t y_rows, int64_t ldy, int64_t K, const float* bias, void* out, int64_t ldo,
                   int k_splits, int64_t split_stride, void* stream) {
-  if (c == nullptr) { set_err("null context"); return MMD_ERR_ARG; }
+  CHECK_CTX(c);
   mmd::GemmArgs a;
   a.X = static_cast<const __nv_bfloat16*>(X);
   a.X2 = static_cast<const __nv_bfloat16*>(X2);
@@ -52,11 +128,277 @@ int mmd_gemm_bf16(mmd_ctx* c, int epi, int act, const void* X, const void* X2, i
   a.x_rows = (int)x_rows; a.y_rows = (int)y_rows; a.K = (int)K;
   a.ldx = ldx; a.ldy = ldy; a.epi = epi; a.act = act; a.bias = bias; a.out = out; a.ldo = ldo;
   a.k_splits = k_splits; a.split_stride = split_stride;
-  int rc = mmd::gemm_launch(c->gemm, a, static_cast<cudaStream_t>(stream));
-  if (rc != 0) set_err(mmd::gemm_last_error());
-  return rc;
+  RUN(mmd::gemm_launch(c->gemm, a, S(stream)), "mmd_gemm_bf16");
+  return 0;
 }
 
 int mmd_gemm_splits(int64_t K, int k_splits) { return mmd::gemm_effective_splits((int)K, k_splits); }
+
+int mmd_im2col(const void* pixels, int px_dtype, int normalize, void* A, int T, int img, int patch, int k_pad, void* stream) {
+  if (pixels == nullptr || A == nullptr || T < 0 || patch <= 0 || img < patch || k_pad < 3 * patch * patch)
+    return fail(MMD_ERR_ARG, "mmd_im2col: bad arguments");
+  if (T == 0) return 0;
+  RUNK(mmd::launch_im2col(pixels, px_dtype, normalize, static_cast<__nv_bfloat16*>(A), T, 3, img, patch, k_pad, S(stream)), "mmd_im2col");
+  return check_launch("mmd_im2col");
+}
+
+int mmd_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_f32, int64_t rows, int D, float eps,
+                  void* stream) {
+  if (rows == 0) return 0;
+  RUNK(mmd::launch_layernorm(x, gamma, beta, out, out_f32, rows, D, eps, S(stream)), "mmd_layernorm");
+  return check_launch("mmd_layernorm");
+}
+
+int mmd_vit_attention(const void* qkv, void* out, int T, int S_, int H, int dh, void* stream) {
+  RUNK(mmd::launch_vit_attention(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), T, S_, H, dh, S(stream)),
+       "mmd_vit_attention (head_dim must be 72)");
+  return check_launch("mmd_vit_attention");
+}
+
+int mmd_resid_add_rmsnorm(float* resid, const float* partial, int n_planes, int64_t plane_stride, const float* w, void* out_bf16,
+                          float* out_f32, int64_t rows, int H, float eps, void* stream) {
+  RUNK(mmd::launch_resid_add_rmsnorm(resid, partial, n_planes, plane_stride, w, static_cast<__nv_bfloat16*>(out_bf16), out_f32,
+                                     rows, H, eps, S(stream)), "mmd_resid_add_rmsnorm");
+  return check_launch("mmd_resid_add_rmsnorm");
+}
+
+int mmd_qkv_finish(const float* partial, int n_planes, int64_t plane_stride, const float* bias, const float* rope_cos,
+                   const float* rope_sin, const int* tok_pos, const int* tok_slot, void* q_out, void* kv_layer, int M, int Hq,
+                   int Hkv, int dh, void* stream) {
+  RUNK(mmd::launch_qkv_finish(partial, n_planes, plane_stride, bias, rope_cos, rope_sin, tok_pos, tok_slot,
+                              static_cast<__nv_bfloat16*>(q_out), static_cast<__nv_bfloat16*>(kv_layer), M, Hq, Hkv, dh,
+                              MMD_PAGE_TOKENS, S(stream)), "mmd_qkv_finish");
+  return check_launch("mmd_qkv_finish");
+}
+
+int mmd_kv_attention_splits(mmd_ctx* c, int max_n_q, int Hq, int Hkv, int n_streams, int max_kv_len) {
+  if (c == nullptr || Hkv <= 0) return 1;
+  return mmd::kv_attention_pick_splits(max_n_q * (Hq / Hkv), Hkv, n_streams, max_kv_len, c->num_sms);
+}
+
+int mmd_kv_attention(mmd_ctx* c, const void* q, const void* kv_layer, const int* stream_desc, const int* block_tables,
+                     int n_streams, int max_n_q, int total_q, int max_kv_len, float* o_part, float* ml_part, void* out, int Hq,
+                     int Hkv, int dh, int n_splits, void* stream) {
+  CHECK_CTX(c);
+  if (n_splits <= 0) n_splits = mmd_kv_attention_splits(c, max_n_q, Hq, Hkv, n_streams, max_kv_len);
+  RUNK(mmd::launch_kv_attention(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(kv_layer), stream_desc,
+                                block_tables, n_streams, max_n_q, total_q, o_part, ml_part, static_cast<__nv_bfloat16*>(out),
+                                Hq, Hkv, dh, MMD_PAGE_TOKENS, n_splits, S(stream)), "mmd_kv_attention (head_dim must be 128)");
+  return check_launch("mmd_kv_attention");
+}
+
+int mmd_tap_pool(const void* in, int in_dtype, void* out, int out_dtype, const int* tap_idx, const float* tap_w, int T, int n_in,
+                 int n_out, int max_taps, int D, int maxpool, void* stream) {
+  RUNK(mmd::launch_tap_pool(in, in_dtype, out, out_dtype, tap_idx, tap_w, T, n_in, n_out, max_taps, D, maxpool, S(stream)), "mmd_tap_pool");
+  return check_launch("mmd_tap_pool");
+}
+
+int mmd_heads(const float* hidden_f32, const int* rows, const float* head_w, float* logits_out, float* scores_out, int n_rows,
+              int H, void* stream) {
+  RUNK(mmd::launch_heads(hidden_f32, rows, head_w, logits_out, scores_out, n_rows, H, S(stream)), "mmd_heads");
+  return check_launch("mmd_heads");
+}
+
+int mmd_argmax(const float* logits, int64_t V, const int64_t* penal_ids, int n_penal, float penalty, int64_t* out_id, void* stream) {
+  RUNK(mmd::launch_argmax(logits, 1, 0, (int)V, reinterpret_cast<const long long*>(penal_ids), n_penal, penalty,
+                          reinterpret_cast<long long*>(out_id), nullptr, S(stream)), "mmd_argmax");
+  return check_launch("mmd_argmax");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SigLIP tower
+// ---------------------------------------------------------------------------------------------------------------
+struct VitBufs { __nv_bfloat16 *x, *qkv, *h; };
+static int64_t vit_carve(const mmd_vit_weights* w, int T, Bump& b, VitBufs* o) {
+  const int G = w->image_size / w->patch_size;
+  const int64_t M = (int64_t)T * G * G;
+  const int wide = w->mlp > w->k_pad ? w->mlp : w->k_pad;
+  o->x = b.take<__nv_bfloat16>(M * w->dim);
+  o->qkv = b.take<__nv_bfloat16>(M * 3 * w->dim);
+  o->h = b.take<__nv_bfloat16>(M * wide);  // fc1 output; also holds the im2col matrix
+  return b.off;
+}
+
+int64_t mmd_vit_workspace_bytes(const mmd_vit_weights* w, int T) {
+  if (w == nullptr || T <= 0) return 0;
+  Bump b(nullptr, 0);
+  VitBufs o;
+  return vit_carve(w, T, b, &o);
+}
+
+int mmd_vit_forward(mmd_ctx* c, const mmd_vit_weights* w, const void* pixels, int px_dtype, int normalize, int T,
+                    float* resid_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  CHECK_CTX(c);
+  if (w == nullptr || pixels == nullptr || resid_out == nullptr || workspace == nullptr || T < 0)
+    return fail(MMD_ERR_ARG, "mmd_vit_forward: null argument");
+  if (T == 0) return 0;
+  if (w->dim % w->heads != 0 || w->dim % 8 != 0 || w->mlp % 8 != 0 || w->k_pad % 8 != 0 || w->k_pad < 3 * w->patch_size * w->patch_size)
+    return fail(MMD_ERR_ARG, "mmd_vit_forward: unsupported architecture (dims must be multiples of 8)");
+  Bump b(workspace, workspace_bytes);
+  VitBufs buf;
+  vit_carve(w, T, b, &buf);
+  if (!b.ok) return fail(MMD_ERR_WORKSPACE, "mmd_vit_forward: workspace too small");
+  cudaStream_t s = S(stream);
+  const int G = w->image_size / w->patch_size, Sg = G * G;
+  const int M = T * Sg, D = w->dim;
+  const float eps = 1e-6f;
+  // embeddings: resid = pos_emb (broadcast) ; resid += im2col(pixels) @ patch_w^T + patch_b
+  RUNK(mmd::launch_im2col(pixels, px_dtype, normalize, buf.h, T, 3, w->image_size, w->patch_size, w->k_pad, s), "im2col");
+  RUNK(mmd::launch_broadcast_rows(w->pos_emb, resid_out, M, Sg, D, s), "pos_emb");
+  RUN(gemm_normal(c, buf.h, M, w->patch_w, D, w->k_pad, w->k_pad, mmd::EPI_RESID_F32, 0, w->patch_b, resid_out, D, s), "patch_embed");
+  for (int l = 0; l < w->n_layers; ++l) {
+    const mmd_vit_layer& L = w->layers[l];
+    RUNK(mmd::launch_layernorm(resid_out, L.ln1_w, L.ln1_b, buf.x, 0, M, D, eps, s), "ln1");
+    RUN(gemm_normal(c, buf.x, M, L.qkv_w, 3 * D, D, D, mmd::EPI_BF16, mmd::ACT_NONE, L.qkv_b, buf.qkv, 3 * D, s), "qkv");
+    RUNK(mmd::launch_vit_attention(buf.qkv, buf.x, T, Sg, w->heads, D / w->heads, s), "vit_attention (head_dim must be 72)");
+    RUN(gemm_normal(c, buf.x, M, L.out_w, D, D, D, mmd::EPI_RESID_F32, 0, L.out_b, resid_out, D, s), "out_proj");
+    RUNK(mmd::launch_layernorm(resid_out, L.ln2_w, L.ln2_b, buf.x, 0, M, D, eps, s), "ln2");
+    RUN(gemm_normal(c, buf.x, M, L.fc1_w, w->mlp, D, D, mmd::EPI_BF16, mmd::ACT_GELU_TANH, L.fc1_b, buf.h, w->mlp, s), "fc1");
+    RUN(gemm_normal(c, buf.h, M, L.fc2_w, D, w->mlp, w->mlp, mmd::EPI_RESID_F32, 0, L.fc2_b, resid_out, D, s), "fc2");
+  }
+  return check_launch("mmd_vit_forward");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// projector + pooling
+// ---------------------------------------------------------------------------------------------------------------
+struct ProjBufs { __nv_bfloat16 *g, *a; float* b; };
+static int64_t proj_carve(const mmd_projector_weights* w, int T, Bump& b, ProjBufs* o) {
+  o->g = b.take<__nv_bfloat16>((int64_t)T * w->n_gather * w->vit_dim);
+  o->a = b.take<__nv_bfloat16>((int64_t)T * w->n_gather * w->hidden);
+  o->b = b.take<float>((int64_t)T * w->n_gather * w->hidden);
+  return b.off;
+}
+int64_t mmd_projector_workspace_bytes(const mmd_projector_weights* w, int T) {
+  if (w == nullptr || T <= 0) return 0;
+  Bump b(nullptr, 0);
+  ProjBufs o;
+  return proj_carve(w, T, b, &o);
+}
+
+int mmd_projector_pool(mmd_ctx* c, const mmd_projector_weights* w, const float* vit_resid, int T, void* out_bf16, void* workspace,
+                       int64_t workspace_bytes, void* stream) {
+  CHECK_CTX(c);
+  if (w == nullptr || vit_resid == nullptr || out_bf16 == nullptr || workspace == nullptr || T < 0)
+    return fail(MMD_ERR_ARG, "mmd_projector_pool: null argument");
+  if (T == 0) return 0;
+  if (w->vit_dim % 8 != 0 || w->hidden % 8 != 0) return fail(MMD_ERR_ARG, "mmd_projector_pool: dims must be multiples of 8");
+  Bump b(workspace, workspace_bytes);
+  ProjBufs buf;
+  proj_carve(w, T, b, &buf);
+  if (!b.ok) return fail(MMD_ERR_WORKSPACE, "mmd_projector_pool: workspace too small");
+  cudaStream_t s = S(stream);
+  const int Mg = T * w->n_gather, H = w->hidden;
+  // Only the source tokens the pooling reads go through the projector (169 of 729 for bilinear 27->7); Linear2 keeps
+  // its fp32 accumulator and the pooling combines in fp32, so the frame tokens are rounded to bf16 exactly once.
+  RUNK(mmd::launch_gather_rows_f32_to_bf16(vit_resid, w->gather_idx, buf.g, T, w->n_src_tokens, w->n_gather, w->vit_dim, s), "gather");
+  RUN(gemm_normal(c, buf.g, Mg, w->w1, H, w->vit_dim, w->vit_dim, mmd::EPI_BF16, mmd::ACT_GELU_ERF, w->b1, buf.a, H, s), "proj.0+gelu");
+  RUN(gemm_normal(c, buf.a, Mg, w->w2, H, H, H, mmd::EPI_F32, mmd::ACT_NONE, w->b2, buf.b, H, s), "proj.2");
+  RUNK(mmd::launch_tap_pool(buf.b, mmd::DT_F32, out_bf16, mmd::DT_BF16, w->tap_idx, w->tap_w, T, w->n_gather, w->n_out,
+                            w->max_taps, H, w->maxpool, s), "tap_pool");
+  return check_launch("mmd_projector_pool");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// decoder step
+// ---------------------------------------------------------------------------------------------------------------
+struct DecBufs {
+  float *resid, *planes, *hidden_f32, *o_part, *ml_part;
+  __nv_bfloat16 *x, *q, *attn, *h, *lm_x;
+};
+constexpr int kMaxSplits = 8;
+constexpr int kMaxAttnSplits = 32;
+static int64_t dec_carve(const mmd_dec_weights* w, int max_tokens, int max_lm_rows, Bump& b, DecBufs* o) {
+  const int64_t M = max_tokens;
+  const int H = w->hidden, QD = w->q_heads * w->head_dim, NQKV = (w->q_heads + 2 * w->kv_heads) * w->head_dim;
+  const int nmax = NQKV > H ? NQKV : H;
+  o->resid = b.take<float>(M * H);
+  o->hidden_f32 = b.take<float>(M * H);
+  o->planes = b.take<float>((int64_t)kMaxSplits * M * nmax);
+  o->x = b.take<__nv_bfloat16>(M * H);
+  o->q = b.take<__nv_bfloat16>(M * QD);
+  o->attn = b.take<__nv_bfloat16>(M * QD);
+  o->h = b.take<__nv_bfloat16>(M * w->mlp);
+  o->o_part = b.take<float>((int64_t)kMaxAttnSplits * M * QD);
+  o->ml_part = b.take<float>((int64_t)kMaxAttnSplits * M * w->q_heads * 2);
+  o->lm_x = b.take<__nv_bfloat16>((int64_t)(max_lm_rows > 0 ? max_lm_rows : 1) * H);
+  return b.off;
+}
+
+int64_t mmd_decoder_workspace_bytes(mmd_ctx*, const mmd_dec_weights* w, int max_tokens, int max_lm_rows) {
+  if (w == nullptr || max_tokens <= 0) return 0;
+  Bump b(nullptr, 0);
+  DecBufs o;
+  return dec_carve(w, max_tokens, max_lm_rows, b, &o);
+}
+
+int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* pool, const mmd_step* st, void* workspace,
+                     int64_t workspace_bytes, void* stream) {
+  CHECK_CTX(c);
+  if (w == nullptr || pool == nullptr || st == nullptr || workspace == nullptr) return fail(MMD_ERR_ARG, "mmd_decoder_step: null argument");
+  const int M = st->n_tokens;
+  if (M <= 0) return 0;
+  if (w->head_dim != 128 || w->q_heads % w->kv_heads != 0 || w->hidden % 8 != 0 || w->mlp % 8 != 0)
+    return fail(MMD_ERR_ARG, "mmd_decoder_step: unsupported architecture (head_dim 128, dims multiples of 8)");
+  if (st->n_streams <= 0 || st->stream_desc == nullptr || st->block_tables == nullptr || st->tok_pos == nullptr ||
+      st->tok_slot == nullptr || st->src_row == nullptr)
+    return fail(MMD_ERR_ARG, "mmd_decoder_step: incomplete step description");
+  if (st->max_kv_len > w->max_pos) return fail(MMD_ERR_ARG, "mmd_decoder_step: context exceeds the RoPE table (max_pos)");
+  if (st->n_lm_rows > 0 && (w->lm_head == nullptr || st->lm_logits_out == nullptr || st->lm_rows == nullptr))
+    return fail(MMD_ERR_ARG, "mmd_decoder_step: lm rows requested without lm_head / output buffer");
+  Bump b(workspace, workspace_bytes);
+  DecBufs buf;
+  dec_carve(w, M, st->n_lm_rows, b, &buf);
+  if (!b.ok) return fail(MMD_ERR_WORKSPACE, "mmd_decoder_step: workspace too small");
+  cudaStream_t s = S(stream);
+  const int H = w->hidden, Hq = w->q_heads, Hkv = w->kv_heads, dh = w->head_dim;
+  const int QD = Hq * dh, NQKV = (Hq + 2 * Hkv) * dh, I = w->mlp;
+
+  // inputs_embeds = cat(embed_tokens(prefix ids), frame tokens) -> fp32 residual stream   (test/inference.py:235-238)
+  RUNK(mmd::launch_gather_rows_bf16_to_f32(static_cast<const __nv_bfloat16*>(w->embed), static_cast<const __nv_bfloat16*>(st->frame_tokens),
+                                           st->src_row, buf.resid, M, H, s), "embed/concat");
+  RUNK(mmd::launch_resid_add_rmsnorm(buf.resid, nullptr, 0, 0, w->layers[0].ln1_w, buf.x, nullptr, M, H, w->rms_eps, s), "input_layernorm");
+  const int s_qkv = choose_splits(c->num_sms, NQKV, H, M);
+  const int s_o = choose_splits(c->num_sms, H, QD, M);
+  const int s_down = choose_splits(c->num_sms, H, I, M);
+  int attn_splits = mmd::kv_attention_pick_splits(st->max_n_q * (Hq / Hkv), Hkv, st->n_streams, st->max_kv_len, c->num_sms);
+  if (attn_splits > kMaxAttnSplits) attn_splits = kMaxAttnSplits;
+  for (int l = 0; l < w->n_layers; ++l) {
+    const mmd_dec_layer& L = w->layers[l];
+    int eff = 1;
+    RUN(gemm_T_partials(c, buf.x, M, L.qkv_w, NQKV, H, s_qkv, buf.planes, s, &eff), "qkv_proj");
+    __nv_bfloat16* kv_layer = static_cast<__nv_bfloat16*>(pool->pool) + (int64_t)l * pool->layer_stride;
+    RUNK(mmd::launch_qkv_finish(buf.planes, eff, (int64_t)M * NQKV, L.qkv_b, w->rope_cos, w->rope_sin, st->tok_pos, st->tok_slot,
+                                buf.q, kv_layer, M, Hq, Hkv, dh, MMD_PAGE_TOKENS, s), "qkv_finish");
+    RUNK(mmd::launch_kv_attention(buf.q, kv_layer, st->stream_desc, st->block_tables, st->n_streams, st->max_n_q, M, buf.o_part,
+                                  buf.ml_part, buf.attn, Hq, Hkv, dh, MMD_PAGE_TOKENS, attn_splits, s), "kv_attention");
+    RUN(gemm_T_partials(c, buf.attn, M, L.o_w, H, QD, s_o, buf.planes, s, &eff), "o_proj");
+    RUNK(mmd::launch_resid_add_rmsnorm(buf.resid, buf.planes, eff, (int64_t)M * H, L.ln2_w, buf.x, nullptr, M, H, w->rms_eps, s),
+         "post_attention_layernorm");
+    {
+      mmd::GemmArgs a;
+      a.X = static_cast<const __nv_bfloat16*>(L.gate_w); a.X2 = static_cast<const __nv_bfloat16*>(L.up_w);
+      a.x_rows = I; a.ldx = H; a.Y = buf.x; a.y_rows = M; a.ldy = H; a.K = H;
+      a.epi = mmd::EPI_T_SWIGLU; a.out = buf.h; a.ldo = I;
+      RUN(mmd::gemm_launch(c->gemm, a, s), "gate_up_swiglu");
+    }
+    RUN(gemm_T_partials(c, buf.h, M, L.down_w, H, I, s_down, buf.planes, s, &eff), "down_proj");
+    const bool last = (l + 1 == w->n_layers);
+    const float* next_w = last ? w->final_norm_w : w->layers[l + 1].ln1_w;
+    RUNK(mmd::launch_resid_add_rmsnorm(buf.resid, buf.planes, eff, (int64_t)M * H, next_w, buf.x, last ? buf.hidden_f32 : nullptr, M,
+                                       H, w->rms_eps, s), "next_layernorm");
+  }
+  if (st->n_score_rows > 0) {
+    if (st->score_rows == nullptr || st->head_logits_out == nullptr || st->scores_out == nullptr || w->heads_w == nullptr)
+      return fail(MMD_ERR_ARG, "mmd_decoder_step: score rows requested without buffers");
+    RUNK(mmd::launch_heads(buf.hidden_f32, st->score_rows, w->heads_w, st->head_logits_out, st->scores_out, st->n_score_rows, H, s), "heads");
+  }
+  if (st->n_lm_rows > 0) {
+    gather_rows_bf16_kernel<<<st->n_lm_rows, 128, 0, s>>>(buf.x, st->lm_rows, buf.lm_x, H / 8);
+    int eff = 1;
+    RUN(gemm_T_partials(c, buf.lm_x, st->n_lm_rows, w->lm_head, w->vocab, H, 1, st->lm_logits_out, s, &eff), "lm_head");
+  }
+  return check_launch("mmd_decoder_step");
+}
 
 }  // extern "C"

@@ -1,0 +1,478 @@
+// CUDA-core kernels around the tcgen05 GEMMs: patch im2col (+ pixel normalisation), LayerNorm / RMSNorm with the fp32
+// residual stream, split-K reduction fused into the consumers (QKV bias + RoPE + paged-KV append; residual add +
+// RMSNorm), row gathers, tap pooling (bilinear / average / max), final norm + score heads, argmax.
+// All of them are HBM/latency-bound: 16-B vectorised, coalesced accesses, warp-shuffle reductions.
+#include "kernels.cuh"
+
+#include <cuda_bf16.h>
+#include <math.h>
+
+namespace mmd {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int NT>
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = (l < NT / 32) ? sh[l] : 0.f;
+  r = warp_sum(r);
+  return r;
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// im2col for the 14x14/stride-14 patch embedding: A[t*G*G + gy*G + gx, c*P*P + py*P + px] (K padded with zeros).
+// Replaces nn.Conv2d in SiglipVisionEmbeddings (TF:models/siglip/modeling_siglip.py:124-130) together with the
+// image-processor rescale/normalise ((x/255 - 0.5)/0.5; models/vision_live.py:13, LLaVA SigLipImageProcessor).
+// ------------------------------------------------------------------------------------------------------------
+template <typename TIn, bool NORMALIZE>
+__global__ void im2col_kernel(const TIn* __restrict__ px, __nv_bfloat16* __restrict__ A, int T, int C, int img, int P,
+                              int G, int Kpad) {
+  // one block per (frame, patch-row gy); threads sweep the [C, P, img] strip so global reads are row-contiguous
+  const int t = blockIdx.x / G, gy = blockIdx.x % G;
+  const int strip = C * P * img;
+  for (int e = threadIdx.x; e < strip; e += blockDim.x) {
+    const int x = e % img;
+    const int py = (e / img) % P;
+    const int c = e / (img * P);
+    const int gx = x / P, pxx = x % P;
+    if (gx >= G) continue;
+    float v = static_cast<float>(px[(((long long)t * C + c) * img + (gy * P + py)) * img + x]);
+    if (NORMALIZE) v = (v * 0.00392156862745098f - 0.5f) / 0.5f;
+    A[((long long)(t * G + gy) * G + gx) * Kpad + (c * P + py) * P + pxx] = __float2bfloat16_rn(v);
+  }
+  const int Kreal = C * P * P;
+  for (int e = threadIdx.x; e < G * (Kpad - Kreal); e += blockDim.x) {
+    const int gx = e / (Kpad - Kreal), k = Kreal + e % (Kpad - Kreal);
+    A[((long long)(t * G + gy) * G + gx) * Kpad + k] = __float2bfloat16_rn(0.f);
+  }
+}
+
+int launch_im2col(const void* px, int px_dtype, int normalize, __nv_bfloat16* A, int T, int C, int img, int P, int Kpad,
+                  cudaStream_t s) {
+  const int G = img / P;
+  dim3 grid(T * G), block(256);
+  if (px_dtype == DT_U8) {
+    if (normalize) im2col_kernel<uint8_t, true><<<grid, block, 0, s>>>((const uint8_t*)px, A, T, C, img, P, G, Kpad);
+    else im2col_kernel<uint8_t, false><<<grid, block, 0, s>>>((const uint8_t*)px, A, T, C, img, P, G, Kpad);
+  } else if (px_dtype == DT_F32) {
+    if (normalize) im2col_kernel<float, true><<<grid, block, 0, s>>>((const float*)px, A, T, C, img, P, G, Kpad);
+    else im2col_kernel<float, false><<<grid, block, 0, s>>>((const float*)px, A, T, C, img, P, G, Kpad);
+  } else if (px_dtype == DT_BF16) {
+    if (normalize) im2col_kernel<__nv_bfloat16, true><<<grid, block, 0, s>>>((const __nv_bfloat16*)px, A, T, C, img, P, G, Kpad);
+    else im2col_kernel<__nv_bfloat16, false><<<grid, block, 0, s>>>((const __nv_bfloat16*)px, A, T, C, img, P, G, Kpad);
+  } else {
+    return -2;
+  }
+  return 0;
+}
+
+// residual[row, :] = pos_emb[row % S, :]  (the patch-embed GEMM then accumulates conv + bias on top: EPI_RESID_F32)
+__global__ void broadcast_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows, int S, int D4) {
+  const long long n = rows * D4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / D4;
+    const int c = (int)(i % D4);
+    reinterpret_cast<float4*>(dst)[i] = __ldg(reinterpret_cast<const float4*>(src) + (r % S) * D4 + c);
+  }
+}
+int launch_broadcast_rows(const float* src, float* dst, long long rows, int S, int D, cudaStream_t s) {
+  if (D % 4) return -2;
+  const long long n = rows * (D / 4);
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  broadcast_rows_kernel<<<blocks, 256, 0, s>>>(src, dst, rows, S, D / 4);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm: fp32 residual row -> bf16 GEMM operand (or fp32).  One warp per row, row cached in registers.
+// Restates nn.LayerNorm(eps=1e-6) of SiglipEncoderLayer (TF:models/siglip/modeling_siglip.py:333-362).
+// ------------------------------------------------------------------------------------------------------------
+template <int MAXV, bool OUT_F32>
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 void* __restrict__ out, long long rows, int D, float eps) {
+  const int warps_per_block = blockDim.x >> 5;
+  const long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int D4 = D >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  float4 v[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int c = lane + j * 32;
+    if (c < D4) {
+      v[j] = xr[c];
+      sum += v[j].x + v[j].y + v[j].z + v[j].w;
+    }
+  }
+  const float mean = warp_sum(sum) / D;
+  float var = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int c = lane + j * 32;
+    if (c < D4) {
+      const float a = v[j].x - mean, b = v[j].y - mean, cc = v[j].z - mean, d = v[j].w - mean;
+      var += a * a + b * b + cc * cc + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(var) / D + eps);
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int c = lane + j * 32;
+    if (c < D4) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+      const float o0 = (v[j].x - mean) * rstd * g.x + b.x, o1 = (v[j].y - mean) * rstd * g.y + b.y;
+      const float o2 = (v[j].z - mean) * rstd * g.z + b.z, o3 = (v[j].w - mean) * rstd * g.w + b.w;
+      if (OUT_F32) {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * D)[c] = make_float4(o0, o1, o2, o3);
+      } else {
+        uint2 o;
+        o.x = pack2(o0, o1);
+        o.y = pack2(o2, o3);
+        reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + row * D)[c] = o;
+      }
+    }
+  }
+}
+int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_f32, long long rows, int D,
+                     float eps, cudaStream_t s) {
+  if (D % 4 != 0 || D > 12 * 128) return -2;
+  const int wpb = 8;
+  const unsigned blocks = (unsigned)((rows + wpb - 1) / wpb);
+  if (out_f32) layernorm_kernel<12, true><<<blocks, wpb * 32, 0, s>>>(x, gamma, beta, out, rows, D, eps);
+  else layernorm_kernel<12, false><<<blocks, wpb * 32, 0, s>>>(x, gamma, beta, out, rows, D, eps);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// resid[row,:] += sum_s partial[s][row,:]  (split-K planes of o_proj / down_proj), then RMSNorm -> bf16 operand of the
+// next GEMM (and optionally the fp32 normalised row).  Qwen2RMSNorm: w * (x * rsqrt(mean(x^2) + eps))
+// (TF:models/qwen2/modeling_qwen2.py:249-263); residual adds of Qwen2DecoderLayer (:280-310).
+// ------------------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void resid_add_rmsnorm_kernel(float* __restrict__ resid, const float* __restrict__ partial, int n_planes,
+                                         long long plane_stride, const float* __restrict__ w, __nv_bfloat16* __restrict__ out_bf16,
+                                         float* __restrict__ out_f32, int H, float eps) {
+  extern __shared__ float row_sh[];  // H floats
+  __shared__ float red[NT / 32];
+  const long long row = blockIdx.x;
+  const int H4 = H >> 2;
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < H4; c += NT) {
+    float4 v = reinterpret_cast<float4*>(resid + row * H)[c];
+    for (int p = 0; p < n_planes; ++p) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(partial + p * plane_stride + row * H) + c);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    if (n_planes > 0) reinterpret_cast<float4*>(resid + row * H)[c] = v;
+    reinterpret_cast<float4*>(row_sh)[c] = v;
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  const float tot = block_sum<NT>(ss, red);
+  if (w == nullptr) return;
+  const float rstd = rsqrtf(tot / H + eps);
+  for (int c = threadIdx.x; c < H4; c += NT) {
+    const float4 v = reinterpret_cast<float4*>(row_sh)[c];
+    const float4 g = __ldg(reinterpret_cast<const float4*>(w) + c);
+    const float o0 = v.x * rstd * g.x, o1 = v.y * rstd * g.y, o2 = v.z * rstd * g.z, o3 = v.w * rstd * g.w;
+    if (out_bf16 != nullptr) {
+      uint2 o;
+      o.x = pack2(o0, o1);
+      o.y = pack2(o2, o3);
+      reinterpret_cast<uint2*>(out_bf16 + row * H)[c] = o;
+    }
+    if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + row * H)[c] = make_float4(o0, o1, o2, o3);
+  }
+}
+int launch_resid_add_rmsnorm(float* resid, const float* partial, int n_planes, long long plane_stride, const float* w,
+                             __nv_bfloat16* out_bf16, float* out_f32, long long rows, int H, float eps, cudaStream_t s) {
+  if (H % 4 != 0 || rows <= 0) return rows == 0 ? 0 : -2;
+  constexpr int NT = 256;
+  resid_add_rmsnorm_kernel<NT><<<(unsigned)rows, NT, H * sizeof(float), s>>>(resid, partial, n_planes, plane_stride, w,
+                                                                           out_bf16, out_f32, H, eps);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// QKV finish: sum split-K planes + bias, rotate q/k (RoPE, rotate_half convention), write Q as bf16 [M, Hq, dh] and
+// append K/V (bf16) to the paged KV pool at the token's physical slot.  Replaces q/k/v bias add, apply_rotary_pos_emb
+// and DynamicCache.update's torch.cat (TF:models/qwen2/modeling_qwen2.py:127-146,215-233; TF:cache_utils.py:119-120).
+// KV pool layout per layer: [page][2 (K,V)][kv_head][PAGE_TOKENS][dh]; slot = page * PAGE_TOKENS + offset.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void qkv_finish_kernel(const float* __restrict__ partial, int n_planes, long long plane_stride,
+                                  const float* __restrict__ bias, const float* __restrict__ cos_tab,
+                                  const float* __restrict__ sin_tab, const int* __restrict__ tok_pos,
+                                  const int* __restrict__ tok_slot, __nv_bfloat16* __restrict__ q_out,
+                                  __nv_bfloat16* __restrict__ kv_layer, int Hq, int Hkv, int dh, int page_tokens) {
+  // grid: (token, head) with head in [0, Hq + 2*Hkv); block: dh/2 threads, thread d handles the pair (d, d + dh/2)
+  const int tok = blockIdx.x;
+  const int head = blockIdx.y;
+  const int d = threadIdx.x;
+  const int half = dh >> 1;
+  const int N = (Hq + 2 * Hkv) * dh;
+  const int col0 = head * dh + d, col1 = col0 + half;
+  float x0 = bias ? __ldg(bias + col0) : 0.f, x1 = bias ? __ldg(bias + col1) : 0.f;
+  for (int p = 0; p < n_planes; ++p) {
+    const float* pl = partial + p * plane_stride + (long long)tok * N;
+    x0 += __ldg(pl + col0);
+    x1 += __ldg(pl + col1);
+  }
+  const int pos = tok_pos[tok];
+  if (head < Hq + Hkv) {  // q and k are rotated
+    const float c = __ldg(cos_tab + (long long)pos * half + d), sn = __ldg(sin_tab + (long long)pos * half + d);
+    const float r0 = x0 * c - x1 * sn;
+    const float r1 = x1 * c + x0 * sn;
+    x0 = r0;
+    x1 = r1;
+  }
+  if (head < Hq) {
+    __nv_bfloat16* dst = q_out + ((long long)tok * Hq + head) * dh;
+    dst[d] = __float2bfloat16_rn(x0);
+    dst[d + half] = __float2bfloat16_rn(x1);
+  } else {
+    const int is_v = head >= Hq + Hkv;
+    const int kvh = head - Hq - (is_v ? Hkv : 0);
+    const int slot = tok_slot[tok];
+    const int page = slot / page_tokens, off = slot % page_tokens;
+    __nv_bfloat16* dst = kv_layer + ((((long long)page * 2 + is_v) * Hkv + kvh) * page_tokens + off) * dh;
+    dst[d] = __float2bfloat16_rn(x0);
+    dst[d + half] = __float2bfloat16_rn(x1);
+  }
+}
+int launch_qkv_finish(const float* partial, int n_planes, long long plane_stride, const float* bias, const float* cos_tab,
+                      const float* sin_tab, const int* tok_pos, const int* tok_slot, __nv_bfloat16* q_out,
+                      __nv_bfloat16* kv_layer, int M, int Hq, int Hkv, int dh, int page_tokens, cudaStream_t s) {
+  if (M <= 0) return 0;
+  if (dh % 2 || dh / 2 > 1024) return -2;
+  dim3 grid(M, Hq + 2 * Hkv);
+  qkv_finish_kernel<<<grid, dh / 2, 0, s>>>(partial, n_planes, plane_stride, bias, cos_tab, sin_tab, tok_pos, tok_slot, q_out,
+                                           kv_layer, Hq, Hkv, dh, page_tokens);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Row gathers.
+//   embed rows (bf16 table) -> fp32 residual rows: get_input_embeddings()(ids) + torch.cat with the frame tokens
+//   (test/inference.py:235-238); src_row < 0 means "take row -(src_row+1) of `other`" (the frame-token buffer).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void gather_rows_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ table, const __nv_bfloat16* __restrict__ other,
+                                               const int* __restrict__ src_row, float* __restrict__ dst, int H8) {
+  const long long row = blockIdx.x;
+  const int sr = src_row[row];
+  const uint4* src = reinterpret_cast<const uint4*>(sr >= 0 ? table + (long long)sr * H8 * 8 : other + (long long)(-(sr + 1)) * H8 * 8);
+  float4* d = reinterpret_cast<float4*>(dst + row * H8 * 8);
+  for (int c = threadIdx.x; c < H8; c += blockDim.x) {
+    const uint4 u = __ldg(src + c);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    const float2 cc = __bfloat1622float2(h[2]), e = __bfloat1622float2(h[3]);
+    d[2 * c] = make_float4(a.x, a.y, b.x, b.y);
+    d[2 * c + 1] = make_float4(cc.x, cc.y, e.x, e.y);
+  }
+}
+int launch_gather_rows_bf16_to_f32(const __nv_bfloat16* table, const __nv_bfloat16* other, const int* src_row, float* dst,
+                                   long long rows, int H, cudaStream_t s) {
+  if (H % 8) return -2;
+  if (rows <= 0) return 0;
+  gather_rows_bf16_to_f32_kernel<<<(unsigned)rows, 128, 0, s>>>(table, other, src_row, dst, H / 8);
+  return 0;
+}
+
+// fp32 rows (ViT residual stream, pre-post_layernorm) -> bf16 rows, keeping only the tokens the pooling reads:
+// dst[t*G + g, :] = bf16(src[t*S + idx[g], :]).  The tower output is cast to the model dtype before mm_projector
+// (video_head_live_llava_qwen.py:96-98, :90-91).
+__global__ void gather_rows_f32_to_bf16_kernel(const float* __restrict__ src, const int* __restrict__ idx, __nv_bfloat16* __restrict__ dst,
+                                               int S, int G, int D4) {
+  const long long orow = blockIdx.x;
+  const long long t = orow / G;
+  const int g = (int)(orow % G);
+  const float4* s4 = reinterpret_cast<const float4*>(src + (t * S + idx[g]) * (long long)D4 * 4);
+  uint2* d = reinterpret_cast<uint2*>(dst + orow * (long long)D4 * 4);
+  for (int c = threadIdx.x; c < D4; c += blockDim.x) {
+    const float4 v = s4[c];
+    uint2 o;
+    o.x = pack2(v.x, v.y);
+    o.y = pack2(v.z, v.w);
+    d[c] = o;
+  }
+}
+int launch_gather_rows_f32_to_bf16(const float* src, const int* idx, __nv_bfloat16* dst, int T, int S, int G, int D, cudaStream_t s) {
+  if (D % 4) return -2;
+  if (T <= 0) return 0;
+  gather_rows_f32_to_bf16_kernel<<<(unsigned)(T * G), 128, 0, s>>>(src, idx, dst, S, G, D / 4);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Tap pooling: out[t, o, :] = sum_j w[o][j] * in[t, idx[o][j], :]   (bilinear resize / average pool), or the max
+// over the taps.  Tap tables are built on the host from torch's own F.interpolate / pooling applied to an identity
+// basis, so the weights are exactly the reference's (video_head_live_llava_qwen.py:100-119; vision_live.py:19-25).
+// ------------------------------------------------------------------------------------------------------------
+template <typename TIn, typename TOut, bool MAXPOOL>
+__global__ void tap_pool_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, const int* __restrict__ tap_idx,
+                                const float* __restrict__ tap_w, int n_in, int n_out, int max_taps, int D) {
+  const long long orow = blockIdx.x;
+  const long long t = orow / n_out;
+  const int o = (int)(orow % n_out);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc = MAXPOOL ? -INFINITY : 0.f;
+    for (int j = 0; j < max_taps; ++j) {
+      const int src = tap_idx[o * max_taps + j];
+      if (src < 0) break;
+      const float v = static_cast<float>(in[(t * n_in + src) * (long long)D + c]);
+      if (MAXPOOL) acc = fmaxf(acc, v);
+      else acc = fmaf(tap_w[o * max_taps + j], v, acc);
+    }
+    out[orow * (long long)D + c] = static_cast<TOut>(acc);
+  }
+}
+int launch_tap_pool(const void* in, int in_dtype, void* out, int out_dtype, const int* tap_idx, const float* tap_w, int T,
+                    int n_in, int n_out, int max_taps, int D, int maxpool, cudaStream_t s) {
+  if (T <= 0) return 0;
+  dim3 grid(T * n_out), block(256);
+#define TAP_LAUNCH(TI, TO)                                                                                              \
+  do {                                                                                                                  \
+    if (maxpool) tap_pool_kernel<TI, TO, true><<<grid, block, 0, s>>>((const TI*)in, (TO*)out, tap_idx, tap_w, n_in, n_out, max_taps, D); \
+    else tap_pool_kernel<TI, TO, false><<<grid, block, 0, s>>>((const TI*)in, (TO*)out, tap_idx, tap_w, n_in, n_out, max_taps, D);        \
+  } while (0)
+  if (in_dtype == DT_BF16 && out_dtype == DT_BF16) TAP_LAUNCH(__nv_bfloat16, __nv_bfloat16);
+  else if (in_dtype == DT_F32 && out_dtype == DT_F32) TAP_LAUNCH(float, float);
+  else if (in_dtype == DT_F32 && out_dtype == DT_BF16) TAP_LAUNCH(float, __nv_bfloat16);
+  else if (in_dtype == DT_BF16 && out_dtype == DT_F32) TAP_LAUNCH(__nv_bfloat16, float);
+  else return -2;
+#undef TAP_LAUNCH
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Score heads on selected rows of the final-norm output: informative_head / relevance_head (nn.Linear(H, 2, bias=False),
+// video_head_live_llava_qwen.py:77-78,160-161), .float(), softmax(-1)[1] (test/inference.py:243-244) = sigmoid(l1 - l0).
+// logits_out[r] = {inf0, inf1, rel0, rel1}; scores_out[r] = {informative_score, relevance_score}.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void heads_kernel(const float* __restrict__ hidden_f32, const int* __restrict__ rows, const float* __restrict__ head_w,
+                             float* __restrict__ logits_out, float* __restrict__ scores_out, int H) {
+  __shared__ float red[4][8];
+  const int r = blockIdx.x;
+  const float* h = hidden_f32 + (long long)rows[r] * H;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    const float v = h[c];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = fmaf(v, __ldg(head_w + (long long)k * H + c), acc[k]);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    acc[k] = warp_sum(acc[k]);
+    if (l == 0) red[k][w] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float lg[4];
+    for (int k = 0; k < 4; ++k) {
+      float sacc = 0.f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) sacc += red[k][i];
+      lg[k] = sacc;
+      logits_out[r * 4 + k] = sacc;
+    }
+    scores_out[r * 2 + 0] = 1.f / (1.f + expf(lg[0] - lg[1]));
+    scores_out[r * 2 + 1] = 1.f / (1.f + expf(lg[2] - lg[3]));
+  }
+}
+int launch_heads(const float* hidden_f32, const int* rows, const float* head_w, float* logits_out, float* scores_out, int n_rows,
+                 int H, cudaStream_t s) {
+  if (n_rows <= 0) return 0;
+  heads_kernel<<<n_rows, 256, 0, s>>>(hidden_f32, rows, head_w, logits_out, scores_out, H);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Greedy pick over lm_head logits of one row (split-K planes summed on the fly), with the HF repetition penalty
+// (logit < 0 ? logit * p : logit / p for previously generated ids; models/modeling_live.py:51-77).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void argmax_kernel(const float* __restrict__ partial, int n_planes, long long plane_stride, int V,
+                              const long long* __restrict__ penal_ids, int n_penal, float penalty, long long* __restrict__ out_id,
+                              float* __restrict__ out_logit) {
+  __shared__ float bv[32];
+  __shared__ int bi[32];
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    float v = 0.f;
+    for (int p = 0; p < n_planes; ++p) v += __ldg(partial + p * plane_stride + c);
+    if (n_penal > 0) {
+      for (int j = 0; j < n_penal; ++j) {
+        if (penal_ids[j] == c) { v = v < 0.f ? v * penalty : v / penalty; break; }
+      }
+    }
+    if (v > best || (v == best && c < besti)) { best = v; besti = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { bv[w] = best; bi[w] = besti; }
+  __syncthreads();
+  if (w == 0) {
+    best = l < (int)(blockDim.x >> 5) ? bv[l] : -INFINITY;
+    besti = l < (int)(blockDim.x >> 5) ? bi[l] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+    }
+    if (l == 0) {
+      *out_id = besti;
+      if (out_logit) *out_logit = best;
+    }
+  }
+}
+int launch_argmax(const float* partial, int n_planes, long long plane_stride, int V, const long long* penal_ids, int n_penal,
+                  float penalty, long long* out_id, float* out_logit, cudaStream_t s) {
+  argmax_kernel<<<1, 1024, 0, s>>>(partial, n_planes, plane_stride, V, penal_ids, n_penal, penalty, out_id, out_logit);
+  return 0;
+}
+
+// out[row, :] = bf16(sum_s partial[s][row, :] + bias)   (generic split-K finish for small-M linear layers)
+__global__ void splitk_finish_bf16_kernel(const float* __restrict__ partial, int n_planes, long long plane_stride,
+                                          const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int N, int act) {
+  const long long row = blockIdx.x;
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    float v = bias ? __ldg(bias + c) : 0.f;
+    for (int p = 0; p < n_planes; ++p) v += __ldg(partial + p * plane_stride + row * N + c);
+    if (act == 2) v = 0.5f * v * (1.0f + erff(v * 0.7071067811865476f));
+    else if (act == 1) v = 0.5f * v * (1.0f + tanhf(0.7978845608028654f * (v + 0.044715f * v * v * v)));
+    out[row * N + c] = __float2bfloat16_rn(v);
+  }
+}
+int launch_splitk_finish_bf16(const float* partial, int n_planes, long long plane_stride, const float* bias,
+                              __nv_bfloat16* out, long long rows, int N, int act, cudaStream_t s) {
+  if (rows <= 0) return 0;
+  splitk_finish_bf16_kernel<<<(unsigned)rows, 256, 0, s>>>(partial, n_planes, plane_stride, bias, out, N, act);
+  return 0;
+}
+
+}  // namespace mmd

@@ -1,0 +1,415 @@
+"""Host-side runtime over the C ABI: weight packing (reference state_dict keys -> kernel layouts), the vision encoder
+(SigLIP tower + projector + pooling) and the decoder with its paged KV pool.  PyTorch is used for device memory,
+streams and host<->device copies only; all arithmetic on the path happens in libmmduet_b200.so."""
+import ctypes
+import math
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import ModelConfig
+
+VT = "model.vision_tower.vision_tower.vision_model."
+PAGE = _lib.PAGE_TOKENS
+
+
+def _bf16(t, device):
+    return t.detach().to(device=device, dtype=torch.bfloat16).contiguous()
+
+
+def _f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def pooling_taps(grid, stride, mode, out_size=None):
+    """Tap matrix [n_out, grid*grid] of the reference's pooling, obtained by pushing an identity basis through torch's
+    own operators (video_head_live_llava_qwen.py:107-114; vision_live.py:19-25 for 'adaptive')."""
+    import torch.nn.functional as F
+    S = grid * grid
+    eye = torch.eye(S, dtype=torch.float32).view(1, S, grid, grid)
+    if mode == "bilinear":
+        out = F.interpolate(eye, size=[math.ceil(grid / stride)] * 2, mode="bilinear")
+    elif mode == "average":
+        out = F.avg_pool2d(eye, stride)
+    elif mode == "max":
+        out = F.max_pool2d(eye, stride)
+    elif mode == "adaptive":
+        out = F.adaptive_avg_pool2d(eye, out_size)
+    else:
+        raise ValueError(f"Unexpected mm_spatial_pool_mode: {mode}")
+    return out.view(S, -1).t().contiguous()
+
+
+def taps_to_tables(taps):
+    """[n_out, S] tap matrix -> (gather_idx [G], tap_idx [n_out, max_taps] into the gathered set, tap_w)."""
+    used = (taps != 0).any(dim=0).nonzero().flatten()
+    remap = {int(s): i for i, s in enumerate(used.tolist())}
+    rows = [[(remap[int(j)], float(taps[o, j])) for j in (taps[o] != 0).nonzero().flatten().tolist()] for o in range(taps.shape[0])]
+    max_taps = max(len(r) for r in rows)
+    idx = np.full((taps.shape[0], max_taps), -1, dtype=np.int32)
+    wgt = np.zeros((taps.shape[0], max_taps), dtype=np.float32)
+    for o, r in enumerate(rows):
+        for j, (i, w) in enumerate(r):
+            idx[o, j] = i
+            wgt[o, j] = w
+    return used.to(torch.int32), torch.from_numpy(idx), torch.from_numpy(wgt), max_taps
+
+
+class VisionEngine:
+    """model.visual_embed(frames) of the reference (models/modeling_live.py:26-33): SigLIP tower (26 layers, pre-post-LN)
+    -> mm_projector -> spatial pooling -> [T * tokens, hidden] bf16; also the legacy models/vision_live.py entry."""
+
+    MAX_BATCH = 32  # test/inference.py:208 encodes in batches of 32
+
+    def __init__(self, cfg: ModelConfig, state_dict, device, with_projector=True, n_layers=None, legacy_post_ln=False):
+        cfg.validate()
+        self.cfg, self.device = cfg, torch.device(device)
+        self.lib = _lib.load()
+        self.ctx = _lib.context(self.device.index)
+        sd, dev = state_dict, self.device
+        D, P = cfg.vit_dim, cfg.patch_size
+        k_real = 3 * P * P
+        self.k_pad = (k_real + 7) // 8 * 8
+        keep = []
+        pw = torch.zeros(D, self.k_pad, dtype=torch.bfloat16, device=dev)
+        pw[:, :k_real] = _bf16(sd[VT + "embeddings.patch_embedding.weight"].reshape(D, k_real), dev)
+        patch_b = _f32(sd[VT + "embeddings.patch_embedding.bias"], dev)
+        # the position embedding is an fp32 add on the residual stream; keep the (bf16-representable) parameter in fp32
+        pos = _f32(sd[VT + "embeddings.position_embedding.weight"], dev)
+        keep += [pw, patch_b, pos]
+        self.n_layers = cfg.vit_layers if n_layers is None else n_layers
+        layers = (_lib.VitLayer * self.n_layers)()
+        for i in range(self.n_layers):
+            p = f"{VT}encoder.layers.{i}."
+            qkv_w = _bf16(torch.cat([sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv"], 0), dev)
+            qkv_b = _f32(torch.cat([sd[p + f"self_attn.{n}_proj.bias"] for n in "qkv"], 0), dev)
+            t = dict(ln1_w=_f32(sd[p + "layer_norm1.weight"], dev), ln1_b=_f32(sd[p + "layer_norm1.bias"], dev),
+                     qkv_w=qkv_w, qkv_b=qkv_b,
+                     out_w=_bf16(sd[p + "self_attn.out_proj.weight"], dev), out_b=_f32(sd[p + "self_attn.out_proj.bias"], dev),
+                     ln2_w=_f32(sd[p + "layer_norm2.weight"], dev), ln2_b=_f32(sd[p + "layer_norm2.bias"], dev),
+                     fc1_w=_bf16(sd[p + "mlp.fc1.weight"], dev), fc1_b=_f32(sd[p + "mlp.fc1.bias"], dev),
+                     fc2_w=_bf16(sd[p + "mlp.fc2.weight"], dev), fc2_b=_f32(sd[p + "mlp.fc2.bias"], dev))
+            for k, v in t.items():
+                setattr(layers[i], k, v.data_ptr())
+            keep.append(t)
+        self._layers = layers
+        self.vit = _lib.VitWeights(image_size=cfg.image_size, patch_size=P, dim=D, heads=cfg.vit_heads, mlp=cfg.vit_mlp,
+                                   n_layers=self.n_layers, k_pad=self.k_pad, patch_w=pw.data_ptr(), patch_b=patch_b.data_ptr(),
+                                   pos_emb=pos.data_ptr(), layers=layers)
+        self.post_ln = None
+        if legacy_post_ln:
+            self.post_ln = (_f32(sd[VT + "post_layernorm.weight"], dev), _f32(sd[VT + "post_layernorm.bias"], dev))
+        self.proj = None
+        if with_projector:
+            taps = pooling_taps(cfg.grid, cfg.pool_stride, cfg.pool_mode)
+            gidx, tidx, tw, max_taps = taps_to_tables(taps)
+            self.tokens_per_frame = taps.shape[0]
+            t = dict(w1=_bf16(sd["model.mm_projector.0.weight"], dev), b1=_f32(sd["model.mm_projector.0.bias"], dev),
+                     w2=_bf16(sd["model.mm_projector.2.weight"], dev), b2=_f32(sd["model.mm_projector.2.bias"], dev),
+                     gather_idx=gidx.to(dev), tap_idx=tidx.to(dev).contiguous(), tap_w=tw.to(dev).contiguous())
+            keep.append(t)
+            self.proj = _lib.ProjectorWeights(vit_dim=D, hidden=cfg.hidden, n_src_tokens=cfg.patches, n_gather=int(gidx.numel()),
+                                              n_out=self.tokens_per_frame, max_taps=max_taps, maxpool=int(cfg.pool_mode == "max"),
+                                              **{k: v.data_ptr() for k, v in t.items()})
+        self._keep = keep
+        self._ws = {}
+        self._legacy_taps = {}
+
+    def _workspace(self, T):
+        ws = self._ws.get(T)
+        if ws is None:
+            n = self.lib.mmd_vit_workspace_bytes(ctypes.byref(self.vit), T)
+            if self.proj is not None:
+                n = max(n, self.lib.mmd_projector_workspace_bytes(ctypes.byref(self.proj), T))
+            ws = (torch.empty(n, dtype=torch.uint8, device=self.device),
+                  torch.empty(T * self.cfg.patches, self.cfg.vit_dim, dtype=torch.float32, device=self.device))
+            self._ws = {T: ws}  # keep only the latest size
+        return ws
+
+    def _pixel_dtype(self, frames):
+        if frames.dtype == torch.uint8:
+            return _lib.DT_U8
+        if frames.dtype == torch.bfloat16:
+            return _lib.DT_BF16
+        if frames.dtype == torch.float32:
+            return _lib.DT_F32
+        raise TypeError(f"frames dtype {frames.dtype} unsupported (uint8, bfloat16, float32)")
+
+    def tower(self, frames, normalize=False):
+        """[T,3,H,W] pixels -> fp32 hidden state [T*patches, vit_dim] of the last executed layer (pre-post_layernorm).
+        The returned tensor is a workspace view that the next call overwrites."""
+        assert frames.is_cuda and frames.dim() == 4 and frames.shape[1] == 3, frames.shape
+        assert frames.shape[2] == self.cfg.image_size and frames.shape[3] == self.cfg.image_size, frames.shape
+        frames = frames.contiguous()
+        T = frames.shape[0]
+        ws, resid = self._workspace(T)
+        rc = self.lib.mmd_vit_forward(self.ctx, ctypes.byref(self.vit), frames.data_ptr(), self._pixel_dtype(frames), int(normalize),
+                                      T, resid.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, "mmd_vit_forward")
+        return resid
+
+    def visual_embed(self, frames, normalize=False):
+        """frames [T,3,384,384] (already image-processed unless normalize=True) -> bf16 [T*tokens_per_frame, hidden]."""
+        if self.proj is None:
+            raise _lib.MmdError("this VisionEngine was built without the projector")
+        outs = []
+        for b in range(0, frames.shape[0], self.MAX_BATCH):
+            chunk = frames[b:b + self.MAX_BATCH]
+            T = chunk.shape[0]
+            resid = self.tower(chunk, normalize)
+            ws, _ = self._workspace(T)
+            out = torch.empty(T * self.tokens_per_frame, self.cfg.hidden, dtype=torch.bfloat16, device=self.device)
+            rc = self.lib.mmd_projector_pool(self.ctx, ctypes.byref(self.proj), resid.data_ptr(), T, out.data_ptr(), ws.data_ptr(),
+                                             ws.numel(), _lib.stream_ptr())
+            _lib.check(rc, "mmd_projector_pool")
+            outs.append(out)
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+    def legacy_encode(self, frames_0_255, frame_token_pooled=(7, 7)):
+        """models/vision_live.py:11-31 semantics: rescale+normalize, all layers, post_layernorm, adaptive_avg_pool2d."""
+        if self.post_ln is None:
+            raise _lib.MmdError("legacy_encode needs legacy_post_ln=True (post_layernorm weights)")
+        outs = []
+        key = tuple(frame_token_pooled)
+        if key not in self._legacy_taps:
+            gidx, tidx, tw, max_taps = taps_to_tables(pooling_taps(self.cfg.grid, 0, "adaptive", key))
+            assert gidx.numel() == self.cfg.patches
+            self._legacy_taps[key] = (tidx.to(self.device).contiguous(), tw.to(self.device).contiguous(), max_taps, tidx.shape[0])
+        tidx, tw, max_taps, n_out = self._legacy_taps[key]
+        D, S = self.cfg.vit_dim, self.cfg.patches
+        for b in range(0, frames_0_255.shape[0], self.MAX_BATCH):
+            chunk = frames_0_255[b:b + self.MAX_BATCH]
+            T = chunk.shape[0]
+            resid = self.tower(chunk, normalize=True)
+            normed = torch.empty(T * S, D, dtype=torch.float32, device=self.device)
+            rc = self.lib.mmd_layernorm(resid.data_ptr(), self.post_ln[0].data_ptr(), self.post_ln[1].data_ptr(), normed.data_ptr(), 1,
+                                        T * S, D, 1e-6, _lib.stream_ptr())
+            _lib.check(rc, "mmd_layernorm")
+            out = torch.empty(T, n_out, D, dtype=torch.float32, device=self.device)
+            rc = self.lib.mmd_tap_pool(normed.data_ptr(), _lib.DT_F32, out.data_ptr(), _lib.DT_F32, tidx.data_ptr(), tw.data_ptr(), T, S,
+                                       n_out, max_taps, D, 0, _lib.stream_ptr())
+            _lib.check(rc, "mmd_tap_pool")
+            outs.append(out)
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+
+class KVStorage:
+    """Pages of one stream (video) in the pool.  `length` = tokens currently valid."""
+
+    def __init__(self, engine):
+        self.engine = engine
+        self.pages = []
+        self.length = 0
+
+    def ensure(self, new_len):
+        need = (new_len + PAGE - 1) // PAGE
+        while len(self.pages) < need:
+            self.pages.append(self.engine._alloc_page())
+
+    def truncate(self, length):
+        """O(1) rollback (the 4.44.2 'drop the returned cache' meaning); pages beyond are recycled."""
+        assert 0 <= length <= self.length
+        self.length = length
+        need = (length + PAGE - 1) // PAGE
+        while len(self.pages) > need:
+            self.engine._free_page(self.pages.pop())
+
+    def release(self):
+        self.truncate(0)
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:  # noqa: BLE001  (interpreter shutdown)
+            pass
+
+
+class CacheView:
+    """What the reference calls `past_key_values`: an immutable (storage, length) pair.  Passing an OLDER view back
+    into forward() rolls the stream back to that length, exactly like dropping a newer legacy-tuple cache did."""
+
+    def __init__(self, storage, length):
+        self.storage, self.length = storage, length
+
+    def get_seq_length(self, layer_idx=0):
+        return self.length
+
+    def __len__(self):
+        return self.length
+
+    def __bool__(self):
+        return self.length > 0
+
+
+class DecoderEngine:
+    """Qwen2 decoder + informative/relevance heads over a paged KV pool (video_head_live_llava_qwen.py:121-205)."""
+
+    def __init__(self, cfg: ModelConfig, state_dict, device, n_pages=None, max_tokens=512, max_lm_rows=1, max_context=None):
+        cfg.validate()
+        self.cfg, self.device = cfg, torch.device(device)
+        self.lib = _lib.load()
+        self.ctx = _lib.context(self.device.index)
+        sd, dev = state_dict, self.device
+        H = cfg.hidden
+        keep = []
+        layers = (_lib.DecLayer * cfg.layers)()
+        for i in range(cfg.layers):
+            p = f"model.layers.{i}."
+            t = dict(ln1_w=_f32(sd[p + "input_layernorm.weight"], dev),
+                     qkv_w=_bf16(torch.cat([sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv"], 0), dev),
+                     qkv_b=_f32(torch.cat([sd[p + f"self_attn.{n}_proj.bias"] for n in "qkv"], 0), dev),
+                     o_w=_bf16(sd[p + "self_attn.o_proj.weight"], dev),
+                     ln2_w=_f32(sd[p + "post_attention_layernorm.weight"], dev),
+                     gate_w=_bf16(sd[p + "mlp.gate_proj.weight"], dev), up_w=_bf16(sd[p + "mlp.up_proj.weight"], dev),
+                     down_w=_bf16(sd[p + "mlp.down_proj.weight"], dev))
+            for k, v in t.items():
+                setattr(layers[i], k, v.data_ptr())
+            keep.append(t)
+        self.max_context = int(max_context or cfg.max_pos)
+        # RoPE tables exactly as Qwen2RotaryEmbedding computes them in fp32 (TF:models/qwen2/modeling_qwen2.py:102-125)
+        inv_freq = 1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, dtype=torch.int64).float() / cfg.head_dim))
+        freqs = torch.arange(self.max_context, dtype=torch.float32)[:, None] * inv_freq[None, :]
+        t = dict(final_norm_w=_f32(sd["model.norm.weight"], dev), embed=_bf16(sd["model.embed_tokens.weight"], dev),
+                 heads_w=_f32(torch.cat([sd["informative_head.weight"], sd["relevance_head.weight"]], 0), dev),
+                 rope_cos=_f32(freqs.cos(), dev), rope_sin=_f32(freqs.sin(), dev))
+        self.embed = t["embed"]
+        lm = sd.get("lm_head.weight")
+        self.lm_head = _bf16(lm, dev) if lm is not None else None
+        keep.append(t)
+        self._layers, self._keep = layers, keep
+        self.w = _lib.DecWeights(hidden=H, n_layers=cfg.layers, q_heads=cfg.q_heads, kv_heads=cfg.kv_heads, head_dim=cfg.head_dim,
+                                 mlp=cfg.mlp, vocab=cfg.vocab, max_pos=self.max_context, rms_eps=cfg.rms_eps, layers=layers,
+                                 lm_head=self.lm_head.data_ptr() if self.lm_head is not None else 0,
+                                 **{k: v.data_ptr() for k, v in t.items()})
+        if n_pages is None:
+            n_pages = (self.max_context + PAGE - 1) // PAGE + 1
+        self.n_pages = n_pages
+        self.pool = torch.empty(cfg.layers, n_pages, 2, cfg.kv_heads, PAGE, cfg.head_dim, dtype=torch.bfloat16, device=dev)
+        self.kv = _lib.KvPool(pool=self.pool.data_ptr(), layer_stride=self.pool.stride(0), n_pages=n_pages)
+        self._free = list(range(n_pages - 1, -1, -1))
+        self._lock = threading.Lock()
+        self.max_tokens, self.max_lm_rows = max_tokens, max_lm_rows
+        self._ws = None
+        self._ensure_ws(max_tokens, max_lm_rows)
+
+    # ---- pages ----
+    def _alloc_page(self):
+        if not self._free:
+            raise _lib.MmdError(f"KV pool exhausted ({self.n_pages} pages of {PAGE} tokens)")
+        return self._free.pop()
+
+    def _free_page(self, p):
+        self._free.append(p)
+
+    def new_stream(self):
+        return KVStorage(self)
+
+    def _ensure_ws(self, n_tokens, n_lm):
+        if self._ws is None or n_tokens > self.max_tokens or n_lm > self.max_lm_rows:
+            self.max_tokens, self.max_lm_rows = max(self.max_tokens, n_tokens), max(self.max_lm_rows, n_lm)
+            n = self.lib.mmd_decoder_workspace_bytes(self.ctx, ctypes.byref(self.w), self.max_tokens, self.max_lm_rows)
+            self._ws = torch.empty(n, dtype=torch.uint8, device=self.device)
+
+    # ---- the step ----
+    def step(self, items, score="last", lm="none"):
+        """One decoder pass over several streams.
+
+        items: list of dicts {storage: KVStorage, past: int (view length to append at), and either
+                              embeds: bf16 [M,H] tensor  or  ids: list[int] (+ optional frames: bf16 [n,H] appended after)}
+        score: 'last' (last row of each item), 'all', 'frame_ends' (item key 'score_rows': row offsets inside the item) or 'none'
+        lm:    'none' or 'last' (lm_head logits for the last row of each item)
+        Returns dict(head_logits [n,4], scores [n,2], lm_logits [n_lm,V] or None, views [CacheView per item])."""
+        with self._lock:
+            return self._step_locked(items, score, lm)
+
+    def _step_locked(self, items, score, lm):
+        H, dev = self.cfg.hidden, self.device
+        src_row, tok_pos, tok_slot, desc, tables, score_rows, lm_rows = [], [], [], [], [], [], []
+        emb_chunks, emb_rows = [], 0
+        q_start, max_n_q, max_kv = 0, 0, 0
+        views = []
+        for it in items:
+            st, past = it["storage"], int(it["past"])
+            if past > st.length:
+                raise _lib.MmdError("cache view is longer than the stream (stale view after a rollback)")
+            if past < st.length:
+                st.truncate(past)  # an older view was passed back: rollback
+            ids = it.get("ids")
+            rows = []
+            if it.get("embeds") is not None:
+                e = it["embeds"]
+                assert e.dim() == 2 and e.shape[1] == H, e.shape
+                emb_chunks.append(e if e.dtype == torch.bfloat16 else e.to(torch.bfloat16))
+                rows = [-(emb_rows + j) - 1 for j in range(e.shape[0])]
+                emb_rows += e.shape[0]
+            else:
+                rows = [int(i) for i in (ids if ids is not None else [])]
+                if any(r < 0 or r >= self.cfg.vocab for r in rows):
+                    raise _lib.MmdError("token id out of range")
+                fr = it.get("frames")
+                if fr is not None and fr.shape[0] > 0:
+                    assert fr.dim() == 2 and fr.shape[1] == H, fr.shape
+                    emb_chunks.append(fr if fr.dtype == torch.bfloat16 else fr.to(torch.bfloat16))
+                    rows += [-(emb_rows + j) - 1 for j in range(fr.shape[0])]
+                    emb_rows += fr.shape[0]
+            n_q = len(rows)
+            if n_q == 0:
+                raise _lib.MmdError("empty step item")
+            new_len = past + n_q
+            if new_len > self.max_context:
+                raise _lib.MmdError(f"context {new_len} exceeds max_context {self.max_context}")
+            st.ensure(new_len)
+            src_row += rows
+            for j in range(n_q):
+                pos = past + j
+                tok_pos.append(pos)
+                tok_slot.append(st.pages[pos // PAGE] * PAGE + pos % PAGE)
+            desc += [q_start, n_q, new_len, len(tables)]
+            tables += st.pages[:(new_len + PAGE - 1) // PAGE]
+            if score == "last":
+                score_rows.append(q_start + n_q - 1)
+            elif score == "all":
+                score_rows += list(range(q_start, q_start + n_q))
+            elif score == "frame_ends":
+                score_rows += [q_start + r for r in it["score_rows"]]
+            if lm == "last":
+                lm_rows.append(q_start + n_q - 1)
+            st.length = new_len
+            views.append(CacheView(st, new_len))
+            q_start += n_q
+            max_n_q, max_kv = max(max_n_q, n_q), max(max_kv, new_len)
+        M = q_start
+        self._ensure_ws(M, len(lm_rows))
+        meta = np.asarray(src_row + tok_pos + tok_slot + desc + tables + score_rows + lm_rows, dtype=np.int32)
+        meta_d = torch.from_numpy(meta).pin_memory().to(dev, non_blocking=True)
+        base = meta_d.data_ptr()
+        o = 0
+
+        def seg(n):
+            nonlocal o
+            p = base + 4 * o
+            o += n
+            return p
+        p_src, p_pos, p_slot = seg(M), seg(M), seg(M)
+        p_desc, p_tab = seg(len(desc)), seg(len(tables))
+        p_score, p_lm = seg(len(score_rows)), seg(len(lm_rows))
+        if emb_chunks:
+            frame_tokens = emb_chunks[0] if len(emb_chunks) == 1 else torch.cat(emb_chunks, 0)
+            frame_tokens = frame_tokens.contiguous()
+        else:
+            frame_tokens = None
+        n_s, n_l = len(score_rows), len(lm_rows)
+        head_logits = torch.empty(max(n_s, 1), 4, dtype=torch.float32, device=dev)
+        scores = torch.empty(max(n_s, 1), 2, dtype=torch.float32, device=dev)
+        lm_logits = torch.empty(n_l, self.cfg.vocab, dtype=torch.float32, device=dev) if n_l else None
+        step = _lib.Step(n_tokens=M, src_row=p_src, frame_tokens=_lib.ptr(frame_tokens), tok_pos=p_pos, tok_slot=p_slot,
+                         n_streams=len(items), stream_desc=p_desc, block_tables=p_tab, max_n_q=max_n_q, max_kv_len=max_kv,
+                         n_score_rows=n_s, score_rows=p_score, head_logits_out=head_logits.data_ptr(), scores_out=scores.data_ptr(),
+                         n_lm_rows=n_l, lm_rows=p_lm, lm_logits_out=_lib.ptr(lm_logits))
+        rc = self.lib.mmd_decoder_step(self.ctx, ctypes.byref(self.w), ctypes.byref(self.kv), ctypes.byref(step), self._ws.data_ptr(),
+                                       self._ws.numel(), _lib.stream_ptr())
+        _lib.check(rc, "mmd_decoder_step")
+        self._last_meta = (meta_d, frame_tokens)  # keep alive until the kernels have consumed them
+        return {"head_logits": head_logits[:n_s], "scores": scores[:n_s], "lm_logits": lm_logits, "views": views}

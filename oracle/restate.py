@@ -324,16 +324,22 @@ class LiveLoopOracle:
 # deterministic weights and synthetic frames (shared by the oracle, the fixtures and the CUDA path)
 # ------------------------------------------------------------------------------------------------------------
 def make_weights(arch, seed=1234, device="cpu", dtype=torch.float32, round_bf16=True, include_lm_head=True,
-                 legacy_post_ln=False):
-    """Random-init state_dict with the reference's key names.  Distributions follow the HF initialisers in spirit
-    (std 0.02 linears, LayerNorm 1/0 with small perturbations so that scale/bias paths are exercised); values are
-    rounded to bf16 when `round_bf16` so that the fp32 oracle and the bf16 kernels see identical weights."""
-    g = torch.Generator(device="cpu").manual_seed(seed)
+                 legacy_post_ln=False, generate_on_device=False):
+    """Random-init state_dict with the reference's key names.  Scales follow the HF / torch default initialisers
+    (SigLIP: lecun-normal patch embedding, xavier attention/MLP; mm_projector: nn.Linear default, std 1/sqrt(3*fan_in);
+    Qwen2: normal(0, 0.02)), because the north-star tolerance (max-abs 2e-2) is absolute and was stated at that scale
+    (frame embeddings abs-max ~4.6, rms ~1.1).  Norm scales/biases get small perturbations so
+    that every scale/bias path is exercised.  Values are rounded to bf16 when `round_bf16` so that the fp32 oracle and
+    the bf16 kernels see identical weights."""
+    gen_dev = device if generate_on_device else "cpu"   # full-size weights: seconds on the GPU, minutes on CPU
+    g = torch.Generator(device=gen_dev).manual_seed(seed)
     w = {}
 
     def rnd(*shape, std=0.02):
-        t = torch.randn(*shape, generator=g, dtype=torch.float32) * std
-        return t
+        t = torch.randn(*shape, generator=g, dtype=torch.float32, device=gen_dev) * std
+        if round_bf16:
+            t = t.bfloat16().float()
+        return t.to(device=device, dtype=dtype)
 
     D, Dm = arch.vit_dim, arch.vit_mlp
     w[VT + "embeddings.patch_embedding.weight"] = rnd(D, 3, arch.patch_size, arch.patch_size, std=(3 * arch.patch_size ** 2) ** -0.5)
@@ -348,44 +354,42 @@ def make_weights(arch, seed=1234, device="cpu", dtype=torch.float32, round_bf16=
         for proj in ("q_proj", "k_proj", "v_proj", "out_proj"):
             w[p + f"self_attn.{proj}.weight"] = rnd(D, D, std=D ** -0.5)
             w[p + f"self_attn.{proj}.bias"] = rnd(D, std=0.02)
-        w[p + "mlp.fc1.weight"] = rnd(Dm, D, std=D ** -0.5)
+        w[p + "mlp.fc1.weight"] = rnd(Dm, D, std=(2.0 / (D + Dm)) ** 0.5)
         w[p + "mlp.fc1.bias"] = rnd(Dm, std=0.02)
-        w[p + "mlp.fc2.weight"] = rnd(D, Dm, std=Dm ** -0.5)
+        w[p + "mlp.fc2.weight"] = rnd(D, Dm, std=(2.0 / (D + Dm)) ** 0.5)
         w[p + "mlp.fc2.bias"] = rnd(D, std=0.02)
     if legacy_post_ln:
         w[VT + "post_layernorm.weight"] = 1.0 + rnd(D, std=0.05)
         w[VT + "post_layernorm.bias"] = rnd(D, std=0.05)
     H = arch.hidden
-    w["model.mm_projector.0.weight"] = rnd(H, D, std=D ** -0.5)
+    w["model.mm_projector.0.weight"] = rnd(H, D, std=(3 * D) ** -0.5)
     w["model.mm_projector.0.bias"] = rnd(H, std=0.02)
-    w["model.mm_projector.2.weight"] = rnd(H, H, std=H ** -0.5)
+    w["model.mm_projector.2.weight"] = rnd(H, H, std=(3 * H) ** -0.5)
     w["model.mm_projector.2.bias"] = rnd(H, std=0.02)
-    w["model.embed_tokens.weight"] = rnd(arch.vocab, H, std=1.0)
+    w["model.embed_tokens.weight"] = rnd(arch.vocab, H, std=0.02)
     kvd = arch.kv_heads * arch.head_dim
     for i in range(arch.layers):
         p = f"model.layers.{i}."
         w[p + "input_layernorm.weight"] = 1.0 + rnd(H, std=0.05)
         w[p + "post_attention_layernorm.weight"] = 1.0 + rnd(H, std=0.05)
-        w[p + "self_attn.q_proj.weight"] = rnd(H, H, std=H ** -0.5)
+        w[p + "self_attn.q_proj.weight"] = rnd(H, H, std=0.02)
         w[p + "self_attn.q_proj.bias"] = rnd(H, std=0.1)
-        w[p + "self_attn.k_proj.weight"] = rnd(kvd, H, std=H ** -0.5)
+        w[p + "self_attn.k_proj.weight"] = rnd(kvd, H, std=0.02)
         w[p + "self_attn.k_proj.bias"] = rnd(kvd, std=0.1)
-        w[p + "self_attn.v_proj.weight"] = rnd(kvd, H, std=H ** -0.5)
+        w[p + "self_attn.v_proj.weight"] = rnd(kvd, H, std=0.02)
         w[p + "self_attn.v_proj.bias"] = rnd(kvd, std=0.1)
-        w[p + "self_attn.o_proj.weight"] = rnd(H, H, std=H ** -0.5)
-        w[p + "mlp.gate_proj.weight"] = rnd(arch.mlp, H, std=H ** -0.5)
-        w[p + "mlp.up_proj.weight"] = rnd(arch.mlp, H, std=H ** -0.5)
-        w[p + "mlp.down_proj.weight"] = rnd(H, arch.mlp, std=arch.mlp ** -0.5)
+        w[p + "self_attn.o_proj.weight"] = rnd(H, H, std=0.02)
+        w[p + "mlp.gate_proj.weight"] = rnd(arch.mlp, H, std=0.02)
+        w[p + "mlp.up_proj.weight"] = rnd(arch.mlp, H, std=0.02)
+        w[p + "mlp.down_proj.weight"] = rnd(H, arch.mlp, std=0.02)
     w["model.norm.weight"] = 1.0 + rnd(H, std=0.05)
     if include_lm_head:
         w["lm_head.weight"] = rnd(arch.vocab, H, std=0.02)
     w["informative_head.weight"] = rnd(2, H, std=0.02)
     w["relevance_head.weight"] = rnd(2, H, std=0.02)
-    for k in w:
-        t = w[k]
-        if round_bf16:
-            t = t.bfloat16().float()
-        w[k] = t.to(device=device, dtype=dtype)
+    if round_bf16:  # the "1.0 + noise" LayerNorm/RMSNorm scales are sums: round them too
+        for k in w:
+            w[k] = w[k].float().bfloat16().float().to(dtype)
     return w
 
 

@@ -1,0 +1,275 @@
+"""GPU tests, kernel level: each C-ABI building block against a plain fp32 torch statement of the same op."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from mmduet_b200 import _lib, ops
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    return _lib, ops, _lib.load(), _lib.context(0)
+
+
+def _s():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def test_library_refuses_nothing_silently(env):
+    _lib, ops, lib, ctx = env
+    assert lib.mmd_num_sms(ctx) >= 100
+    x = torch.zeros(8, 12, device="cuda", dtype=torch.bfloat16)  # K not a multiple of 8
+    w = torch.zeros(8, 12, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(_lib.MmdError):
+        ops.gemm(x, w)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 1152, 1152), (729, 4304, 1152), (729, 1152, 4304), (1000, 1152, 592),
+                                   (77, 144, 328), (2000, 288, 1000)])
+def test_gemm_normal(env, M, N, K):
+    _lib, ops, lib, ctx = env
+    torch.manual_seed(M + N + K)
+    x = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
+    b = torch.randn(N, device="cuda")
+    ref = x.float() @ w.float().t() + b
+    out = ops.gemm(x, w, bias=b, epi=_lib.EPI_F32)
+    assert (out - ref).abs().max() < 1e-3
+    out = ops.gemm(x, w, bias=b, act=_lib.ACT_GELU_TANH)
+    assert (out.float() - torch.nn.functional.gelu(ref, approximate="tanh")).abs().max() < 2e-2
+    out = ops.gemm(x, w, bias=b, act=_lib.ACT_GELU_ERF)
+    assert (out.float() - torch.nn.functional.gelu(ref)).abs().max() < 2e-2
+    res = torch.randn(M, N, device="cuda")
+    acc = res.clone()
+    ops.gemm(x, w, bias=b, out=acc, epi=_lib.EPI_RESID_F32)
+    assert (acc - (res + ref)).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(49, 4608, 3584, 4), (49, 3584, 18944, 5), (1, 2048, 896, 1), (81, 1152, 896, 3),
+                                           (300, 896, 2432, 2), (60, 512, 256, 8)])
+def test_gemm_swap_ab_splitk(env, M, N, K, splits):
+    _lib, ops, lib, ctx = env
+    torch.manual_seed(M + N + K)
+    x = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    w = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
+    parts = ops.gemm_t_partials(x, w, splits)
+    assert (parts.sum(0) - x.float() @ w.float().t()).abs().max() < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(49, 18944, 3584), (200, 2432, 896), (7, 512, 256)])
+def test_gemm_swiglu(env, M, N, K):
+    _lib, ops, lib, ctx = env
+    torch.manual_seed(M + N)
+    x = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    wg = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
+    wu = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
+    out = ops.gemm_t_swiglu(x, wg, wu)
+    ref = torch.nn.functional.silu(x.float() @ wg.float().t()) * (x.float() @ wu.float().t())
+    assert ((out.float() - ref).abs() / (1 + ref.abs())).max() < 1e-2
+
+
+@pytest.mark.parametrize("dtype,normalize", [(torch.uint8, True), (torch.float32, False), (torch.bfloat16, False), (torch.float32, True)])
+def test_im2col(env, dtype, normalize):
+    _lib, ops, lib, ctx = env
+    T, img, P = 3, 384, 14
+    G, kreal, kpad = img // P, 3 * P * P, 592
+    if dtype == torch.uint8:
+        px = torch.randint(0, 256, (T, 3, img, img), device="cuda", dtype=torch.uint8)
+    else:
+        px = (torch.rand(T, 3, img, img, device="cuda") * (255 if normalize else 2) - (0 if normalize else 1)).to(dtype)
+    A = torch.full((T * G * G, kpad), 7.0, device="cuda", dtype=torch.bfloat16)
+    code = {torch.uint8: _lib.DT_U8, torch.bfloat16: _lib.DT_BF16, torch.float32: _lib.DT_F32}[dtype]
+    _lib.check(lib.mmd_im2col(px.data_ptr(), code, int(normalize), A.data_ptr(), T, img, P, kpad, _s()))
+    x = px.float()
+    if normalize:
+        x = (x * 0.00392156862745098 - 0.5) / 0.5
+    ref = torch.nn.functional.unfold(x[:, :, :G * P, :G * P], kernel_size=P, stride=P).transpose(1, 2).reshape(T * G * G, kreal)
+    assert (A[:, :kreal].float() - ref.bfloat16().float()).abs().max() <= 1e-2
+    assert (A[:, kreal:] == 0).all()
+
+
+@pytest.mark.parametrize("D", [1152, 288, 144])
+def test_layernorm(env, D):
+    _lib, ops, lib, ctx = env
+    rows = 1000
+    x = torch.randn(rows, D, device="cuda") * 3 + 0.5
+    g, b = torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
+    ref = torch.nn.functional.layer_norm(x, (D,), g, b, 1e-6)
+    out = torch.empty(rows, D, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.mmd_layernorm(x.data_ptr(), g.data_ptr(), b.data_ptr(), out.data_ptr(), 0, rows, D, 1e-6, _s()))
+    assert ((out.float() - ref).abs() / (1 + ref.abs())).max() < 8e-3
+    out32 = torch.empty(rows, D, device="cuda")
+    _lib.check(lib.mmd_layernorm(x.data_ptr(), g.data_ptr(), b.data_ptr(), out32.data_ptr(), 1, rows, D, 1e-6, _s()))
+    assert (out32 - ref).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("T,S,H", [(2, 729, 16), (1, 729, 4), (3, 100, 2), (1, 64, 2), (1, 129, 1)])
+def test_vit_attention(env, T, S, H):
+    _lib, ops, lib, ctx = env
+    dh = 72
+    torch.manual_seed(S)
+    qkv = (torch.randn(T * S, 3 * H * dh, device="cuda") * 1.5).bfloat16()
+    out = torch.empty(T * S, H * dh, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.mmd_vit_attention(qkv.data_ptr(), out.data_ptr(), T, S, H, dh, _s()))
+    q, k, v = (t.view(T, S, H, dh).transpose(1, 2) for t in qkv.float().view(T, S, 3, H * dh).unbind(2))
+    att = torch.softmax(q @ k.transpose(-1, -2) * dh ** -0.5, -1)
+    ref = (att @ v).transpose(1, 2).reshape(T * S, H * dh)
+    assert (out.float() - ref).abs().max() < 2e-2
+
+
+def test_resid_add_rmsnorm(env):
+    _lib, ops, lib, ctx = env
+    rows, H, planes = 53, 3584, 5
+    resid = torch.randn(rows, H, device="cuda")
+    parts = torch.randn(planes, rows, H, device="cuda")
+    w = torch.randn(H, device="cuda")
+    want_res = resid + parts.sum(0)
+    want = want_res * torch.rsqrt(want_res.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+    r = resid.clone()
+    ob = torch.empty(rows, H, device="cuda", dtype=torch.bfloat16)
+    of = torch.empty(rows, H, device="cuda")
+    _lib.check(lib.mmd_resid_add_rmsnorm(r.data_ptr(), parts.data_ptr(), planes, parts.stride(0), w.data_ptr(), ob.data_ptr(),
+                                         of.data_ptr(), rows, H, 1e-6, _s()))
+    assert (r - want_res).abs().max() < 1e-5
+    assert (of - want).abs().max() < 1e-4
+    assert (ob.float() - want).abs().max() < 5e-2
+    r2 = resid.clone()  # zero planes: pure norm, residual untouched
+    _lib.check(lib.mmd_resid_add_rmsnorm(r2.data_ptr(), 0, 0, 0, w.data_ptr(), ob.data_ptr(), 0, rows, H, 1e-6, _s()))
+    assert torch.equal(r2, resid)
+
+
+def _rope_tables(n, dh, theta=1e6):
+    inv = 1.0 / (theta ** (torch.arange(0, dh, 2, dtype=torch.int64).float() / dh))
+    fr = torch.arange(n, dtype=torch.float32)[:, None] * inv[None]
+    return fr.cos().cuda().contiguous(), fr.sin().cuda().contiguous()
+
+
+def _rot(x, cos, sin):
+    h = x.shape[-1] // 2
+    c, s = torch.cat([cos, cos], -1), torch.cat([sin, sin], -1)
+    return x * c + torch.cat((-x[..., h:], x[..., :h]), -1) * s
+
+
+def test_qkv_finish_and_kv_attention(env):
+    """Appends three chunks per stream (two streams with different histories) and checks Q, the pool contents and the
+    attention output against a dense fp32 statement with a bottom-right causal mask."""
+    _lib, ops, lib, ctx = env
+    Hq, Hkv, dh, PAGE = 14, 2, 128, _lib.PAGE_TOKENS
+    N = (Hq + 2 * Hkv) * dh
+    n_pages = 40
+    torch.manual_seed(0)
+    pool = torch.full((n_pages, 2, Hkv, PAGE, dh), float("nan"), device="cuda", dtype=torch.bfloat16)
+    cos, sin = _rope_tables(4096, dh)
+    bias = torch.randn(N, device="cuda") * 0.1
+    perm = torch.randperm(n_pages).tolist()
+    pages = {0: perm[:16], 1: perm[16:32]}
+    hist = {0: [], 1: []}  # per stream: list of (q, k, v) fp32 after bias+rope, per token
+    for chunk in [(49, 700), (130, 49), (1, 1), (64, 77)]:
+        rows, pos, slot, desc, tables = [], [], [], [], []
+        planes = torch.randn(2, sum(chunk), N, device="cuda") * 0.7
+        q_start = 0
+        for st, n_q in enumerate(chunk):
+            past = len(hist[st])
+            x = planes.sum(0)[q_start:q_start + n_q] + bias
+            p = torch.arange(past, past + n_q, device="cuda")
+            q = _rot(x[:, :Hq * dh].view(n_q, Hq, dh), cos[p][:, None], sin[p][:, None])
+            k = _rot(x[:, Hq * dh:(Hq + Hkv) * dh].view(n_q, Hkv, dh), cos[p][:, None], sin[p][:, None])
+            v = x[:, (Hq + Hkv) * dh:].view(n_q, Hkv, dh)
+            for j in range(n_q):
+                hist[st].append((q[j], k[j], v[j]))
+                pos.append(past + j)
+                slot.append(pages[st][(past + j) // PAGE] * PAGE + (past + j) % PAGE)
+            desc += [q_start, n_q, past + n_q, len(tables)]
+            tables += pages[st][:(past + n_q + PAGE - 1) // PAGE]
+            q_start += n_q
+        M = q_start
+        d_pos, d_slot = torch.tensor(pos, device="cuda", dtype=torch.int32), torch.tensor(slot, device="cuda", dtype=torch.int32)
+        d_desc, d_tab = torch.tensor(desc, device="cuda", dtype=torch.int32), torch.tensor(tables, device="cuda", dtype=torch.int32)
+        q_out = torch.empty(M, Hq, dh, device="cuda", dtype=torch.bfloat16)
+        _lib.check(lib.mmd_qkv_finish(planes.data_ptr(), 2, planes.stride(0), bias.data_ptr(), cos.data_ptr(), sin.data_ptr(),
+                                      d_pos.data_ptr(), d_slot.data_ptr(), q_out.data_ptr(), pool.data_ptr(), M, Hq, Hkv, dh, _s()))
+        for n_splits in (0, 1, 3, 7):
+            max_kv = max(len(hist[0]), len(hist[1]))
+            ns = n_splits or lib.mmd_kv_attention_splits(ctx, max(chunk), Hq, Hkv, 2, max_kv)
+            o_part = torch.empty(ns, M * Hq, dh, device="cuda")
+            ml = torch.empty(ns, M * Hq, 2, device="cuda")
+            out = torch.empty(M, Hq * dh, device="cuda", dtype=torch.bfloat16)
+            _lib.check(lib.mmd_kv_attention(ctx, q_out.data_ptr(), pool.data_ptr(), d_desc.data_ptr(), d_tab.data_ptr(), 2, max(chunk), M,
+                                            max_kv, o_part.data_ptr(), ml.data_ptr(), out.data_ptr(), Hq, Hkv, dh, ns, _s()))
+            q_start = 0
+            for st, n_q in enumerate(chunk):
+                L = len(hist[st])
+                past = L - n_q
+                qs = torch.stack([h[0] for h in hist[st][past:]])                    # [n_q, Hq, dh]
+                ks = torch.stack([h[1] for h in hist[st]]).bfloat16().float()          # [L, Hkv, dh] as stored
+                vs = torch.stack([h[2] for h in hist[st]]).bfloat16().float()
+                assert (q_out[q_start:q_start + n_q].float() - qs).abs().max() < 5e-2
+                qb = q_out[q_start:q_start + n_q].float()
+                kk = ks.repeat_interleave(Hq // Hkv, dim=1)
+                vv = vs.repeat_interleave(Hq // Hkv, dim=1)
+                sc = torch.einsum("qhd,khd->hqk", qb, kk) * dh ** -0.5
+                mask = torch.ones(n_q, L, dtype=torch.bool, device="cuda").tril(diagonal=past)
+                sc = sc.masked_fill(~mask[None], float("-inf"))
+                ref = torch.einsum("hqk,khd->qhd", torch.softmax(sc, -1), vv).reshape(n_q, Hq * dh)
+                err = (out[q_start:q_start + n_q].float() - ref).abs().max().item()
+                assert err < 2e-2, (chunk, n_splits, st, err)
+                q_start += n_q
+    # pool content of stream 0 equals the bf16 of the appended K
+    k0 = torch.stack([h[1] for h in hist[0]])[:PAGE]
+    got = pool[pages[0][0], 0].transpose(0, 1)[:PAGE]  # [PAGE, Hkv, dh]
+    assert (got.float() - k0).abs().max() < 5e-2
+
+
+@pytest.mark.parametrize("mode", ["bilinear", "average", "max"])
+def test_tap_pool(env, mode):
+    _lib, ops, lib, ctx = env
+    from mmduet_b200.engine import pooling_taps, taps_to_tables
+    T, grid, D = 2, 27, 256
+    taps = pooling_taps(grid, 4, mode)
+    gidx, tidx, tw, max_taps = taps_to_tables(taps)
+    n_out = taps.shape[0]
+    x = torch.randn(T, grid * grid, D, device="cuda")
+    xin = x[:, gidx.long().cuda()].contiguous()
+    out = torch.empty(T, n_out, D, device="cuda")
+    tidx, tw = tidx.cuda().contiguous(), tw.cuda().contiguous()
+    _lib.check(lib.mmd_tap_pool(xin.data_ptr(), _lib.DT_F32, out.data_ptr(), _lib.DT_F32, tidx.data_ptr(), tw.data_ptr(),
+                                T, gidx.numel(), n_out, max_taps, D, int(mode == "max"), _s()))
+    xi = x.view(T, grid, grid, D).permute(0, 3, 1, 2)
+    if mode == "bilinear":
+        ref = torch.nn.functional.interpolate(xi, size=[7, 7], mode="bilinear")
+    elif mode == "average":
+        ref = torch.nn.functional.avg_pool2d(xi, 4)
+    else:
+        ref = torch.nn.functional.max_pool2d(xi, 4)
+    ref = ref.permute(0, 2, 3, 1).reshape(T, n_out, D)
+    assert (out - ref).abs().max() < 1e-5
+
+
+def test_heads_and_argmax(env):
+    _lib, ops, lib, ctx = env
+    H = 3584
+    hid = torch.randn(60, H, device="cuda")
+    hw = torch.randn(4, H, device="cuda") * 0.02
+    rows = torch.tensor([48, 59, 0], device="cuda", dtype=torch.int32)
+    logits = torch.empty(3, 4, device="cuda")
+    scores = torch.empty(3, 2, device="cuda")
+    _lib.check(lib.mmd_heads(hid.data_ptr(), rows.data_ptr(), hw.data_ptr(), logits.data_ptr(), scores.data_ptr(), 3, H, _s()))
+    ref = hid[rows.long()] @ hw.t()
+    assert (logits - ref).abs().max() < 1e-4
+    assert (scores[:, 0] - ref[:, :2].softmax(-1)[:, 1]).abs().max() < 1e-5
+    assert (scores[:, 1] - ref[:, 2:].softmax(-1)[:, 1]).abs().max() < 1e-5
+    V = 152064
+    lg = torch.randn(V, device="cuda")
+    out = torch.zeros(1, device="cuda", dtype=torch.int64)
+    _lib.check(lib.mmd_argmax(lg.data_ptr(), V, 0, 0, 1.0, out.data_ptr(), _s()))
+    assert out.item() == lg.argmax().item()
+    top = lg.topk(3).indices
+    pen = top[:2].contiguous()
+    _lib.check(lib.mmd_argmax(lg.data_ptr(), V, pen.data_ptr(), 2, 100.0, out.data_ptr(), _s()))
+    assert out.item() == top[2].item()
