@@ -57,6 +57,7 @@ MMD_API int mmd_num_sms(mmd_ctx*);
 #define MMD_EPI_T_F32 2     /* out_f32[split][m][n] = acc                          */
 #define MMD_EPI_T_SWIGLU 3  /* out_bf16[m][n] = silu(acc_gate) * acc_up            */
 #define MMD_EPI_F32 4       /* out_f32 = acc + bias[n]                             */
+#define MMD_EPI_BF16_HILO 5 /* v = act(acc + bias[n]); out[m,n] = bf16(v), out[m,N+n] = bf16(v - bf16(v)) */
 #define MMD_ACT_NONE 0
 #define MMD_ACT_GELU_TANH 1
 #define MMD_ACT_GELU_ERF 2
@@ -75,9 +76,9 @@ MMD_API int mmd_im2col(const void* pixels, int px_dtype, int normalize, void* A,
 /* LayerNorm over fp32 rows -> bf16 (or fp32) rows; SiglipEncoderLayer layer_norm1/2, post_layernorm. */
 MMD_API int mmd_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_f32, int64_t rows,
                           int D, float eps, void* stream);
-/* Fused SigLIP attention on packed qkv bf16 [T*S, 3*H*dh] -> out bf16 [T*S, H*dh]
- * (TF:models/siglip/modeling_siglip.py:252-330). */
-MMD_API int mmd_vit_attention(const void* qkv, void* out, int T, int S, int H, int dh, void* stream);
+/* Fused SigLIP attention on packed qkv bf16 [T*S, 3*H*dh] -> out bf16 [T*S, H*dh], or with split_hi_lo
+ * [T*S, 2*H*dh] = [bf16(o) | bf16(o - bf16(o))] (TF:models/siglip/modeling_siglip.py:252-330). */
+MMD_API int mmd_vit_attention(const void* qkv, void* out, int T, int S, int H, int dh, int split_hi_lo, void* stream);
 /* resid += sum of split-K planes; out = RMSNorm(resid) * w (bf16 and/or fp32) — Qwen2DecoderLayer residual adds and
  * Qwen2RMSNorm (TF:models/qwen2/modeling_qwen2.py:249-310).  w == NULL: reduction only. */
 MMD_API int mmd_resid_add_rmsnorm(float* resid, const float* partial, int n_planes, int64_t plane_stride, const float* w,
@@ -112,7 +113,7 @@ MMD_API int mmd_argmax(const float* logits, int64_t V, const int64_t* penal_ids,
 typedef struct {
   const float* ln1_w; const float* ln1_b;
   const void* qkv_w;  const float* qkv_b;   /* bf16 [3*dim, dim] (q;k;v stacked), fp32 [3*dim] */
-  const void* out_w;  const float* out_b;   /* bf16 [dim, dim] */
+  const void* out_w;  const float* out_b;   /* bf16 [dim, dim], or [dim, 2*dim] = [W | W] when attn_out_split */
   const float* ln2_w; const float* ln2_b;
   const void* fc1_w;  const float* fc1_b;   /* bf16 [mlp, dim] */
   const void* fc2_w;  const float* fc2_b;   /* bf16 [dim, mlp] */
@@ -120,6 +121,7 @@ typedef struct {
 
 typedef struct {
   int image_size, patch_size, dim, heads, mlp, n_layers, k_pad;
+  int attn_out_split;               /* 1: attention output kept as bf16 hi+lo pairs for the out-projection (+8% FLOPs) */
   const void* patch_w;              /* bf16 [dim, k_pad]: Conv2d weight flattened (c, py, px), zero padded */
   const float* patch_b;             /* fp32 [dim] */
   const float* pos_emb;             /* fp32 [S, dim] */
@@ -133,21 +135,24 @@ MMD_API int mmd_vit_forward(mmd_ctx*, const mmd_vit_weights*, const void* pixels
 /* ---------------------------------------------------------------------------------------------------------------
  * mm_projector + GELU + spatial pooling (a2): gathers the source tokens the pooling reads (169 of 729 for the
  * bilinear 27->7 resize), Linear1 + erf-GELU, Linear2 with an fp32 epilogue, then the tap pooling (bilinear / average
- * weights or max) in fp32 and a single rounding to bf16.
+ * weights or max) in fp32 and a single rounding to bf16 (with `hilo` the GEMM inputs carry ~16 mantissa bits).
  * video_head_live_llava_qwen.py:90-91 (connector), :100-119 (post_projector_pooling).
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct {
   int vit_dim, hidden, n_src_tokens /* S */, n_gather, n_out, max_taps, maxpool;
-  const void* w1; const float* b1;   /* bf16 [hidden, vit_dim] */
-  const void* w2; const float* b2;   /* bf16 [hidden, hidden]  */
+  int hilo;                          /* 1: operands as bf16 hi+lo pairs, weights stored as [W | W] (K doubled) */
+  const void* w1; const float* b1;   /* bf16 [hidden, vit_dim]  (or [hidden, 2*vit_dim] when hilo) */
+  const void* w2; const float* b2;   /* bf16 [hidden, hidden]   (or [hidden, 2*hidden]  when hilo) */
   const int* gather_idx;             /* int32 [n_gather]: source token of each gathered row */
   const int* tap_idx;                /* int32 [n_out, max_taps]: index INTO THE GATHERED set, -1 = end */
   const float* tap_w;                /* fp32 [n_out, max_taps] */
 } mmd_projector_weights;
 
 MMD_API int64_t mmd_projector_workspace_bytes(const mmd_projector_weights*, int T);
-MMD_API int mmd_projector_pool(mmd_ctx*, const mmd_projector_weights*, const float* vit_resid, int T, void* out_bf16,
-                               void* workspace, int64_t workspace_bytes, void* stream);
+/* out: [T*n_out, hidden] in out_dtype (MMD_DT_BF16 = the model dtype the reference returns, or MMD_DT_F32 = the same
+ * values before the final rounding). */
+MMD_API int mmd_projector_pool(mmd_ctx*, const mmd_projector_weights*, const float* vit_resid, int T, void* out,
+                               int out_dtype, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Decoder step (a4/a5/a7): embed/concat -> n_layers x {RMSNorm, QKV(+bias,RoPE,KV append), KV-append attention, o_proj,

@@ -9,7 +9,7 @@ LIB_PATH = os.path.join(_HERE, "libmmduet_b200.so")
 
 c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 
-EPI_BF16, EPI_RESID_F32, EPI_T_F32, EPI_T_SWIGLU, EPI_F32 = 0, 1, 2, 3, 4
+EPI_BF16, EPI_RESID_F32, EPI_T_F32, EPI_T_SWIGLU, EPI_F32, EPI_BF16_HILO = 0, 1, 2, 3, 4, 5
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
 
 
@@ -32,12 +32,12 @@ class VitLayer(ctypes.Structure):
 
 
 class VitWeights(ctypes.Structure):
-    _fields_ = [(n, c_int) for n in ("image_size", "patch_size", "dim", "heads", "mlp", "n_layers", "k_pad")] + \
+    _fields_ = [(n, c_int) for n in ("image_size", "patch_size", "dim", "heads", "mlp", "n_layers", "k_pad", "attn_out_split")] + \
                [("patch_w", c_void_p), ("patch_b", c_void_p), ("pos_emb", c_void_p), ("layers", ctypes.POINTER(VitLayer))]
 
 
 class ProjectorWeights(ctypes.Structure):
-    _fields_ = [(n, c_int) for n in ("vit_dim", "hidden", "n_src_tokens", "n_gather", "n_out", "max_taps", "maxpool")] + \
+    _fields_ = [(n, c_int) for n in ("vit_dim", "hidden", "n_src_tokens", "n_gather", "n_out", "max_taps", "maxpool", "hilo")] + \
                [(n, c_void_p) for n in ("w1", "b1", "w2", "b2", "gather_idx", "tap_idx", "tap_w")]
 
 
@@ -77,7 +77,7 @@ SIGNATURES = {
     "mmd_num_sms": (c_int, [c_void_p]),
     "mmd_im2col": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mmd_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_float, c_void_p]),
-    "mmd_vit_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "mmd_vit_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mmd_resid_add_rmsnorm": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                       c_float, c_void_p]),
     "mmd_qkv_finish": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -93,7 +93,8 @@ SIGNATURES = {
     "mmd_vit_forward": (c_int, [c_void_p, P(VitWeights), c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int64,
                                 c_void_p]),
     "mmd_projector_workspace_bytes": (c_int64, [P(ProjectorWeights), c_int]),
-    "mmd_projector_pool": (c_int, [c_void_p, P(ProjectorWeights), c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    "mmd_projector_pool": (c_int, [c_void_p, P(ProjectorWeights), c_void_p, c_int, c_void_p, c_int, c_void_p, c_int64,
+                                   c_void_p]),
     "mmd_decoder_workspace_bytes": (c_int64, [c_void_p, P(DecWeights), c_int, c_int]),
     "mmd_decoder_step": (c_int, [c_void_p, P(DecWeights), P(KvPool), P(Step), c_void_p, c_int64, c_void_p]),
 }

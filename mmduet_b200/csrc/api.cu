@@ -149,8 +149,8 @@ int mmd_layernorm(const float* x, const float* gamma, const float* beta, void* o
   return check_launch("mmd_layernorm");
 }
 
-int mmd_vit_attention(const void* qkv, void* out, int T, int S_, int H, int dh, void* stream) {
-  RUNK(mmd::launch_vit_attention(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), T, S_, H, dh, S(stream)),
+int mmd_vit_attention(const void* qkv, void* out, int T, int S_, int H, int dh, int split_hi_lo, void* stream) {
+  RUNK(mmd::launch_vit_attention(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), T, S_, H, dh, split_hi_lo, S(stream)),
        "mmd_vit_attention (head_dim must be 72)");
   return check_launch("mmd_vit_attention");
 }
@@ -212,10 +212,11 @@ struct VitBufs { __nv_bfloat16 *x, *qkv, *h; };
 static int64_t vit_carve(const mmd_vit_weights* w, int T, Bump& b, VitBufs* o) {
   const int G = w->image_size / w->patch_size;
   const int64_t M = (int64_t)T * G * G;
-  const int wide = w->mlp > w->k_pad ? w->mlp : w->k_pad;
+  int wide = w->mlp > w->k_pad ? w->mlp : w->k_pad;
+  if (wide < 2 * w->dim) wide = 2 * w->dim;
   o->x = b.take<__nv_bfloat16>(M * w->dim);
   o->qkv = b.take<__nv_bfloat16>(M * 3 * w->dim);
-  o->h = b.take<__nv_bfloat16>(M * wide);  // fc1 output; also holds the im2col matrix
+  o->h = b.take<__nv_bfloat16>(M * wide);  // fc1 output; also holds the im2col matrix and the [hi|lo] attention output
   return b.off;
 }
 
@@ -250,8 +251,13 @@ int mmd_vit_forward(mmd_ctx* c, const mmd_vit_weights* w, const void* pixels, in
     const mmd_vit_layer& L = w->layers[l];
     RUNK(mmd::launch_layernorm(resid_out, L.ln1_w, L.ln1_b, buf.x, 0, M, D, eps, s), "ln1");
     RUN(gemm_normal(c, buf.x, M, L.qkv_w, 3 * D, D, D, mmd::EPI_BF16, mmd::ACT_NONE, L.qkv_b, buf.qkv, 3 * D, s), "qkv");
-    RUNK(mmd::launch_vit_attention(buf.qkv, buf.x, T, Sg, w->heads, D / w->heads, s), "vit_attention (head_dim must be 72)");
-    RUN(gemm_normal(c, buf.x, M, L.out_w, D, D, D, mmd::EPI_RESID_F32, 0, L.out_b, resid_out, D, s), "out_proj");
+    if (w->attn_out_split) {  // out_w is [dim, 2*dim] = [W | W]; the attention output is [hi | lo]
+      RUNK(mmd::launch_vit_attention(buf.qkv, buf.h, T, Sg, w->heads, D / w->heads, 1, s), "vit_attention (head_dim must be 72)");
+      RUN(gemm_normal(c, buf.h, M, L.out_w, D, 2 * D, 2 * D, mmd::EPI_RESID_F32, 0, L.out_b, resid_out, D, s), "out_proj");
+    } else {
+      RUNK(mmd::launch_vit_attention(buf.qkv, buf.x, T, Sg, w->heads, D / w->heads, 0, s), "vit_attention (head_dim must be 72)");
+      RUN(gemm_normal(c, buf.x, M, L.out_w, D, D, D, mmd::EPI_RESID_F32, 0, L.out_b, resid_out, D, s), "out_proj");
+    }
     RUNK(mmd::launch_layernorm(resid_out, L.ln2_w, L.ln2_b, buf.x, 0, M, D, eps, s), "ln2");
     RUN(gemm_normal(c, buf.x, M, L.fc1_w, w->mlp, D, D, mmd::EPI_BF16, mmd::ACT_GELU_TANH, L.fc1_b, buf.h, w->mlp, s), "fc1");
     RUN(gemm_normal(c, buf.h, M, L.fc2_w, D, w->mlp, w->mlp, mmd::EPI_RESID_F32, 0, L.fc2_b, resid_out, D, s), "fc2");
@@ -264,8 +270,9 @@ int mmd_vit_forward(mmd_ctx* c, const mmd_vit_weights* w, const void* pixels, in
 // ---------------------------------------------------------------------------------------------------------------
 struct ProjBufs { __nv_bfloat16 *g, *a; float* b; };
 static int64_t proj_carve(const mmd_projector_weights* w, int T, Bump& b, ProjBufs* o) {
-  o->g = b.take<__nv_bfloat16>((int64_t)T * w->n_gather * w->vit_dim);
-  o->a = b.take<__nv_bfloat16>((int64_t)T * w->n_gather * w->hidden);
+  const int f = w->hilo ? 2 : 1;
+  o->g = b.take<__nv_bfloat16>((int64_t)T * w->n_gather * w->vit_dim * f);
+  o->a = b.take<__nv_bfloat16>((int64_t)T * w->n_gather * w->hidden * f);
   o->b = b.take<float>((int64_t)T * w->n_gather * w->hidden);
   return b.off;
 }
@@ -276,11 +283,12 @@ int64_t mmd_projector_workspace_bytes(const mmd_projector_weights* w, int T) {
   return proj_carve(w, T, b, &o);
 }
 
-int mmd_projector_pool(mmd_ctx* c, const mmd_projector_weights* w, const float* vit_resid, int T, void* out_bf16, void* workspace,
-                       int64_t workspace_bytes, void* stream) {
+int mmd_projector_pool(mmd_ctx* c, const mmd_projector_weights* w, const float* vit_resid, int T, void* out, int out_dtype,
+                       void* workspace, int64_t workspace_bytes, void* stream) {
   CHECK_CTX(c);
-  if (w == nullptr || vit_resid == nullptr || out_bf16 == nullptr || workspace == nullptr || T < 0)
+  if (w == nullptr || vit_resid == nullptr || out == nullptr || workspace == nullptr || T < 0)
     return fail(MMD_ERR_ARG, "mmd_projector_pool: null argument");
+  if (out_dtype != MMD_DT_BF16 && out_dtype != MMD_DT_F32) return fail(MMD_ERR_ARG, "mmd_projector_pool: out dtype must be bf16 or f32");
   if (T == 0) return 0;
   if (w->vit_dim % 8 != 0 || w->hidden % 8 != 0) return fail(MMD_ERR_ARG, "mmd_projector_pool: dims must be multiples of 8");
   Bump b(workspace, workspace_bytes);
@@ -288,14 +296,16 @@ int mmd_projector_pool(mmd_ctx* c, const mmd_projector_weights* w, const float* 
   proj_carve(w, T, b, &buf);
   if (!b.ok) return fail(MMD_ERR_WORKSPACE, "mmd_projector_pool: workspace too small");
   cudaStream_t s = S(stream);
-  const int Mg = T * w->n_gather, H = w->hidden;
-  // Only the source tokens the pooling reads go through the projector (169 of 729 for bilinear 27->7); Linear2 keeps
-  // its fp32 accumulator and the pooling combines in fp32, so the frame tokens are rounded to bf16 exactly once.
-  RUNK(mmd::launch_gather_rows_f32_to_bf16(vit_resid, w->gather_idx, buf.g, T, w->n_src_tokens, w->n_gather, w->vit_dim, s), "gather");
-  RUN(gemm_normal(c, buf.g, Mg, w->w1, H, w->vit_dim, w->vit_dim, mmd::EPI_BF16, mmd::ACT_GELU_ERF, w->b1, buf.a, H, s), "proj.0+gelu");
-  RUN(gemm_normal(c, buf.a, Mg, w->w2, H, H, H, mmd::EPI_F32, mmd::ACT_NONE, w->b2, buf.b, H, s), "proj.2");
-  RUNK(mmd::launch_tap_pool(buf.b, mmd::DT_F32, out_bf16, mmd::DT_BF16, w->tap_idx, w->tap_w, T, w->n_gather, w->n_out,
-                            w->max_taps, H, w->maxpool, s), "tap_pool");
+  const int Mg = T * w->n_gather, H = w->hidden, f = w->hilo ? 2 : 1;
+  // Only the source tokens the pooling reads go through the projector (169 of 729 for bilinear 27->7).  With `hilo` the
+  // GEMM operands are bf16 hi+lo pairs (K doubled against [W | W]), Linear2 keeps its fp32 accumulator and the pooling
+  // combines in fp32: the frame tokens are rounded to bf16 exactly once, at the output.
+  RUNK(mmd::launch_gather_rows_f32_to_bf16(vit_resid, w->gather_idx, buf.g, T, w->n_src_tokens, w->n_gather, w->vit_dim, w->hilo, s), "gather");
+  RUN(gemm_normal(c, buf.g, Mg, w->w1, H, f * w->vit_dim, f * w->vit_dim, w->hilo ? mmd::EPI_BF16_HILO : mmd::EPI_BF16, mmd::ACT_GELU_ERF,
+                  w->b1, buf.a, f * H, s), "proj.0+gelu");
+  RUN(gemm_normal(c, buf.a, Mg, w->w2, H, f * H, f * H, mmd::EPI_F32, mmd::ACT_NONE, w->b2, buf.b, H, s), "proj.2");
+  RUNK(mmd::launch_tap_pool(buf.b, mmd::DT_F32, out, out_dtype == MMD_DT_F32 ? mmd::DT_F32 : mmd::DT_BF16, w->tap_idx, w->tap_w, T,
+                            w->n_gather, w->n_out, w->max_taps, H, w->maxpool, s), "tap_pool");
   return check_launch("mmd_projector_pool");
 }
 

@@ -300,25 +300,36 @@ int launch_gather_rows_bf16_to_f32(const __nv_bfloat16* table, const __nv_bfloat
 // fp32 rows (ViT residual stream, pre-post_layernorm) -> bf16 rows, keeping only the tokens the pooling reads:
 // dst[t*G + g, :] = bf16(src[t*S + idx[g], :]).  The tower output is cast to the model dtype before mm_projector
 // (video_head_live_llava_qwen.py:96-98, :90-91).
+// With HILO the destination row is [hi | lo] (2*D wide): hi = bf16(x), lo = bf16(x - hi).
+template <bool HILO>
 __global__ void gather_rows_f32_to_bf16_kernel(const float* __restrict__ src, const int* __restrict__ idx, __nv_bfloat16* __restrict__ dst,
                                                int S, int G, int D4) {
   const long long orow = blockIdx.x;
   const long long t = orow / G;
   const int g = (int)(orow % G);
   const float4* s4 = reinterpret_cast<const float4*>(src + (t * S + idx[g]) * (long long)D4 * 4);
-  uint2* d = reinterpret_cast<uint2*>(dst + orow * (long long)D4 * 4);
+  uint2* d = reinterpret_cast<uint2*>(dst + orow * (long long)D4 * 4 * (HILO ? 2 : 1));
   for (int c = threadIdx.x; c < D4; c += blockDim.x) {
     const float4 v = s4[c];
     uint2 o;
     o.x = pack2(v.x, v.y);
     o.y = pack2(v.z, v.w);
     d[c] = o;
+    if (HILO) {
+      const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.x));
+      const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.y));
+      uint2 l;
+      l.x = pack2(v.x - h0.x, v.y - h0.y);
+      l.y = pack2(v.z - h1.x, v.w - h1.y);
+      d[D4 + c] = l;
+    }
   }
 }
-int launch_gather_rows_f32_to_bf16(const float* src, const int* idx, __nv_bfloat16* dst, int T, int S, int G, int D, cudaStream_t s) {
+int launch_gather_rows_f32_to_bf16(const float* src, const int* idx, __nv_bfloat16* dst, int T, int S, int G, int D, int hilo, cudaStream_t s) {
   if (D % 4) return -2;
   if (T <= 0) return 0;
-  gather_rows_f32_to_bf16_kernel<<<(unsigned)(T * G), 128, 0, s>>>(src, idx, dst, S, G, D / 4);
+  if (hilo) gather_rows_f32_to_bf16_kernel<true><<<(unsigned)(T * G), 128, 0, s>>>(src, idx, dst, S, G, D / 4);
+  else gather_rows_f32_to_bf16_kernel<false><<<(unsigned)(T * G), 128, 0, s>>>(src, idx, dst, S, G, D / 4);
   return 0;
 }
 

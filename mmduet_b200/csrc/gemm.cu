@@ -189,7 +189,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int xi = xt * BM + lane_row;  // index along X rows (TMEM lane)
       const int y0 = yt * BN;             // first index along Y rows (TMEM column 0)
 
-      if constexpr (EPI == EPI_BF16 || EPI == EPI_RESID_F32 || EPI == EPI_F32) {
+      if constexpr (EPI == EPI_BF16 || EPI == EPI_RESID_F32 || EPI == EPI_F32 || EPI == EPI_BF16_HILO) {
         // normal orientation: lane = output row m, columns = n (contiguous in memory)
         const bool row_ok = xi < p.x_rows;
 #pragma unroll 1
@@ -212,7 +212,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                   f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                   f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
                 }
-                if constexpr (EPI == EPI_BF16) {
+                if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_HILO) {
 #pragma unroll
                   for (int j = 0; j < 8; ++j) f[j] = apply_act<ACT>(f[j]);
                   uint4 o;
@@ -220,6 +220,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                   o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
                   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)xi * p.ldo + n;
                   *reinterpret_cast<uint4*>(dst) = o;
+                  if constexpr (EPI == EPI_BF16_HILO) {
+                    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&o);
+                    uint4 lo;
+                    uint32_t* lw = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float2 hf = __bfloat1622float2(hp[j]);
+                      lw[j] = pack_bf16(f[2 * j] - hf.x, f[2 * j + 1] - hf.y);
+                    }
+                    *reinterpret_cast<uint4*>(dst + p.y_rows) = lo;
+                  }
                 } else {
                   float* dst = reinterpret_cast<float*>(p.out) + (long long)xi * p.ldo + n;
                   float4 r0, r1;
@@ -443,6 +454,10 @@ int gemm_launch(GemmContext* c, const GemmArgs& a, cudaStream_t s) {
       if (a.act == ACT_NONE) return launch_normal<EPI_BF16, ACT_NONE>(c, a, s);
       if (a.act == ACT_GELU_TANH) return launch_normal<EPI_BF16, ACT_GELU_TANH>(c, a, s);
       if (a.act == ACT_GELU_ERF) return launch_normal<EPI_BF16, ACT_GELU_ERF>(c, a, s);
+      break;
+    case EPI_BF16_HILO:
+      if (a.act == ACT_GELU_ERF) return launch_normal<EPI_BF16_HILO, ACT_GELU_ERF>(c, a, s);
+      if (a.act == ACT_NONE) return launch_normal<EPI_BF16_HILO, ACT_NONE>(c, a, s);
       break;
     case EPI_RESID_F32: return launch_normal<EPI_RESID_F32, ACT_NONE>(c, a, s);
     case EPI_F32: return launch_normal<EPI_F32, ACT_NONE>(c, a, s);

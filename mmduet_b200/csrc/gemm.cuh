@@ -17,6 +17,7 @@ enum GemmEpi : int {
   EPI_T_F32 = 2,     // out_f32[split][m, n] = acc                (split-K partial planes, no bias)
   EPI_T_SWIGLU = 3,  // out_bf16[m, n] = silu(acc_gate) * acc_up  (two X operands: gate rows, up rows)
   EPI_F32 = 4,       // out_f32[m, n] = acc + bias[n]
+  EPI_BF16_HILO = 5, // v = act(acc + bias[n]); out_bf16[m, n] = hi = bf16(v); out_bf16[m, N + n] = bf16(v - hi)  (ldo >= 2N)
 };
 enum GemmAct : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2 };
 

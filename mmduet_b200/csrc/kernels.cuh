@@ -20,7 +20,7 @@ int launch_qkv_finish(const float* partial, int n_planes, long long plane_stride
                       __nv_bfloat16* kv_layer, int M, int Hq, int Hkv, int dh, int page_tokens, cudaStream_t s);
 int launch_gather_rows_bf16_to_f32(const __nv_bfloat16* table, const __nv_bfloat16* other, const int* src_row, float* dst,
                                    long long rows, int H, cudaStream_t s);
-int launch_gather_rows_f32_to_bf16(const float* src, const int* idx, __nv_bfloat16* dst, int T, int S, int G, int D, cudaStream_t s);
+int launch_gather_rows_f32_to_bf16(const float* src, const int* idx, __nv_bfloat16* dst, int T, int S, int G, int D, int hilo, cudaStream_t s);
 int launch_tap_pool(const void* in, int in_dtype, void* out, int out_dtype, const int* tap_idx, const float* tap_w, int T,
                     int n_in, int n_out, int max_taps, int D, int maxpool, cudaStream_t s);
 int launch_heads(const float* hidden_f32, const int* rows, const float* head_w, float* logits_out, float* scores_out, int n_rows,
@@ -30,7 +30,7 @@ int launch_argmax(const float* partial, int n_planes, long long plane_stride, in
 int launch_splitk_finish_bf16(const float* partial, int n_planes, long long plane_stride, const float* bias,
                               __nv_bfloat16* out, long long rows, int N, int act, cudaStream_t s);
 
-int launch_vit_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int T, int S, int H, int dh, cudaStream_t s);
+int launch_vit_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int T, int S, int H, int dh, int split_hi_lo, cudaStream_t s);
 
 int kv_attention_pick_splits(int max_rows, int Hkv, int n_streams, int max_kv_len, int num_sms);
 int launch_kv_attention(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, const int* stream_desc, const int* block_tables,

@@ -41,10 +41,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int DH, int DPAD, int LDS>
+// SPLIT: the output row is [hi | lo] with hi = bf16(o) and lo = bf16(o - hi), so that the out-projection GEMM (run with
+// K doubled against [W | W]) consumes the attention output at ~16 mantissa bits.  Rounding o to a single bf16 is the
+// largest single contributor to the tower's deviation from the fp32 oracle (tools/noise_floor.py).
+template <int DH, int DPAD, int LDS, bool SPLIT>
 __global__ void __launch_bounds__(VA_THREADS, 2)
 vit_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int S, int H, float scale_log2e) {
-  // qkv: [T*S, 3*H*DH] rows = tokens, columns = [q | k | v], each [H, DH].  out: [T*S, H*DH].
+  // qkv: [T*S, 3*H*DH] rows = tokens, columns = [q | k | v], each [H, DH].  out: [T*S, H*DH] (or [T*S, 2*H*DH] if SPLIT).
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16* sK = sQ + VA_BM * LDS;
@@ -202,34 +205,43 @@ vit_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
   }
   const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
   const int r0 = q0 + warp * 16 + (lane >> 2), r1 = r0 + 8;
-  const int out_stride = H * DH;
+  const int out_stride = (SPLIT ? 2 : 1) * H * DH;
   __nv_bfloat16* ob = out + (long long)t * S * out_stride + h * DH;
+  auto store2 = [&](int r, int c, float a, float b) {
+    __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
+    *reinterpret_cast<__nv_bfloat162*>(ob + (long long)r * out_stride + c) = hi;
+    if (SPLIT) {
+      const float2 hf = __bfloat1622float2(hi);
+      *reinterpret_cast<__nv_bfloat162*>(ob + (long long)r * out_stride + H * DH + c) = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    }
+  };
 #pragma unroll
   for (int nt = 0; nt < NT_O; ++nt) {
     const int c = nt * 8 + (lane & 3) * 2;
     if (c < DH) {
-      if (r0 < S) *reinterpret_cast<uint32_t*>(ob + (long long)r0 * out_stride + c) = pack_bf16x2(o[nt][0] * inv0, o[nt][1] * inv0);
-      if (r1 < S) *reinterpret_cast<uint32_t*>(ob + (long long)r1 * out_stride + c) = pack_bf16x2(o[nt][2] * inv1, o[nt][3] * inv1);
+      if (r0 < S) store2(r0, c, o[nt][0] * inv0, o[nt][1] * inv0);
+      if (r1 < S) store2(r1, c, o[nt][2] * inv1, o[nt][3] * inv1);
     }
   }
 }
 
 }  // namespace
 
-int launch_vit_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int T, int S, int H, int dh, cudaStream_t s) {
+int launch_vit_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int T, int S, int H, int dh, int split_hi_lo, cudaStream_t s) {
   if (T <= 0) return 0;
   if (dh != 72) return -2;  // SigLIP-so400m head_dim; other sizes need another instantiation
   constexpr int DH = 72, DPAD = 80, LDS = 88;
   constexpr int SMEM = (VA_BM + 4 * VA_BN) * LDS * 2;
-  auto kern = vit_attention_kernel<DH, DPAD, LDS>;
   static bool attr = false;
   if (!attr) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return -4;
+    if (cudaFuncSetAttribute(vit_attention_kernel<DH, DPAD, LDS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return -4;
+    if (cudaFuncSetAttribute(vit_attention_kernel<DH, DPAD, LDS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return -4;
     attr = true;
   }
   dim3 grid((S + VA_BM - 1) / VA_BM, H, T);
   const float scale_log2e = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
-  kern<<<grid, VA_THREADS, SMEM, s>>>(qkv, out, S, H, scale_log2e);
+  if (split_hi_lo) vit_attention_kernel<DH, DPAD, LDS, true><<<grid, VA_THREADS, SMEM, s>>>(qkv, out, S, H, scale_log2e);
+  else vit_attention_kernel<DH, DPAD, LDS, false><<<grid, VA_THREADS, SMEM, s>>>(qkv, out, S, H, scale_log2e);
   return 0;
 }
 

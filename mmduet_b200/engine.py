@@ -63,7 +63,8 @@ class VisionEngine:
 
     MAX_BATCH = 32  # test/inference.py:208 encodes in batches of 32
 
-    def __init__(self, cfg: ModelConfig, state_dict, device, with_projector=True, n_layers=None, legacy_post_ln=False):
+    def __init__(self, cfg: ModelConfig, state_dict, device, with_projector=True, n_layers=None, legacy_post_ln=False,
+                 attn_out_split=True, projector_hilo=True):
         cfg.validate()
         self.cfg, self.device = cfg, torch.device(device)
         self.lib = _lib.load()
@@ -87,7 +88,9 @@ class VisionEngine:
             qkv_b = _f32(torch.cat([sd[p + f"self_attn.{n}_proj.bias"] for n in "qkv"], 0), dev)
             t = dict(ln1_w=_f32(sd[p + "layer_norm1.weight"], dev), ln1_b=_f32(sd[p + "layer_norm1.bias"], dev),
                      qkv_w=qkv_w, qkv_b=qkv_b,
-                     out_w=_bf16(sd[p + "self_attn.out_proj.weight"], dev), out_b=_f32(sd[p + "self_attn.out_proj.bias"], dev),
+                     out_w=(_bf16(torch.cat([sd[p + "self_attn.out_proj.weight"]] * 2, 1), dev) if attn_out_split
+                            else _bf16(sd[p + "self_attn.out_proj.weight"], dev)),
+                     out_b=_f32(sd[p + "self_attn.out_proj.bias"], dev),
                      ln2_w=_f32(sd[p + "layer_norm2.weight"], dev), ln2_b=_f32(sd[p + "layer_norm2.bias"], dev),
                      fc1_w=_bf16(sd[p + "mlp.fc1.weight"], dev), fc1_b=_f32(sd[p + "mlp.fc1.bias"], dev),
                      fc2_w=_bf16(sd[p + "mlp.fc2.weight"], dev), fc2_b=_f32(sd[p + "mlp.fc2.bias"], dev))
@@ -96,7 +99,7 @@ class VisionEngine:
             keep.append(t)
         self._layers = layers
         self.vit = _lib.VitWeights(image_size=cfg.image_size, patch_size=P, dim=D, heads=cfg.vit_heads, mlp=cfg.vit_mlp,
-                                   n_layers=self.n_layers, k_pad=self.k_pad, patch_w=pw.data_ptr(), patch_b=patch_b.data_ptr(),
+                                   n_layers=self.n_layers, k_pad=self.k_pad, attn_out_split=int(attn_out_split), patch_w=pw.data_ptr(), patch_b=patch_b.data_ptr(),
                                    pos_emb=pos.data_ptr(), layers=layers)
         self.post_ln = None
         if legacy_post_ln:
@@ -106,12 +109,14 @@ class VisionEngine:
             taps = pooling_taps(cfg.grid, cfg.pool_stride, cfg.pool_mode)
             gidx, tidx, tw, max_taps = taps_to_tables(taps)
             self.tokens_per_frame = taps.shape[0]
-            t = dict(w1=_bf16(sd["model.mm_projector.0.weight"], dev), b1=_f32(sd["model.mm_projector.0.bias"], dev),
-                     w2=_bf16(sd["model.mm_projector.2.weight"], dev), b2=_f32(sd["model.mm_projector.2.bias"], dev),
+            rep = 2 if projector_hilo else 1
+            t = dict(w1=_bf16(torch.cat([sd["model.mm_projector.0.weight"]] * rep, 1), dev), b1=_f32(sd["model.mm_projector.0.bias"], dev),
+                     w2=_bf16(torch.cat([sd["model.mm_projector.2.weight"]] * rep, 1), dev), b2=_f32(sd["model.mm_projector.2.bias"], dev),
                      gather_idx=gidx.to(dev), tap_idx=tidx.to(dev).contiguous(), tap_w=tw.to(dev).contiguous())
             keep.append(t)
             self.proj = _lib.ProjectorWeights(vit_dim=D, hidden=cfg.hidden, n_src_tokens=cfg.patches, n_gather=int(gidx.numel()),
                                               n_out=self.tokens_per_frame, max_taps=max_taps, maxpool=int(cfg.pool_mode == "max"),
+                                              hilo=int(projector_hilo),
                                               **{k: v.data_ptr() for k, v in t.items()})
         self._keep = keep
         self._ws = {}
@@ -150,8 +155,10 @@ class VisionEngine:
         _lib.check(rc, "mmd_vit_forward")
         return resid
 
-    def visual_embed(self, frames, normalize=False):
-        """frames [T,3,384,384] (already image-processed unless normalize=True) -> bf16 [T*tokens_per_frame, hidden]."""
+    def visual_embed(self, frames, normalize=False, out_dtype=torch.bfloat16):
+        """frames [T,3,384,384] (already image-processed unless normalize=True) -> [T*tokens_per_frame, hidden] in the model
+        dtype (bf16, what the reference returns) or in fp32 (the same values before the final rounding)."""
+        assert out_dtype in (torch.bfloat16, torch.float32)
         if self.proj is None:
             raise _lib.MmdError("this VisionEngine was built without the projector")
         outs = []
@@ -160,9 +167,10 @@ class VisionEngine:
             T = chunk.shape[0]
             resid = self.tower(chunk, normalize)
             ws, _ = self._workspace(T)
-            out = torch.empty(T * self.tokens_per_frame, self.cfg.hidden, dtype=torch.bfloat16, device=self.device)
-            rc = self.lib.mmd_projector_pool(self.ctx, ctypes.byref(self.proj), resid.data_ptr(), T, out.data_ptr(), ws.data_ptr(),
-                                             ws.numel(), _lib.stream_ptr())
+            out = torch.empty(T * self.tokens_per_frame, self.cfg.hidden, dtype=out_dtype, device=self.device)
+            rc = self.lib.mmd_projector_pool(self.ctx, ctypes.byref(self.proj), resid.data_ptr(), T, out.data_ptr(),
+                                             _lib.DT_BF16 if out_dtype == torch.bfloat16 else _lib.DT_F32, ws.data_ptr(), ws.numel(),
+                                             _lib.stream_ptr())
             _lib.check(rc, "mmd_projector_pool")
             outs.append(out)
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
