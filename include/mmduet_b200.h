@@ -208,6 +208,17 @@ MMD_API int64_t mmd_decoder_workspace_bytes(mmd_ctx*, const mmd_dec_weights*, in
 MMD_API int mmd_decoder_step(mmd_ctx*, const mmd_dec_weights*, const mmd_kv_pool*, const mmd_step*, void* workspace,
                              int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Measurement hooks (bench.py): kernels launched by the stage functions so far, and optional CUDA-event timing of
+ * named launch sites ("all" or a comma-separated list of mmd_profile_tag_name values) on the launching stream.
+ * mmd_profile_stop synchronises on the recorded events and fills ms_sum[tag] / counts[tag] (mmd_profile_num_tags long).
+ * ------------------------------------------------------------------------------------------------------------- */
+MMD_API unsigned long long mmd_launch_count(mmd_ctx*);
+MMD_API int mmd_profile_num_tags(void);
+MMD_API const char* mmd_profile_tag_name(int i);
+MMD_API int mmd_profile_start(mmd_ctx*, const char* tags_csv);
+MMD_API int mmd_profile_stop(mmd_ctx*, float* ms_sum, int* counts);
+
 #ifdef __cplusplus
 }
 #endif

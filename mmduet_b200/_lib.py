@@ -75,6 +75,11 @@ SIGNATURES = {
                               c_int64, c_void_p, c_void_p, c_int64, c_int, c_int64, c_void_p]),
     "mmd_gemm_splits": (c_int, [c_int64, c_int]),
     "mmd_num_sms": (c_int, [c_void_p]),
+    "mmd_launch_count": (ctypes.c_ulonglong, [c_void_p]),
+    "mmd_profile_num_tags": (c_int, []),
+    "mmd_profile_tag_name": (ctypes.c_char_p, [c_int]),
+    "mmd_profile_start": (c_int, [c_void_p, ctypes.c_char_p]),
+    "mmd_profile_stop": (c_int, [c_void_p, c_void_p, c_void_p]),
     "mmd_im2col": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mmd_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_float, c_void_p]),
     "mmd_vit_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
@@ -140,6 +145,24 @@ def context(device=None):
                 raise MmdError(f"mmd_create({device}) failed: {lib.mmd_last_error().decode()}")
             _ctx[device] = h
     return h
+
+
+def launch_count(device=None):
+    return int(load().mmd_launch_count(context(device)))
+
+
+def profile_start(tags="all", device=None):
+    check(load().mmd_profile_start(context(device), tags.encode()), "mmd_profile_start")
+
+
+def profile_stop(device=None):
+    """Returns {tag: (total_ms, launches)} for the tags that fired."""
+    lib = load()
+    n = lib.mmd_profile_num_tags()
+    ms = (ctypes.c_float * n)()
+    cnt = (ctypes.c_int * n)()
+    check(lib.mmd_profile_stop(context(device), ms, cnt), "mmd_profile_stop")
+    return {lib.mmd_profile_tag_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i] > 0}
 
 
 def stream_ptr():

@@ -4,7 +4,9 @@
 #include "gemm.cuh"
 #include "kernels.cuh"
 
+#include <cstring>
 #include <string>
+#include <vector>
 
 namespace {
 thread_local std::string g_err;
@@ -26,15 +28,59 @@ inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 }  // namespace
 
+// Launch sites of the three stage functions, by name: used for the launch counter and the optional per-stage CUDA-event
+// timing (mmd_profile_start / mmd_profile_stop) that bench.py uses for the roofline of the dominant kernel.
+static const char* const kTags[] = {
+    "im2col", "pos_emb", "patch_embed", "ln1", "qkv", "vit_attention", "out_proj", "ln2", "fc1", "fc2",
+    "gather", "proj.0+gelu", "proj.2", "tap_pool",
+    "embed/concat", "input_layernorm", "qkv_proj", "qkv_finish", "kv_attention", "o_proj", "post_attention_layernorm",
+    "gate_up_swiglu", "down_proj", "next_layernorm", "heads", "lm_head"};
+constexpr int kNumTags = sizeof(kTags) / sizeof(kTags[0]);
+static int tag_of(const char* name) {
+  for (int i = 0; i < kNumTags; ++i) if (strcmp(kTags[i], name) == 0) return i;
+  return -1;
+}
+
+struct ProfRec { int tag; cudaEvent_t a, b; };
 struct mmd_ctx {
   int device;
   int num_sms;
   mmd::GemmContext* gemm;
+  unsigned long long launches = 0;
+  bool prof_on = false;
+  unsigned long long prof_mask = 0;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  std::vector<ProfRec> recs;
+};
+
+struct ProfScope {
+  mmd_ctx* c; cudaStream_t s; cudaEvent_t b = nullptr;
+  ProfScope(mmd_ctx* c_, const char* name, cudaStream_t s_, int n_kernels) : c(c_), s(s_) {
+    c->launches += n_kernels;
+    if (!c->prof_on) return;
+    const int tag = tag_of(name);
+    if (tag < 0 || !((c->prof_mask >> tag) & 1ull)) return;
+    while (c->ev_pool.size() < c->ev_used + 2) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      c->ev_pool.push_back(e);
+    }
+    cudaEvent_t a = c->ev_pool[c->ev_used++];
+    b = c->ev_pool[c->ev_used++];
+    cudaEventRecord(a, s);
+    c->recs.push_back({tag, a, b});
+  }
+  ~ProfScope() { if (b) cudaEventRecord(b, s); }
 };
 
 #define CHECK_CTX(c) do { if ((c) == nullptr) return fail(MMD_ERR_ARG, "null context"); } while (0)
 #define RUN(expr, what) do { int rc_ = (expr); if (rc_ != 0) return fail(rc_, std::string(what) + ": " + mmd::gemm_last_error()); } while (0)
 #define RUNK(expr, what) do { int rc_ = (expr); if (rc_ != 0) return fail(rc_, std::string(what) + ": bad arguments"); } while (0)
+// stage-function variants: count the launch and time it when profiling is on (needs `c` and `s` in scope)
+#define PRUN(expr, what) do { ProfScope ps_(c, what, s, 1); int rc_ = (expr); if (rc_ != 0) return fail(rc_, std::string(what) + ": " + mmd::gemm_last_error()); } while (0)
+#define PRUNK(expr, what) do { ProfScope ps_(c, what, s, 1); int rc_ = (expr); if (rc_ != 0) return fail(rc_, std::string(what) + ": bad arguments"); } while (0)
+#define PRUNK2(expr, what) do { ProfScope ps_(c, what, s, 2); int rc_ = (expr); if (rc_ != 0) return fail(rc_, std::string(what) + ": bad arguments"); } while (0)
 
 static int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -244,23 +290,23 @@ int mmd_vit_forward(mmd_ctx* c, const mmd_vit_weights* w, const void* pixels, in
   const int M = T * Sg, D = w->dim;
   const float eps = 1e-6f;
   // embeddings: resid = pos_emb (broadcast) ; resid += im2col(pixels) @ patch_w^T + patch_b
-  RUNK(mmd::launch_im2col(pixels, px_dtype, normalize, buf.h, T, 3, w->image_size, w->patch_size, w->k_pad, s), "im2col");
-  RUNK(mmd::launch_broadcast_rows(w->pos_emb, resid_out, M, Sg, D, s), "pos_emb");
-  RUN(gemm_normal(c, buf.h, M, w->patch_w, D, w->k_pad, w->k_pad, mmd::EPI_RESID_F32, 0, w->patch_b, resid_out, D, s), "patch_embed");
+  PRUNK(mmd::launch_im2col(pixels, px_dtype, normalize, buf.h, T, 3, w->image_size, w->patch_size, w->k_pad, s), "im2col");
+  PRUNK(mmd::launch_broadcast_rows(w->pos_emb, resid_out, M, Sg, D, s), "pos_emb");
+  PRUN(gemm_normal(c, buf.h, M, w->patch_w, D, w->k_pad, w->k_pad, mmd::EPI_RESID_F32, 0, w->patch_b, resid_out, D, s), "patch_embed");
   for (int l = 0; l < w->n_layers; ++l) {
     const mmd_vit_layer& L = w->layers[l];
-    RUNK(mmd::launch_layernorm(resid_out, L.ln1_w, L.ln1_b, buf.x, 0, M, D, eps, s), "ln1");
-    RUN(gemm_normal(c, buf.x, M, L.qkv_w, 3 * D, D, D, mmd::EPI_BF16, mmd::ACT_NONE, L.qkv_b, buf.qkv, 3 * D, s), "qkv");
+    PRUNK(mmd::launch_layernorm(resid_out, L.ln1_w, L.ln1_b, buf.x, 0, M, D, eps, s), "ln1");
+    PRUN(gemm_normal(c, buf.x, M, L.qkv_w, 3 * D, D, D, mmd::EPI_BF16, mmd::ACT_NONE, L.qkv_b, buf.qkv, 3 * D, s), "qkv");
     if (w->attn_out_split) {  // out_w is [dim, 2*dim] = [W | W]; the attention output is [hi | lo]
-      RUNK(mmd::launch_vit_attention(buf.qkv, buf.h, T, Sg, w->heads, D / w->heads, 1, s), "vit_attention (head_dim must be 72)");
-      RUN(gemm_normal(c, buf.h, M, L.out_w, D, 2 * D, 2 * D, mmd::EPI_RESID_F32, 0, L.out_b, resid_out, D, s), "out_proj");
+      PRUNK(mmd::launch_vit_attention(buf.qkv, buf.h, T, Sg, w->heads, D / w->heads, 1, s), "vit_attention");
+      PRUN(gemm_normal(c, buf.h, M, L.out_w, D, 2 * D, 2 * D, mmd::EPI_RESID_F32, 0, L.out_b, resid_out, D, s), "out_proj");
     } else {
-      RUNK(mmd::launch_vit_attention(buf.qkv, buf.x, T, Sg, w->heads, D / w->heads, 0, s), "vit_attention (head_dim must be 72)");
-      RUN(gemm_normal(c, buf.x, M, L.out_w, D, D, D, mmd::EPI_RESID_F32, 0, L.out_b, resid_out, D, s), "out_proj");
+      PRUNK(mmd::launch_vit_attention(buf.qkv, buf.x, T, Sg, w->heads, D / w->heads, 0, s), "vit_attention");
+      PRUN(gemm_normal(c, buf.x, M, L.out_w, D, D, D, mmd::EPI_RESID_F32, 0, L.out_b, resid_out, D, s), "out_proj");
     }
-    RUNK(mmd::launch_layernorm(resid_out, L.ln2_w, L.ln2_b, buf.x, 0, M, D, eps, s), "ln2");
-    RUN(gemm_normal(c, buf.x, M, L.fc1_w, w->mlp, D, D, mmd::EPI_BF16, mmd::ACT_GELU_TANH, L.fc1_b, buf.h, w->mlp, s), "fc1");
-    RUN(gemm_normal(c, buf.h, M, L.fc2_w, D, w->mlp, w->mlp, mmd::EPI_RESID_F32, 0, L.fc2_b, resid_out, D, s), "fc2");
+    PRUNK(mmd::launch_layernorm(resid_out, L.ln2_w, L.ln2_b, buf.x, 0, M, D, eps, s), "ln2");
+    PRUN(gemm_normal(c, buf.x, M, L.fc1_w, w->mlp, D, D, mmd::EPI_BF16, mmd::ACT_GELU_TANH, L.fc1_b, buf.h, w->mlp, s), "fc1");
+    PRUN(gemm_normal(c, buf.h, M, L.fc2_w, D, w->mlp, w->mlp, mmd::EPI_RESID_F32, 0, L.fc2_b, resid_out, D, s), "fc2");
   }
   return check_launch("mmd_vit_forward");
 }
@@ -300,11 +346,11 @@ int mmd_projector_pool(mmd_ctx* c, const mmd_projector_weights* w, const float* 
   // Only the source tokens the pooling reads go through the projector (169 of 729 for bilinear 27->7).  With `hilo` the
   // GEMM operands are bf16 hi+lo pairs (K doubled against [W | W]), Linear2 keeps its fp32 accumulator and the pooling
   // combines in fp32: the frame tokens are rounded to bf16 exactly once, at the output.
-  RUNK(mmd::launch_gather_rows_f32_to_bf16(vit_resid, w->gather_idx, buf.g, T, w->n_src_tokens, w->n_gather, w->vit_dim, w->hilo, s), "gather");
-  RUN(gemm_normal(c, buf.g, Mg, w->w1, H, f * w->vit_dim, f * w->vit_dim, w->hilo ? mmd::EPI_BF16_HILO : mmd::EPI_BF16, mmd::ACT_GELU_ERF,
+  PRUNK(mmd::launch_gather_rows_f32_to_bf16(vit_resid, w->gather_idx, buf.g, T, w->n_src_tokens, w->n_gather, w->vit_dim, w->hilo, s), "gather");
+  PRUN(gemm_normal(c, buf.g, Mg, w->w1, H, f * w->vit_dim, f * w->vit_dim, w->hilo ? mmd::EPI_BF16_HILO : mmd::EPI_BF16, mmd::ACT_GELU_ERF,
                   w->b1, buf.a, f * H, s), "proj.0+gelu");
-  RUN(gemm_normal(c, buf.a, Mg, w->w2, H, f * H, f * H, mmd::EPI_F32, mmd::ACT_NONE, w->b2, buf.b, H, s), "proj.2");
-  RUNK(mmd::launch_tap_pool(buf.b, mmd::DT_F32, out, out_dtype == MMD_DT_F32 ? mmd::DT_F32 : mmd::DT_BF16, w->tap_idx, w->tap_w, T,
+  PRUN(gemm_normal(c, buf.a, Mg, w->w2, H, f * H, f * H, mmd::EPI_F32, mmd::ACT_NONE, w->b2, buf.b, H, s), "proj.2");
+  PRUNK(mmd::launch_tap_pool(buf.b, mmd::DT_F32, out, out_dtype == MMD_DT_F32 ? mmd::DT_F32 : mmd::DT_BF16, w->tap_idx, w->tap_w, T,
                             w->n_gather, w->n_out, w->max_taps, H, w->maxpool, s), "tap_pool");
   return check_launch("mmd_projector_pool");
 }
@@ -365,9 +411,9 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
   const int QD = Hq * dh, NQKV = (Hq + 2 * Hkv) * dh, I = w->mlp;
 
   // inputs_embeds = cat(embed_tokens(prefix ids), frame tokens) -> fp32 residual stream   (test/inference.py:235-238)
-  RUNK(mmd::launch_gather_rows_bf16_to_f32(static_cast<const __nv_bfloat16*>(w->embed), static_cast<const __nv_bfloat16*>(st->frame_tokens),
+  PRUNK(mmd::launch_gather_rows_bf16_to_f32(static_cast<const __nv_bfloat16*>(w->embed), static_cast<const __nv_bfloat16*>(st->frame_tokens),
                                            st->src_row, buf.resid, M, H, s), "embed/concat");
-  RUNK(mmd::launch_resid_add_rmsnorm(buf.resid, nullptr, 0, 0, w->layers[0].ln1_w, buf.x, nullptr, M, H, w->rms_eps, s), "input_layernorm");
+  PRUNK(mmd::launch_resid_add_rmsnorm(buf.resid, nullptr, 0, 0, w->layers[0].ln1_w, buf.x, nullptr, M, H, w->rms_eps, s), "input_layernorm");
   const int s_qkv = choose_splits(c->num_sms, NQKV, H, M);
   const int s_o = choose_splits(c->num_sms, H, QD, M);
   const int s_down = choose_splits(c->num_sms, H, I, M);
@@ -376,39 +422,82 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
   for (int l = 0; l < w->n_layers; ++l) {
     const mmd_dec_layer& L = w->layers[l];
     int eff = 1;
-    RUN(gemm_T_partials(c, buf.x, M, L.qkv_w, NQKV, H, s_qkv, buf.planes, s, &eff), "qkv_proj");
+    PRUN(gemm_T_partials(c, buf.x, M, L.qkv_w, NQKV, H, s_qkv, buf.planes, s, &eff), "qkv_proj");
     __nv_bfloat16* kv_layer = static_cast<__nv_bfloat16*>(pool->pool) + (int64_t)l * pool->layer_stride;
-    RUNK(mmd::launch_qkv_finish(buf.planes, eff, (int64_t)M * NQKV, L.qkv_b, w->rope_cos, w->rope_sin, st->tok_pos, st->tok_slot,
+    PRUNK(mmd::launch_qkv_finish(buf.planes, eff, (int64_t)M * NQKV, L.qkv_b, w->rope_cos, w->rope_sin, st->tok_pos, st->tok_slot,
                                 buf.q, kv_layer, M, Hq, Hkv, dh, MMD_PAGE_TOKENS, s), "qkv_finish");
-    RUNK(mmd::launch_kv_attention(buf.q, kv_layer, st->stream_desc, st->block_tables, st->n_streams, st->max_n_q, M, buf.o_part,
+    PRUNK2(mmd::launch_kv_attention(buf.q, kv_layer, st->stream_desc, st->block_tables, st->n_streams, st->max_n_q, M, buf.o_part,
                                   buf.ml_part, buf.attn, Hq, Hkv, dh, MMD_PAGE_TOKENS, attn_splits, s), "kv_attention");
-    RUN(gemm_T_partials(c, buf.attn, M, L.o_w, H, QD, s_o, buf.planes, s, &eff), "o_proj");
-    RUNK(mmd::launch_resid_add_rmsnorm(buf.resid, buf.planes, eff, (int64_t)M * H, L.ln2_w, buf.x, nullptr, M, H, w->rms_eps, s),
+    PRUN(gemm_T_partials(c, buf.attn, M, L.o_w, H, QD, s_o, buf.planes, s, &eff), "o_proj");
+    PRUNK(mmd::launch_resid_add_rmsnorm(buf.resid, buf.planes, eff, (int64_t)M * H, L.ln2_w, buf.x, nullptr, M, H, w->rms_eps, s),
          "post_attention_layernorm");
     {
       mmd::GemmArgs a;
       a.X = static_cast<const __nv_bfloat16*>(L.gate_w); a.X2 = static_cast<const __nv_bfloat16*>(L.up_w);
       a.x_rows = I; a.ldx = H; a.Y = buf.x; a.y_rows = M; a.ldy = H; a.K = H;
       a.epi = mmd::EPI_T_SWIGLU; a.out = buf.h; a.ldo = I;
-      RUN(mmd::gemm_launch(c->gemm, a, s), "gate_up_swiglu");
+      PRUN(mmd::gemm_launch(c->gemm, a, s), "gate_up_swiglu");
     }
-    RUN(gemm_T_partials(c, buf.h, M, L.down_w, H, I, s_down, buf.planes, s, &eff), "down_proj");
+    PRUN(gemm_T_partials(c, buf.h, M, L.down_w, H, I, s_down, buf.planes, s, &eff), "down_proj");
     const bool last = (l + 1 == w->n_layers);
     const float* next_w = last ? w->final_norm_w : w->layers[l + 1].ln1_w;
-    RUNK(mmd::launch_resid_add_rmsnorm(buf.resid, buf.planes, eff, (int64_t)M * H, next_w, buf.x, last ? buf.hidden_f32 : nullptr, M,
+    PRUNK(mmd::launch_resid_add_rmsnorm(buf.resid, buf.planes, eff, (int64_t)M * H, next_w, buf.x, last ? buf.hidden_f32 : nullptr, M,
                                        H, w->rms_eps, s), "next_layernorm");
   }
   if (st->n_score_rows > 0) {
     if (st->score_rows == nullptr || st->head_logits_out == nullptr || st->scores_out == nullptr || w->heads_w == nullptr)
       return fail(MMD_ERR_ARG, "mmd_decoder_step: score rows requested without buffers");
-    RUNK(mmd::launch_heads(buf.hidden_f32, st->score_rows, w->heads_w, st->head_logits_out, st->scores_out, st->n_score_rows, H, s), "heads");
+    PRUNK(mmd::launch_heads(buf.hidden_f32, st->score_rows, w->heads_w, st->head_logits_out, st->scores_out, st->n_score_rows, H, s), "heads");
   }
   if (st->n_lm_rows > 0) {
     gather_rows_bf16_kernel<<<st->n_lm_rows, 128, 0, s>>>(buf.x, st->lm_rows, buf.lm_x, H / 8);
+    c->launches += 1;
     int eff = 1;
-    RUN(gemm_T_partials(c, buf.lm_x, st->n_lm_rows, w->lm_head, w->vocab, H, 1, st->lm_logits_out, s, &eff), "lm_head");
+    PRUN(gemm_T_partials(c, buf.lm_x, st->n_lm_rows, w->lm_head, w->vocab, H, 1, st->lm_logits_out, s, &eff), "lm_head");
   }
   return check_launch("mmd_decoder_step");
+}
+
+int mmd_profile_num_tags(void) { return kNumTags; }
+const char* mmd_profile_tag_name(int i) { return (i >= 0 && i < kNumTags) ? kTags[i] : ""; }
+unsigned long long mmd_launch_count(mmd_ctx* c) { return c ? c->launches : 0; }
+
+int mmd_profile_start(mmd_ctx* c, const char* tags_csv) {
+  CHECK_CTX(c);
+  c->prof_mask = 0;
+  std::string csv = tags_csv ? tags_csv : "all";
+  if (csv == "all") c->prof_mask = ~0ull;
+  else {
+    size_t pos = 0;
+    while (pos <= csv.size()) {
+      size_t e = csv.find(',', pos);
+      if (e == std::string::npos) e = csv.size();
+      const int t = tag_of(csv.substr(pos, e - pos).c_str());
+      if (t < 0) return fail(MMD_ERR_ARG, "mmd_profile_start: unknown tag " + csv.substr(pos, e - pos));
+      c->prof_mask |= 1ull << t;
+      pos = e + 1;
+    }
+  }
+  c->recs.clear();
+  c->ev_used = 0;
+  c->prof_on = true;
+  return 0;
+}
+
+int mmd_profile_stop(mmd_ctx* c, float* ms_sum, int* counts) {
+  CHECK_CTX(c);
+  c->prof_on = false;
+  for (int i = 0; i < kNumTags; ++i) { if (ms_sum) ms_sum[i] = 0.f; if (counts) counts[i] = 0; }
+  for (const ProfRec& r : c->recs) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return fail(MMD_ERR_CUDA, "mmd_profile_stop: event sync failed");
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) return fail(MMD_ERR_CUDA, "mmd_profile_stop: elapsed failed");
+    if (ms_sum) ms_sum[r.tag] += ms;
+    if (counts) counts[r.tag] += 1;
+  }
+  c->recs.clear();
+  c->ev_used = 0;
+  return 0;
 }
 
 }  // extern "C"

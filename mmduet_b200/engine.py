@@ -384,6 +384,8 @@ class DecoderEngine:
                 score_rows += [q_start + r for r in it["score_rows"]]
             if lm == "last":
                 lm_rows.append(q_start + n_q - 1)
+            elif lm == "all":
+                lm_rows += list(range(q_start, q_start + n_q))
             st.length = new_len
             views.append(CacheView(st, new_len))
             q_start += n_q
