@@ -3,7 +3,9 @@
 #include "../../include/mmduet_b200.h"
 #include "gemm.cuh"
 #include "kernels.cuh"
+#include "launch.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -47,6 +49,7 @@ struct mmd_ctx {
   int num_sms;
   mmd::GemmContext* gemm;
   unsigned long long launches = 0;
+  bool use_pdl = true;   // programmatic dependent launch across the decoder step's kernels (MMD_NO_PDL=1 disables)
   bool prof_on = false;
   unsigned long long prof_mask = 0;
   std::vector<cudaEvent_t> ev_pool;
@@ -128,6 +131,8 @@ static int gemm_normal(mmd_ctx* c, const void* act, int M, const void* w, int N,
 
 __global__ void gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict__ rows,
                                         __nv_bfloat16* __restrict__ dst, int H8) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint4* s = reinterpret_cast<const uint4*>(src + (long long)rows[blockIdx.x] * H8 * 8);
   uint4* d = reinterpret_cast<uint4*>(dst + (long long)blockIdx.x * H8 * 8);
   for (int c = threadIdx.x; c < H8; c += blockDim.x) d[c] = s[c];
@@ -152,6 +157,8 @@ mmd_ctx* mmd_create(int device) {
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
   c->gemm = g;
+  const char* no_pdl = getenv("MMD_NO_PDL");
+  c->use_pdl = !(no_pdl && no_pdl[0] == '1');
   return c;
 }
 
@@ -168,6 +175,7 @@ int mmd_gemm_bf16(mmd_ctx* c, int epi, int act, const void* X, const void* X2, i
                   int k_splits, int64_t split_stride, void* stream) {
   CHECK_CTX(c);
   mmd::GemmArgs a;
+  if (ldx < 0) { a.x_blocked = 1; ldx = K; }  // ldx = -1: X/X2 are tile-blocked weights (mmd_pack_blocked)
   a.X = static_cast<const __nv_bfloat16*>(X);
   a.X2 = static_cast<const __nv_bfloat16*>(X2);
   a.Y = static_cast<const __nv_bfloat16*>(Y);
@@ -410,6 +418,7 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
   const int H = w->hidden, Hq = w->q_heads, Hkv = w->kv_heads, dh = w->head_dim;
   const int QD = Hq * dh, NQKV = (Hq + 2 * Hkv) * dh, I = w->mlp;
 
+  struct PdlGuard { PdlGuard(bool on) { mmd::g_use_pdl = on; } ~PdlGuard() { mmd::g_use_pdl = false; } } pdl_guard(c->use_pdl);
   // inputs_embeds = cat(embed_tokens(prefix ids), frame tokens) -> fp32 residual stream   (test/inference.py:235-238)
   PRUNK(mmd::launch_gather_rows_bf16_to_f32(static_cast<const __nv_bfloat16*>(w->embed), static_cast<const __nv_bfloat16*>(st->frame_tokens),
                                            st->src_row, buf.resid, M, H, s), "embed/concat");
@@ -450,7 +459,7 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
     PRUNK(mmd::launch_heads(buf.hidden_f32, st->score_rows, w->heads_w, st->head_logits_out, st->scores_out, st->n_score_rows, H, s), "heads");
   }
   if (st->n_lm_rows > 0) {
-    gather_rows_bf16_kernel<<<st->n_lm_rows, 128, 0, s>>>(buf.x, st->lm_rows, buf.lm_x, H / 8);
+    mmd::launch_k(gather_rows_bf16_kernel, dim3(st->n_lm_rows), dim3(128), 0, s, (const __nv_bfloat16*)buf.x, st->lm_rows, buf.lm_x, H / 8);
     c->launches += 1;
     int eff = 1;
     PRUN(gemm_T_partials(c, buf.lm_x, st->n_lm_rows, w->lm_head, w->vocab, H, 1, st->lm_logits_out, s, &eff), "lm_head");

@@ -3,11 +3,21 @@
 // RMSNorm), row gathers, tap pooling (bilinear / average / max), final norm + score heads, argmax.
 // All of them are HBM/latency-bound: 16-B vectorised, coalesced accesses, warp-shuffle reductions.
 #include "kernels.cuh"
+#include "launch.cuh"
 
 #include <cuda_bf16.h>
 #include <math.h>
 
 namespace mmd {
+
+thread_local bool g_use_pdl = false;
+
+// programmatic dependent launch (see ptx.cuh): let the next kernel start its prologue / weight prefetch, then wait for
+// the producers of our inputs.  Both are no-ops for kernels launched without the attribute.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -174,6 +184,7 @@ __global__ void resid_add_rmsnorm_kernel(float* __restrict__ resid, const float*
                                          float* __restrict__ out_f32, int H, float eps) {
   extern __shared__ float row_sh[];  // H floats
   __shared__ float red[NT / 32];
+  pdl_prologue();
   const long long row = blockIdx.x;
   const int H4 = H >> 2;
   float ss = 0.f;
@@ -207,8 +218,8 @@ int launch_resid_add_rmsnorm(float* resid, const float* partial, int n_planes, l
                              __nv_bfloat16* out_bf16, float* out_f32, long long rows, int H, float eps, cudaStream_t s) {
   if (H % 4 != 0 || rows <= 0) return rows == 0 ? 0 : -2;
   constexpr int NT = 256;
-  resid_add_rmsnorm_kernel<NT><<<(unsigned)rows, NT, H * sizeof(float), s>>>(resid, partial, n_planes, plane_stride, w,
-                                                                           out_bf16, out_f32, H, eps);
+  launch_k(resid_add_rmsnorm_kernel<NT>, dim3((unsigned)rows), dim3(NT), H * sizeof(float), s, resid, partial, n_planes,
+           plane_stride, w, out_bf16, out_f32, H, eps);
   return 0;
 }
 
@@ -224,6 +235,7 @@ __global__ void qkv_finish_kernel(const float* __restrict__ partial, int n_plane
                                   const int* __restrict__ tok_slot, __nv_bfloat16* __restrict__ q_out,
                                   __nv_bfloat16* __restrict__ kv_layer, int Hq, int Hkv, int dh, int page_tokens) {
   // grid: (token, head) with head in [0, Hq + 2*Hkv); block: dh/2 threads, thread d handles the pair (d, d + dh/2)
+  pdl_prologue();
   const int tok = blockIdx.x;
   const int head = blockIdx.y;
   const int d = threadIdx.x;
@@ -264,8 +276,8 @@ int launch_qkv_finish(const float* partial, int n_planes, long long plane_stride
   if (M <= 0) return 0;
   if (dh % 2 || dh / 2 > 1024) return -2;
   dim3 grid(M, Hq + 2 * Hkv);
-  qkv_finish_kernel<<<grid, dh / 2, 0, s>>>(partial, n_planes, plane_stride, bias, cos_tab, sin_tab, tok_pos, tok_slot, q_out,
-                                           kv_layer, Hq, Hkv, dh, page_tokens);
+  launch_k(qkv_finish_kernel, grid, dim3(dh / 2), 0, s, partial, n_planes, plane_stride, bias, cos_tab, sin_tab, tok_pos, tok_slot,
+           q_out, kv_layer, Hq, Hkv, dh, page_tokens);
   return 0;
 }
 
@@ -276,6 +288,7 @@ int launch_qkv_finish(const float* partial, int n_planes, long long plane_stride
 // ------------------------------------------------------------------------------------------------------------
 __global__ void gather_rows_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ table, const __nv_bfloat16* __restrict__ other,
                                                const int* __restrict__ src_row, float* __restrict__ dst, int H8) {
+  pdl_prologue();
   const long long row = blockIdx.x;
   const int sr = src_row[row];
   const uint4* src = reinterpret_cast<const uint4*>(sr >= 0 ? table + (long long)sr * H8 * 8 : other + (long long)(-(sr + 1)) * H8 * 8);
@@ -293,7 +306,7 @@ int launch_gather_rows_bf16_to_f32(const __nv_bfloat16* table, const __nv_bfloat
                                    long long rows, int H, cudaStream_t s) {
   if (H % 8) return -2;
   if (rows <= 0) return 0;
-  gather_rows_bf16_to_f32_kernel<<<(unsigned)rows, 128, 0, s>>>(table, other, src_row, dst, H / 8);
+  launch_k(gather_rows_bf16_to_f32_kernel, dim3((unsigned)rows), dim3(128), 0, s, table, other, src_row, dst, H / 8);
   return 0;
 }
 
@@ -382,6 +395,7 @@ int launch_tap_pool(const void* in, int in_dtype, void* out, int out_dtype, cons
 __global__ void heads_kernel(const float* __restrict__ hidden_f32, const int* __restrict__ rows, const float* __restrict__ head_w,
                              float* __restrict__ logits_out, float* __restrict__ scores_out, int H) {
   __shared__ float red[4][8];
+  pdl_prologue();
   const int r = blockIdx.x;
   const float* h = hidden_f32 + (long long)rows[r] * H;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -412,7 +426,7 @@ __global__ void heads_kernel(const float* __restrict__ hidden_f32, const int* __
 int launch_heads(const float* hidden_f32, const int* rows, const float* head_w, float* logits_out, float* scores_out, int n_rows,
                  int H, cudaStream_t s) {
   if (n_rows <= 0) return 0;
-  heads_kernel<<<n_rows, 256, 0, s>>>(hidden_f32, rows, head_w, logits_out, scores_out, H);
+  launch_k(heads_kernel, dim3(n_rows), dim3(256), 0, s, hidden_f32, rows, head_w, logits_out, scores_out, H);
   return 0;
 }
 

@@ -10,6 +10,7 @@
 //   Qwen2 q/k/v/o/gate/up/down (video_head_live_llava_qwen.py:141-150).
 #include "gemm.cuh"
 #include "ptx.cuh"
+#include "launch.cuh"
 
 #include <mutex>
 #include <string>
@@ -36,6 +37,8 @@ struct GemmKernelParams {
   void* out;
   long long ldo;
   long long split_stride;
+  int pdl_prefetch_x;   // X operand (weights, swap-AB) may be loaded before griddepcontrol.wait
+  int x_blocked;        // X/X2 tensor maps are 4-D over the tile-blocked weight layout
 };
 
 template <int BN, bool DUAL>
@@ -80,6 +83,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     const __grid_constant__ CUtensorMap tmY, const GemmKernelParams p) {
   using Cfg = GemmCfg<BN, DUAL>;
   constexpr int STAGES = Cfg::STAGES;
+  // swap-AB: X holds the weights.  Token tiles (y) are then the fastest-varying tile index, so the CTAs that share a
+  // weight tile run at the same time and the second reader hits L2 instead of streaming the weights twice from HBM.
+  constexpr bool kWeightsOnX = (EPI == EPI_T_F32 || EPI == EPI_T_SWIGLU);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
@@ -114,26 +120,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
+  griddep_launch_dependents();
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int ks = tile % p.k_splits;
-        const int rest = tile / p.k_splits;
-        const int xt = rest % p.x_tiles, yt = rest / p.x_tiles;
-        const int kb0 = ks * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t sX = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sY = sX + Cfg::X_BYTES * (DUAL ? 2 : 1);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-          tma_load_2d(sX, &tmX, full_bar(stage), kb * BK, xt * BM);
-          if constexpr (DUAL) tma_load_2d(sX + Cfg::X_BYTES, &tmX2, full_bar(stage), kb * BK, xt * BM);
-          tma_load_2d(sY, &tmY, full_bar(stage), kb * BK, yt * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      // k-block iterator over this CTA's tiles
+      int tile = blockIdx.x, kb = 0, kb1 = 0, xt = 0, yt = 0;
+      auto load_tile = [&]() {
+        if (tile < total_tiles) {
+          const int ks = tile % p.k_splits;
+          const int rest = tile / p.k_splits;
+          if constexpr (kWeightsOnX) { yt = rest % p.y_tiles; xt = rest / p.y_tiles; }
+          else { xt = rest % p.x_tiles; yt = rest / p.x_tiles; }
+          kb = ks * p.kb_per_split;
+          kb1 = min(p.kb_total, kb + p.kb_per_split);
         }
+      };
+      auto advance = [&]() {
+        if (++kb >= kb1) { tile += gridDim.x; load_tile(); }
+      };
+      load_tile();
+      auto load_x = [&](const CUtensorMap* m, uint32_t dst, uint32_t bar) {
+        if (p.x_blocked) tma_load_4d(dst, m, bar, 0, 0, kb, xt);
+        else tma_load_2d(dst, m, bar, kb * BK, xt * BM);
+      };
+      uint32_t stage = 0, phase = 0;
+      if (p.pdl_prefetch_x) {
+        // Programmatic dependent launch: the X operand (weights) does not depend on the preceding kernels, so the first
+        // ring of stages streams weight tiles from HBM while those kernels are still running; the Y operand
+        // (activations) is loaded only after griddepcontrol.wait.
+        int pre_kb[STAGES], pre_yt[STAGES];
+        int n_pre = 0;
+        while (tile < total_tiles && n_pre < STAGES) {
+          const uint32_t sX = smem_base + n_pre * Cfg::STAGE_BYTES;
+          mbar_arrive_expect_tx(full_bar(n_pre), Cfg::STAGE_BYTES);
+          load_x(&tmX, sX, full_bar(n_pre));
+          if constexpr (DUAL) load_x(&tmX2, sX + Cfg::X_BYTES, full_bar(n_pre));
+          pre_kb[n_pre] = kb; pre_yt[n_pre] = yt;
+          ++n_pre;
+          advance();
+        }
+        griddep_wait();
+        for (int i = 0; i < n_pre; ++i) {
+          const uint32_t sY = smem_base + i * Cfg::STAGE_BYTES + Cfg::X_BYTES * (DUAL ? 2 : 1);
+          tma_load_2d(sY, &tmY, full_bar(i), pre_kb[i] * BK, pre_yt[i] * BN);
+        }
+        if (n_pre == STAGES) { stage = 0; phase = 1; } else { stage = n_pre; phase = 0; }
+      } else {
+        griddep_wait();
+      }
+      while (tile < total_tiles) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sX = smem_base + stage * Cfg::STAGE_BYTES;
+        const uint32_t sY = sX + Cfg::X_BYTES * (DUAL ? 2 : 1);
+        mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+        load_x(&tmX, sX, full_bar(stage));
+        if constexpr (DUAL) load_x(&tmX2, sX + Cfg::X_BYTES, full_bar(stage));
+        tma_load_2d(sY, &tmY, full_bar(stage), kb * BK, yt * BN);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        advance();
       }
     }
     __syncwarp();
@@ -176,13 +221,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     __syncwarp();
   } else {
     // ===================== epilogue warps (TMEM -> registers -> global) =====================
+    griddep_wait();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int lane_row = q * 32 + (int)lane_id();
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int ks = tile % p.k_splits;
       const int rest = tile / p.k_splits;
-      const int xt = rest % p.x_tiles, yt = rest / p.x_tiles;
+      const int xt = kWeightsOnX ? rest / p.y_tiles : rest % p.x_tiles;
+      const int yt = kWeightsOnX ? rest % p.y_tiles : rest / p.x_tiles;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_COLS;
@@ -391,6 +438,40 @@ static int get_map(GemmContext* c, const void* ptr, int rows, int K, long long l
   return 0;
 }
 
+// 4-D map over tile-blocked weights [rows/128][K/64][128][64]: box {64,128,1,1} = one contiguous 16 KB tile.
+static int get_map_blocked(GemmContext* c, const void* ptr, int rows, int K, CUtensorMap* out) {
+  MapKey key{ptr, rows, K, -1, -1};
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto it = c->maps.find(key);
+    if (it != c->maps.end()) { *out = it->second; return 0; }
+  }
+  if (rows % BM != 0 || K % BK != 0 || (reinterpret_cast<uintptr_t>(ptr) & 127) != 0) {
+    g_gemm_err = "blocked weights need rows % 128 == 0, K % 64 == 0 and 128-B alignment";
+    return -2;
+  }
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)BK, (cuuint64_t)BM, (cuuint64_t)(K / BK), (cuuint64_t)(rows / BM)};
+  cuuint64_t strides[3] = {(cuuint64_t)BK * 2, (cuuint64_t)BK * BM * 2, (cuuint64_t)BK * BM * 2 * (cuuint64_t)(K / BK)};
+  cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)BM, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = c->encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(blocked) failed (%d) rows=%d K=%d", (int)r, rows, K);
+    g_gemm_err = buf;
+    return -3;
+  }
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->maps.emplace(key, m);
+  }
+  *out = m;
+  return 0;
+}
+
 int gemm_effective_splits(int K, int k_splits) {
   const int kb_total = (K + BK - 1) / BK;
   if (k_splits < 1) k_splits = 1;
@@ -411,9 +492,15 @@ static int launch_cfg(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
   }
   CUtensorMap tmX, tmX2, tmY;
   int rc;
-  if ((rc = get_map(c, a.X, a.x_rows, a.K, a.ldx, BM, &tmX)) != 0) return rc;
-  if (DUAL) { if ((rc = get_map(c, a.X2, a.x_rows, a.K, a.ldx, BM, &tmX2)) != 0) return rc; }
-  else tmX2 = tmX;
+  if (a.x_blocked) {
+    if ((rc = get_map_blocked(c, a.X, a.x_rows, a.K, &tmX)) != 0) return rc;
+    if (DUAL) { if ((rc = get_map_blocked(c, a.X2, a.x_rows, a.K, &tmX2)) != 0) return rc; }
+    else tmX2 = tmX;
+  } else {
+    if ((rc = get_map(c, a.X, a.x_rows, a.K, a.ldx, BM, &tmX)) != 0) return rc;
+    if (DUAL) { if ((rc = get_map(c, a.X2, a.x_rows, a.K, a.ldx, BM, &tmX2)) != 0) return rc; }
+    else tmX2 = tmX;
+  }
   if ((rc = get_map(c, a.Y, a.y_rows, a.K, a.ldy, BN, &tmY)) != 0) return rc;
 
   GemmKernelParams p;
@@ -429,8 +516,10 @@ static int launch_cfg(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
   int max_ctas = a.max_ctas > 0 ? a.max_ctas : c->num_sms;
   const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
   if (grid <= 0) return 0;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmX, tmX2, tmY, p);
-  cudaError_t e = cudaGetLastError();
+  p.x_blocked = a.x_blocked;
+  p.pdl_prefetch_x = (g_use_pdl && (EPI == EPI_T_F32 || EPI == EPI_T_SWIGLU)) ? 1 : 0;
+  cudaError_t e = launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmX, tmX2, tmY, p);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { g_gemm_err = std::string("gemm launch: ") + cudaGetErrorString(e); return -5; }
   return 0;
 }

@@ -26,6 +26,9 @@ struct GemmArgs {
   const __nv_bfloat16* X2 = nullptr;  // second lane operand (EPI_T_SWIGLU: up_proj rows), same shape as X
   const __nv_bfloat16* Y = nullptr;   // [y_rows, K], row stride ldy
   int x_rows = 0, y_rows = 0, K = 0;
+  // X (and X2) stored tile-blocked: [x_rows/128][K/64][128][64] bf16, i.e. every 128x64 operand tile is one contiguous
+  // 16 KB burst in HBM (needs x_rows % 128 == 0 and K % 64 == 0).  Static weights are packed this way once at load.
+  int x_blocked = 0;
   int64_t ldx = 0, ldy = 0;
   int epi = EPI_BF16, act = ACT_NONE;
   const float* bias = nullptr;        // may be null

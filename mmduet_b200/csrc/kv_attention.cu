@@ -10,6 +10,7 @@
 // Replaces SDPA / flash-attn-2 under Qwen2Attention (TF:models/qwen2/modeling_qwen2.py:187-246,
 // TF:integrations/sdpa_attention.py:41-104) and the O(L) torch.cat of DynamicCache.update (TF:cache_utils.py:119-120).
 #include "kernels.cuh"
+#include "launch.cuh"
 
 #include <cuda_bf16.h>
 #include <math.h>
@@ -58,6 +59,8 @@ kv_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __nv_bfloat16* sK = sQ + KA_BM * KA_LDS;
   __nv_bfloat16* sV = sK + 2 * KA_BN * KA_LDS;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int G = Hq / Hkv;
   const int kvh = blockIdx.x % Hkv, qt = blockIdx.x / Hkv;
@@ -239,6 +242,8 @@ kv_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __
 // out[tok, head*128 + d] = sum_s w_s O_s / sum_s w_s l_s,  w_s = 2^(m_s - max m)
 __global__ void kv_attention_combine_kernel(const float* __restrict__ o_part, const float* __restrict__ ml_part,
                                             __nv_bfloat16* __restrict__ out, int n_splits, long long part_stride_rows) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const long long grow = blockIdx.x;
   const int d = threadIdx.x;
   float mmax = -INFINITY;
@@ -284,9 +289,9 @@ int launch_kv_attention(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, c
   dim3 grid(q_tiles * Hkv, n_splits, n_streams);
   const float scale_log2e = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
   const long long part_rows = (long long)total_q * Hq;
-  kv_attention_kernel<<<grid, KA_THREADS, SMEM, s>>>(q, kv_layer, stream_desc, block_tables, o_part, ml_part, Hq, Hkv, n_splits,
-                                                    part_rows, scale_log2e);
-  kv_attention_combine_kernel<<<(unsigned)part_rows, KA_DH, 0, s>>>(o_part, ml_part, out, n_splits, part_rows);
+  launch_k(kv_attention_kernel, grid, dim3(KA_THREADS), SMEM, s, q, kv_layer, stream_desc, block_tables, o_part, ml_part, Hq, Hkv,
+           n_splits, part_rows, scale_log2e);
+  launch_k(kv_attention_combine_kernel, dim3((unsigned)part_rows), dim3(KA_DH), 0, s, o_part, ml_part, out, n_splits, part_rows);
   return 0;
 }
 

@@ -179,9 +179,79 @@ class LiveInferForBenchmark:
             need_response = True
         return need_response
 
+    # ---- multi-frame decoder passes (frames_per_step > 1) --------------------------------------------------------
+    # Causal attention makes a k-frame pass arithmetically identical to k single-frame steps (tests/test_oracle.py::
+    # test_chunked_frames_equal_stepwise), so the weights are streamed once per k frames.  The sequential decision rule is
+    # preserved: the heads are evaluated at every frame's last token, the first crossing frame j is found, the KV cache is
+    # rolled back to the end of frame j (O(1)) and the unconsumed frames return to the queue.
+    frames_per_step = 1
+
+    def _chunk_len(self):
+        k = min(self.frames_per_step, len(self.frame_embeds_queue))
+        if self.query_queue:
+            # a query is encoded before the first frame whose video_time >= query time (inference() step 1)
+            t_query = self.query_queue[0][0]
+            n = 0
+            while n < k and not (n > 0 and self.video_time + n / self.frame_fps >= t_query):
+                n += 1
+            k = max(n, 1)
+        return k
+
+    def _encode_frames_chunk(self, k):
+        frames = [self.frame_embeds_queue.popleft() for _ in range(k)]
+        if not self.past_key_values:
+            self.last_ids = self._start_ids
+        elif self.last_role == 'assistant' and not self.remove_assistant_turns:
+            self.last_ids = torch.cat([self.last_ids, self._added_stream_prompt_ids], dim=1)
+        else:
+            self.last_ids = torch.tensor([[]], device=self.device, dtype=torch.long)
+        prefix = self.last_ids.view(-1).tolist()
+        P, n = len(prefix), self.frame_num_tokens
+        past = self.past_key_values.length if self.past_key_values else 0
+        view = self.past_key_values if self.past_key_values else self.model.new_cache()
+        emb = torch.cat([f[1].view(-1, self.hidden_size) for f in frames], 0)
+        out = self.model.decoder.step([dict(storage=view.storage, past=view.length, ids=prefix, frames=emb,
+                                            score_rows=[P + n * (j + 1) - 1 for j in range(k)])], score="frame_ends")
+        self.past_key_values = out["views"][0]
+        scores = out["scores"].tolist()                               # one D2H read for the whole chunk
+        lens = [past + P + n * (j + 1) for j in range(k)]
+        return frames, scores, lens
+
+    @torch.no_grad()
+    def _inference_chunked(self, model_response_list):
+        from .engine import CacheView
+        while self.frame_embeds_queue:
+            with self._lock:
+                if self.query_queue and self.video_time >= self.query_queue[0][0]:
+                    self._encode_query()
+                k = self._chunk_len()
+                frames, scores, lens = self._encode_frames_chunk(k)
+                for j in range(k):
+                    self.frame_idx += 1
+                    self.num_frames_no_reply += 1
+                    self.last_role = 'stream'
+                    video_scores = {"informative_score": scores[j][0], "relevance_score": scores[j][1]}
+                    self.debug_data_list.append(dict(time=self.video_time, **video_scores))
+                    if self._decide(video_scores):
+                        if j + 1 < k:   # speculative frames j+1.. are undone: KV rollback + back to the queue
+                            self.past_key_values = CacheView(self.past_key_values.storage, lens[j])
+                            self.past_key_values.storage.truncate(lens[j])
+                            for f in reversed(frames[j + 1:]):
+                                self.frame_embeds_queue.appendleft(f)
+                        response = self._generate_response()
+                        model_response_list.append({'time': self.video_time, 'content': response, 'role': 'assistant'})
+                        self.num_frames_no_reply = 0
+                        self.consecutive_n_frames = 0
+                        self.video_time += 1 / self.frame_fps
+                        break
+                    self.video_time += 1 / self.frame_fps
+        return sorted(model_response_list, key=lambda x: x['time'])
+
     @torch.no_grad()
     def inference(self):
         model_response_list = [{'time': q[0], 'content': q[1], 'role': 'user'} for q in self.query_queue]
+        if self.frames_per_step > 1:
+            return self._inference_chunked(model_response_list)
         while self.frame_embeds_queue:
             with self._lock:
                 # 1. check if a user query is at current time

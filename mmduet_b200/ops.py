@@ -25,35 +25,52 @@ def gemm(x, w, *, bias=None, act=ACT_NONE, out=None, epi=EPI_BF16):
     return out
 
 
-def gemm_t_partials(x, w, k_splits, out=None):
-    """Swap-AB split-K: returns fp32 partial planes [splits, M, N] of x[M,K] @ w[N,K]^T."""
+def pack_blocked(w):
+    """[N,K] row-major weights -> tile-blocked [N/128][K/64][128][64] (every 128x64 operand tile contiguous, 16 KB)."""
+    N, K = w.shape
+    assert N % 128 == 0 and K % 64 == 0, (N, K)
+    return w.view(N // 128, 128, K // 64, 64).permute(0, 2, 1, 3).contiguous()
+
+
+def gemm_t_partials(x, w, k_splits, out=None, blocked_shape=None):
+    """Swap-AB split-K: returns fp32 partial planes [splits, M, N] of x[M,K] @ w[N,K]^T.
+    blocked_shape=(N,K): `w` is a pack_blocked() buffer."""
     _chk2d(x, torch.bfloat16)
-    _chk2d(w, torch.bfloat16)
     M, K = x.shape
-    N = w.shape[0]
+    if blocked_shape is not None:
+        N = blocked_shape[0]
+        assert blocked_shape[1] == K
+        ldw = -1
+    else:
+        _chk2d(w, torch.bfloat16)
+        N = w.shape[0]
+        ldw = w.stride(0)
     lib = _lib.load()
     splits = lib.mmd_gemm_splits(K, k_splits)
     if out is None:
         out = torch.empty(splits, M, N, device=x.device, dtype=torch.float32)
-    rc = lib.mmd_gemm_bf16(_lib.context(x.device.index), EPI_T_F32, ACT_NONE, w.data_ptr(), 0, N, w.stride(0),
+    rc = lib.mmd_gemm_bf16(_lib.context(x.device.index), EPI_T_F32, ACT_NONE, w.data_ptr(), 0, N, ldw,
                            x.data_ptr(), M, x.stride(0), K, 0, out.data_ptr(), out.stride(1), k_splits, out.stride(0),
                            _lib.stream_ptr())
     _lib.check(rc, "mmd_gemm_bf16(T_F32)")
     return out
 
 
-def gemm_t_swiglu(x, w_gate, w_up, out=None):
+def gemm_t_swiglu(x, w_gate, w_up, out=None, blocked_shape=None):
     """Swap-AB fused SwiGLU: out[M,N] = silu(x @ w_gate^T) * (x @ w_up^T), bf16."""
     _chk2d(x, torch.bfloat16)
-    _chk2d(w_gate, torch.bfloat16)
-    _chk2d(w_up, torch.bfloat16)
     M, K = x.shape
-    N = w_gate.shape[0]
+    if blocked_shape is not None:
+        N, ldw = blocked_shape[0], -1
+    else:
+        _chk2d(w_gate, torch.bfloat16)
+        _chk2d(w_up, torch.bfloat16)
+        N, ldw = w_gate.shape[0], w_gate.stride(0)
     if out is None:
         out = torch.empty(M, N, device=x.device, dtype=torch.bfloat16)
     lib = _lib.load()
     rc = lib.mmd_gemm_bf16(_lib.context(x.device.index), EPI_T_SWIGLU, ACT_NONE, w_gate.data_ptr(), w_up.data_ptr(), N,
-                           w_gate.stride(0), x.data_ptr(), M, x.stride(0), K, 0, out.data_ptr(), out.stride(0), 1, 0,
+                           ldw, x.data_ptr(), M, x.stride(0), K, 0, out.data_ptr(), out.stride(0), 1, 0,
                            _lib.stream_ptr())
     _lib.check(rc, "mmd_gemm_bf16(T_SWIGLU)")
     return out

@@ -1,0 +1,146 @@
+"""GPU tests of the frame loop (host mirror of test/inference.py / demo/liveinfer.py over the CUDA model) against the
+oracle's restatement of the same loop: per-frame scores, threshold-crossing frames, rollback, multi-frame passes."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import arch as A
+from oracle import restate as R
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def setup():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    torch.set_grad_enabled(False)
+    from mmduet_b200 import build_model_and_tokenizer
+    from mmduet_b200.config import ModelConfig
+    arch = A.SMALL
+    w = R.make_weights(arch, seed=91)
+    model, tok = build_model_and_tokenizer(state_dict=w, model_config=ModelConfig.from_any(arch), device="cuda:0", max_context=4096)
+    frames = R.synthetic_frames(14, seed=5)
+    return arch, w, model, tok, frames
+
+
+def _args(**kw):
+    from mmduet_b200.arguments_live import LiveTestArguments
+    return LiveTestArguments(frame_fps=2, system_prompt="a b c d e f", **kw)
+
+
+def _oracle_loop(arch, w, infer, frames, **kw):
+    loop = R.LiveLoopOracle(w, arch, start_ids=infer._start_ids.view(-1).tolist(),
+                            stream_prompt_ids=infer._added_stream_prompt_ids.view(-1).tolist(),
+                            stream_generation_ids=infer._added_stream_generation_ids.view(-1).tolist(),
+                            eos_token_id=infer.eos_token_id, frame_fps=2, max_new_tokens=infer.inplace_output_ids.shape[1], **kw)
+    loop.input_video_stream(R.preprocess_frames(frames).bfloat16().float())
+    return loop
+
+
+def test_loop_matches_oracle_with_rollback(setup):
+    from mmduet_b200.inference import LiveInferForBenchmark
+    arch, w, model, tok, frames = setup
+    # 1) grounding-style probe: threshold 1 never generates (charades.sh:11); collect the oracle's scores
+    infer = LiveInferForBenchmark(_args(stream_end_prob_threshold=1.0), model=model, tokenizer=tok)
+    infer.inplace_output_ids = torch.zeros(1, 3, device=infer.device, dtype=torch.long)
+    infer.input_video_stream(frames)
+    assert infer.inference() == []
+    probe = _oracle_loop(arch, w, infer, frames, stream_end_prob_threshold=1.0)
+    assert probe.inference() == []
+    ref = np.array([[d["informative_score"], d["relevance_score"]] for d in probe.debug_data_list])
+    got = np.array([[d["informative_score"], d["relevance_score"]] for d in infer.debug_data_list])
+    assert [d["time"] for d in infer.debug_data_list] == [d["time"] for d in probe.debug_data_list]
+    err = np.abs(ref - got).max()
+    assert err < TOL, err
+    # 2) a threshold in the widest score gap: identical crossing frames, generation with rollback keeps the scores
+    s = np.sort(ref[:, 0])
+    j = int(np.argmax(s[1:] - s[:-1]))
+    thr = float((s[j] + s[j + 1]) / 2)
+    assert (s[j + 1] - s[j]) / 2 > err
+    infer2 = LiveInferForBenchmark(_args(stream_end_prob_threshold=thr, remove_assistant_turns=True), model=model, tokenizer=tok)
+    infer2.inplace_output_ids = torch.zeros(1, 3, device=infer2.device, dtype=torch.long)
+    infer2.input_video_stream(frames)
+    resp = infer2.inference()
+    loop2 = _oracle_loop(arch, w, infer2, frames, stream_end_prob_threshold=thr, remove_assistant_turns=True)
+    resp_ref = loop2.inference()
+    assert [r["time"] for r in resp] == [r["time"] for r in resp_ref]
+    assert len(resp) == int((ref[:, 0] > thr).sum()) > 0
+    got2 = np.array([[d["informative_score"], d["relevance_score"]] for d in infer2.debug_data_list])
+    assert np.abs(got2 - got).max() < 1e-6          # rollback: the context is untouched by the generated turns
+    # 3) running-sum mode (youcook2.sh:14) on both heads
+    kw = dict(stream_end_score_sum_threshold=1.3, score_heads="informative_score,relevance_score", remove_assistant_turns=True)
+    infer3 = LiveInferForBenchmark(_args(**kw), model=model, tokenizer=tok)
+    infer3.inplace_output_ids = torch.zeros(1, 2, device=infer3.device, dtype=torch.long)
+    infer3.input_video_stream(frames)
+    resp3 = infer3.inference()
+    # same rule applied to the oracle's scores (crossings may only differ if a running sum lands within err of the threshold)
+    acc, want, margin = 0.0, [], 1.0
+    for i, (a, b) in enumerate(ref):
+        acc += a + b
+        margin = min(margin, abs(acc - 1.3))
+        if acc > 1.3:
+            want.append(i / 2.0)
+            acc = 0.0
+    if margin > 20 * err:
+        assert [r["time"] for r in resp3] == want
+    with pytest.raises(ValueError):
+        LiveInferForBenchmark(_args(), model=model, tokenizer=tok)
+
+
+@pytest.mark.parametrize("keep_turns", [False, True])
+def test_multi_frame_passes_equal_single_frame_steps(setup, keep_turns):
+    from mmduet_b200.inference import LiveInferForBenchmark
+    arch, w, model, tok, frames = setup
+    runs = {}
+    for k in (1, 4, 5):
+        infer = LiveInferForBenchmark(_args(stream_end_prob_threshold=0.5, remove_assistant_turns=not keep_turns), model=model, tokenizer=tok)
+        infer.frames_per_step = k
+        infer.inplace_output_ids = torch.zeros(1, 3, device=infer.device, dtype=torch.long)
+        infer.input_video_stream(frames)
+        infer.input_query_stream([{"role": "user", "time": 1.6, "content": "what is happening now"}])
+        resp = infer.inference()
+        runs[k] = (resp, [(d["time"], d["informative_score"], d["relevance_score"]) for d in infer.debug_data_list],
+                   infer.past_key_values.length)
+    base = runs[1]
+    assert len(base[1]) == len(frames)
+    for k in (4, 5):
+        resp, dbg, L = runs[k]
+        assert [r["time"] for r in resp] == [r["time"] for r in base[0]]
+        assert [r["content"] for r in resp] == [r["content"] for r in base[0]]
+        assert L == base[2]
+        assert np.abs(np.array(dbg) - np.array(base[1])).max() < 5e-3
+
+
+def test_demo_one_frame_and_query(setup):
+    from mmduet_b200.inference import LiveInferForDemo
+    arch, w, model, tok, frames = setup
+    demo = LiveInferForDemo(_args(stream_end_prob_threshold=1.0), model=model, tokenizer=tok)
+    demo.input_video_stream(frames[:4])
+    r0 = demo.input_one_frame()
+    assert set(r0) == {"frame_idx", "time", "informative_score", "relevance_score", "response"} and r0["frame_idx"] == 1
+    L0 = demo.past_key_values.length
+    demo.encode_given_query("describe the scene")
+    assert demo.past_key_values.length > L0 and demo.last_role == "user" and demo.last_ids.shape == (1, 1)
+    r1 = demo.input_one_frame()
+    assert r1["frame_idx"] == 2 and r1["response"] is None and r1["time"] == 0.5
+
+
+def test_forward_surface_matches_reference_contract(setup):
+    arch, w, model, tok, frames = setup
+    emb = model.visual_embed(frames[:1].cuda())
+    assert emb.shape == (49, arch.hidden) and emb.dtype == torch.bfloat16
+    out = model(inputs_embeds=emb[None], use_cache=True, past_key_values=None, return_dict=True)
+    assert out.logits.shape == (1, 49, arch.vocab) and out.logits.dtype == torch.float32
+    assert out.informative_logits.shape == (1, 49, 2) and out.relevance_logits.shape == (1, 49, 2)
+    assert out.past_key_values.get_seq_length() == 49
+    wd = {k: v.cuda() for k, v in w.items()}
+    o = R.model_forward(wd, arch, emb.float(), R.KVCache(arch.layers), want_lm_logits=True)
+    assert (out.informative_logits[0] - o["informative_logits"]).abs().max() < 5e-2
+    assert (out.logits[0] - o["logits"]).abs().max() < 6e-2
+    ids = torch.tensor([[7, 8, 9]], device="cuda")
+    e = model.joint_embed(ids, None)
+    assert e.shape == (1, 3, arch.hidden)
+    out2 = model(inputs_embeds=e, past_key_values=out.past_key_values, use_cache=True, return_dict=True, logits_to_keep="last")
+    assert out2.past_key_values.get_seq_length() == 52 and out2.logits.shape == (1, 1, arch.vocab)
