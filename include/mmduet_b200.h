@@ -42,6 +42,10 @@ MMD_API const char* mmd_last_error(void);
 MMD_API mmd_ctx* mmd_create(int device);
 MMD_API void mmd_destroy(mmd_ctx*);
 MMD_API int mmd_num_sms(mmd_ctx*);
+/* Attention kernels: 0 (default, currently faster) = mma.sync flash attention (csrc/vit_attention.cu,
+ * csrc/kv_attention.cu); 1 = tcgen05.mma / TMEM flash attention (csrc/attn_tcgen05.cu).  Both are parity-tested.
+ * Process-wide. */
+MMD_API int mmd_set_attention_impl(int impl);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * GEMM (tcgen05.mma, TMA operands, TMEM accumulators) — every nn.Linear on the path.

@@ -170,6 +170,12 @@ void mmd_destroy(mmd_ctx* c) {
 
 int mmd_num_sms(mmd_ctx* c) { return c ? c->num_sms : 0; }
 
+int mmd_set_attention_impl(int impl) {
+  if (impl != 0 && impl != 1) return fail(MMD_ERR_ARG, "mmd_set_attention_impl: 0 (mma.sync) or 1 (tcgen05)");
+  mmd::g_attention_impl = impl;
+  return 0;
+}
+
 int mmd_gemm_bf16(mmd_ctx* c, int epi, int act, const void* X, const void* X2, int64_t x_rows, int64_t ldx,
                   const void* Y, int64_t y_rows, int64_t ldy, int64_t K, const float* bias, void* out, int64_t ldo,
                   int k_splits, int64_t split_stride, void* stream) {

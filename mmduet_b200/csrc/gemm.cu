@@ -26,7 +26,8 @@ const char* gemm_last_error() { return g_gemm_err.c_str(); }
 constexpr int BM = 128;        // UMMA M: TMEM lanes
 constexpr int BK = 64;         // bf16 elements per k-block = one 128-B swizzle row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..5 epilogue
+constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each draining half of the accumulator columns
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..9 epilogue
 constexpr int SMEM_BUDGET = 227 * 1024;
 
 struct GemmKernelParams {
@@ -47,12 +48,13 @@ struct GemmCfg {
   static constexpr int Y_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = X_BYTES * (DUAL ? 2 : 1) + Y_BYTES;
   static constexpr int ACC_COLS = BN * (DUAL ? 2 : 1);
-  static constexpr int TMEM_COLS = 2 * ACC_COLS;                   // double-buffered accumulator
+  static constexpr int TMEM_USED = 2 * ACC_COLS;                   // double-buffered accumulator
+  static constexpr int TMEM_COLS = TMEM_USED <= 32 ? 32 : TMEM_USED <= 64 ? 64 : TMEM_USED <= 128 ? 128 : TMEM_USED <= 256 ? 256 : 512;
   static constexpr int BAR_BYTES = 1024;
   static constexpr int STAGES_RAW = (SMEM_BUDGET - 1024 /*align slack*/ - BAR_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
-  static_assert(TMEM_COLS <= 512, "TMEM overflow");
+  static_assert(TMEM_USED <= 512, "TMEM overflow");
   static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
@@ -109,7 +111,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 32 * GEMM_EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -223,6 +225,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     // ===================== epilogue warps (TMEM -> registers -> global) =====================
     griddep_wait();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;                      // which half of the columns this warp drains
+    const int c_begin = chalf * (BN / 2), c_end = c_begin + BN / 2;
     const int lane_row = q * 32 + (int)lane_id();
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -240,7 +244,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         // normal orientation: lane = output row m, columns = n (contiguous in memory)
         const bool row_ok = xi < p.x_rows;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           if (y0 + c0 >= p.y_rows) break;  // warp-uniform
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_row + c0, v);
@@ -302,7 +306,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         const bool n_ok = xi < p.x_rows;
         float* plane = reinterpret_cast<float*>(p.out) + (long long)ks * p.split_stride;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
           if (y0 + c0 >= p.y_rows) break;
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_row + c0, v);
@@ -319,7 +323,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         const bool n_ok = xi < p.x_rows;
         __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int c0 = c_begin; c0 < c_end; c0 += 16) {
           if (y0 + c0 >= p.y_rows) break;
           uint32_t g[16], u[16];
           tmem_ld_32x32b_x16(t_row + c0, g);
@@ -528,6 +532,8 @@ template <int EPI, int ACT>
 static int launch_normal(GemmContext* c, const GemmArgs& a, cudaStream_t s) {
   if (a.y_rows % 8 != 0) { g_gemm_err = "normal-orientation GEMM needs N % 8 == 0"; return -2; }
   if (a.y_rows <= 128) return launch_cfg<128, false, EPI, ACT>(c, a, s);
+  // N = 1152 (SigLIP out_proj / fc2 / patch embed) tiles exactly by 192 and wastes 10% of the MMAs with 256-wide tiles
+  if (a.y_rows % 192 == 0 && a.y_rows % 256 != 0 && a.y_rows <= 1536) return launch_cfg<192, false, EPI, ACT>(c, a, s);
   return launch_cfg<256, false, EPI, ACT>(c, a, s);
 }
 

@@ -261,11 +261,18 @@ __global__ void kv_attention_combine_kernel(const float* __restrict__ o_part, co
 
 }  // namespace
 
+int g_attention_impl = 0;  // 0 = mma.sync kernels (currently the faster ones), 1 = tcgen05/TMEM kernels (attn_tcgen05.cu)
+
+int launch_kv_attention_tc_main(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, const int* stream_desc, const int* block_tables,
+                                int n_streams, int max_n_q, int total_q, float* o_part, float* ml_part, int Hq, int Hkv, int n_splits,
+                                cudaStream_t s);
+
 int kv_attention_pick_splits(int max_rows, int Hkv, int n_streams, int max_kv_len, int num_sms) {
   const int q_tiles = (max_rows + KA_BM - 1) / KA_BM;
   const int base = q_tiles * Hkv * n_streams;
   const int kv_tiles = (max_kv_len + KA_BN - 1) / KA_BN;
-  int splits = (2 * num_sms + base - 1) / base;
+  // mma.sync kernel: two CTAs per SM; tcgen05 kernel: one CTA per SM
+  int splits = ((g_attention_impl == 1 ? 1 : 2) * num_sms + base - 1) / base;
   const int max_by_work = (kv_tiles + 3) / 4;  // at least ~4 key tiles (256 keys) per split
   if (splits > max_by_work) splits = max_by_work;
   if (splits > 32) splits = 32;
@@ -289,8 +296,14 @@ int launch_kv_attention(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, c
   dim3 grid(q_tiles * Hkv, n_splits, n_streams);
   const float scale_log2e = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
   const long long part_rows = (long long)total_q * Hq;
-  launch_k(kv_attention_kernel, grid, dim3(KA_THREADS), SMEM, s, q, kv_layer, stream_desc, block_tables, o_part, ml_part, Hq, Hkv,
-           n_splits, part_rows, scale_log2e);
+  if (g_attention_impl == 1) {
+    const int rc = launch_kv_attention_tc_main(q, kv_layer, stream_desc, block_tables, n_streams, max_n_q, total_q, o_part, ml_part, Hq,
+                                               Hkv, n_splits, s);
+    if (rc != 0) return rc;
+  } else {
+    launch_k(kv_attention_kernel, grid, dim3(KA_THREADS), SMEM, s, q, kv_layer, stream_desc, block_tables, o_part, ml_part, Hq, Hkv,
+             n_splits, part_rows, scale_log2e);
+  }
   launch_k(kv_attention_combine_kernel, dim3((unsigned)part_rows), dim3(KA_DH), 0, s, o_part, ml_part, out, n_splits, part_rows);
   return 0;
 }

@@ -109,8 +109,16 @@ def test_layernorm(env, D):
     assert (out32 - ref).abs().max() < 1e-4
 
 
+@pytest.fixture(params=[0, 1], ids=["mma_sync", "tcgen05"])
+def attn_impl(env, request):
+    _lib, ops, lib, ctx = env
+    _lib.check(lib.mmd_set_attention_impl(request.param))
+    yield request.param
+    lib.mmd_set_attention_impl(0)
+
+
 @pytest.mark.parametrize("T,S,H", [(2, 729, 16), (1, 729, 4), (3, 100, 2), (1, 64, 2), (1, 129, 1)])
-def test_vit_attention(env, T, S, H):
+def test_vit_attention(env, attn_impl, T, S, H):
     _lib, ops, lib, ctx = env
     dh = 72
     torch.manual_seed(S)
@@ -162,7 +170,7 @@ def _rot(x, cos, sin):
     return x * c + torch.cat((-x[..., h:], x[..., :h]), -1) * s
 
 
-def test_qkv_finish_and_kv_attention(env):
+def test_qkv_finish_and_kv_attention(env, attn_impl):
     """Appends three chunks per stream (two streams with different histories) and checks Q, the pool contents and the
     attention output against a dense fp32 statement with a bottom-right causal mask."""
     _lib, ops, lib, ctx = env
