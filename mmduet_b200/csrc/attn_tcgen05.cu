@@ -1,20 +1,24 @@
 // Flash attention on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM) for sm_100a.
 //
-//   S = Q K^T   : UMMA 128 x 128 x 16, A = Q tile (smem, K-major), B = K tile (smem, K-major)      -> TMEM (double-buffered)
-//   O_j = P V   : UMMA 128 x DH  x 16, A = P tile (smem, K-major), B = V tile (smem, MN-major: the
-//                 same [key][d] image the loader writes for K, no transpose)                        -> TMEM
-//   softmax     : 4 warps, ONE THREAD PER QUERY ROW (TMEM lane): tcgen05.ld the row of S, running max / sum in
-//                 registers with no shuffles, P written to shared memory as bf16 in the 128-B-swizzled K-major layout,
-//                 O accumulated in fp32 registers (O_run = O_run * corr + O_j read back from TMEM).
+// One CTA owns TWO 128-row query tiles of the same head (ping-pong): while the softmax warps of one tile work on their
+// scores, the tensor pipe computes the other tile's products.  Keys/values stream in 64-key tiles shared by both.
+//
+//   S = Q K^T   : UMMA 128 x 64 x 16, A = Q tile (smem, K-major), B = K tile (smem, K-major)  -> TMEM, 2 buffers per q tile
+//   O += P V    : UMMA 128 x DH x 16, A = P tile (smem, K-major), B = V tile (smem, MN-major: the same [key][d] image
+//                 the loader writes for K, no transpose)                                        -> TMEM, accumulated there
+//   softmax     : 2 x 4 warps, ONE THREAD PER QUERY ROW (TMEM lane): tcgen05.ld the score row, running max/sum in
+//                 registers with no shuffles, P stored to shared memory as bf16 in the 128-B-swizzled K-major layout.
+//                 O stays in TMEM across tiles; it is rescaled (tcgen05.ld / st) only when the running maximum grows by
+//                 more than 2^8 ("lazy rescaling"), otherwise the stale maximum keeps serving as the exponent base.
 //   loaders     : 4 warps, 16-B cp.async into the swizzled operand layout (zero fill for rows past the end and for the
-//                 head-dim padding 72 -> 80), handed to the async proxy with fence.proxy.async + mbarrier.
+//                 head-dim padding 72 -> 80), two tiles in flight, handed over with fence.proxy.async + mbarrier.
 //   MMA         : one thread issues every tcgen05.mma and the tcgen05.commit that signals the mbarriers.
 //
 // Two front ends share the pipeline:
 //   * vit:   non-causal attention over the 729 patch tokens of a frame, packed qkv [T*S, 3*H*72]
 //            (TF:models/siglip/modeling_siglip.py:252-330), optional hi+lo output for the out-projection;
-//   * paged: KV-append attention of the Qwen2 decoder over the paged KV pool with GQA row stacking, bottom-right
-//            causal mask and split-KV partial outputs (TF:models/qwen2/modeling_qwen2.py:187-246).
+//   * paged: KV-append attention of the Qwen2 decoder over the paged KV pool (64-token pages = one key tile) with GQA row
+//            stacking, bottom-right causal mask and split-KV partial outputs (TF:models/qwen2/modeling_qwen2.py:187-246).
 #include "kernels.cuh"
 #include "launch.cuh"
 #include "ptx.cuh"
@@ -25,16 +29,22 @@ namespace mmd {
 
 namespace {
 
-constexpr int TA_BM = 128;        // query rows per CTA = TMEM lanes
-constexpr int TA_BN = 128;        // keys per tile
-constexpr int TA_REGION = TA_BM * 128;   // bytes of one 64-column (128-B wide) swizzled operand region with 128 rows
-constexpr int TA_SOFTMAX_WARPS = 4, TA_LOADER_WARPS = 4;
+constexpr int TA_BM = 128;                 // query rows per tile = TMEM lanes
+constexpr int TA_QT = 2;                   // query tiles per CTA
+constexpr int TA_BN = 64;                  // keys per tile
+constexpr int TA_QREGION = TA_BM * 128;    // one 64-column swizzled region of a 128-row operand (16 KB)
+constexpr int TA_KREGION = TA_BN * 128;    // same for a 64-row operand (8 KB)
+constexpr int TA_RING = 3;                 // K and V ring depth
+constexpr int TA_SOFTMAX_WARPS = 4 * TA_QT, TA_LOADER_WARPS = 4;
 constexpr int TA_THREADS = 32 * (TA_SOFTMAX_WARPS + TA_LOADER_WARPS + 1);
+constexpr int TA_TMEM_PER_Q = 256;         // S0 [0,64) S1 [64,128) O [128, 128+DHP)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // byte offset of 16-B chunk `c` (0..7) of row `r` inside a 128-B-swizzled K-major region (rows 128 B apart, 8-row
 // groups 1024 B apart): exactly the image TMA writes with CU_TENSOR_MAP_SWIZZLE_128B.
@@ -42,8 +52,8 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
-// smem descriptor, MN-major operand (here: V as [key][d], d contiguous), 128-B swizzle: LBO = distance between the
-// 64-element blocks along N (d), SBO = distance between 8-row groups along K (keys) = 1024 B.
+// smem descriptor, MN-major operand (V as [key][d], d contiguous), 128-B swizzle: LBO = distance between the 64-element
+// blocks along N (d), SBO = distance between 8-row groups along K (keys) = 1024 B.
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
@@ -56,20 +66,33 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_mn_b(uint32_t M, uint32_t N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-struct AttnSmem {  // offsets from the 1024-B aligned base
-  static constexpr int Q = 0;                       // 2 regions
-  static constexpr int P = Q + 2 * TA_REGION;       // 2 regions (keys 0-63 / 64-127)
-  static constexpr int K0 = P + 2 * TA_REGION;      // per stage: K (2 regions) + V (2 regions)
-  static constexpr int STAGE = 4 * TA_REGION;
-  static constexpr int BARS = K0 + 2 * STAGE;
-  static constexpr int TOTAL = BARS + 256 + 1024;   // + alignment slack
+struct AttnSmem {  // byte offsets from the 1024-B aligned base
+  static constexpr int Q = 0;                                   // [qi][2 regions]
+  static constexpr int P = Q + TA_QT * 2 * TA_QREGION;          // [qi][1 region: 64 keys]
+  static constexpr int K = P + TA_QT * TA_QREGION;              // ring of [2 regions]
+  static constexpr int V = K + TA_RING * 2 * TA_KREGION;
+  static constexpr int BARS = V + TA_RING * 2 * TA_KREGION;
+  static constexpr int TOTAL = BARS + 512 + 1024;               // barriers + alignment slack
 };
 
-enum { BAR_Q_FULL = 0, BAR_KV_FULL = 1, BAR_KV_EMPTY = 3, BAR_S_FULL = 5, BAR_S_EMPTY = 7, BAR_P_FULL = 9, BAR_P_EMPTY = 10,
-       BAR_O_FULL = 11, BAR_O_EMPTY = 12, BAR_COUNT = 13 };
+// barrier indices
+constexpr int BAR_Q_FULL = 0;
+constexpr int BAR_K_FULL = 1, BAR_K_EMPTY = BAR_K_FULL + TA_RING, BAR_V_FULL = BAR_K_EMPTY + TA_RING, BAR_V_EMPTY = BAR_V_FULL + TA_RING;
+constexpr int BAR_S_FULL = BAR_V_EMPTY + TA_RING;   // [qi][2]
+constexpr int BAR_S_EMPTY = BAR_S_FULL + 2 * TA_QT; // [qi][2]
+constexpr int BAR_P_FULL = BAR_S_EMPTY + 2 * TA_QT; // [qi]
+constexpr int BAR_O_FULL = BAR_P_FULL + TA_QT;      // [qi]
+constexpr int BAR_COUNT = BAR_O_FULL + TA_QT;
 
-// ---- problem descriptions (one per CTA) -------------------------------------------------------------------------
 struct VitAttnParams {
   const __nv_bfloat16* qkv;   // [T*S, 3*H*DH]
   __nv_bfloat16* out;         // [T*S, H*DH] or [T*S, 2*H*DH] (hi | lo)
@@ -89,8 +112,6 @@ struct PagedAttnParams {
   float scale_log2e;
 };
 
-// The tile loop shared by both front ends.  `Front` provides: n_tiles, loading of Q / K / V rows, the key limit of
-// every query row (masking) and the output stage.
 template <int DH, typename Front>
 __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base, uint32_t tmem_base) {
   constexpr int DHP = (DH + 15) / 16 * 16;      // head dim padded to the UMMA K/N granularity
@@ -104,129 +125,157 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
     // ======================= loaders =======================
     const int lt = threadIdx.x - 32 * TA_SOFTMAX_WARPS;      // 0..127
     constexpr int NL = 32 * TA_LOADER_WARPS;
-    // Q: 128 rows x CH chunks
-    for (int i = lt; i < TA_BM * CH; i += NL) {
-      const int r = i / CH, c = i % CH;
+    for (int i = lt; i < TA_QT * TA_BM * CH; i += NL) {
+      const int r = i / CH, c = i % CH;                      // r: row within the CTA's 256 query rows
       const __nv_bfloat16* src = fe.q_row(r);
-      cp_async16(smem_base + AttnSmem::Q + (c >> 3) * TA_REGION + sw128_off(r, c & 7), src ? src + c * 8 : fe.any_ptr(), src ? 16 : 0);
+      const uint32_t dst = smem_base + AttnSmem::Q + (r / TA_BM) * 2 * TA_QREGION + (c >> 3) * TA_QREGION + sw128_off(r % TA_BM, c & 7);
+      cp_async16(dst, src ? src + c * 8 : fe.any_ptr(), src ? 16 : 0);
     }
-    cp_async_wait_all();
-    fence_proxy_async_smem();
-    mbar_arrive(bar(BAR_Q_FULL));
+    cp_async_commit();
+    auto publish = [&](int j) {   // tile j's copies of this thread have landed
+      fence_proxy_async_smem();
+      mbar_arrive(bar(BAR_K_FULL + j % TA_RING));
+      mbar_arrive(bar(BAR_V_FULL + j % TA_RING));
+    };
     for (int j = 0; j < n_tiles; ++j) {
-      const int st = j & 1;
-      mbar_wait(bar(BAR_KV_EMPTY + st), ((j >> 1) & 1) ^ 1);
-      const uint32_t kb = smem_base + AttnSmem::K0 + st * AttnSmem::STAGE, vb = kb + 2 * TA_REGION;
+      const int st = j % TA_RING;
+      const uint32_t par = ((j / TA_RING) & 1) ^ 1;
+      mbar_wait(bar(BAR_K_EMPTY + st), par);
+      mbar_wait(bar(BAR_V_EMPTY + st), par);
+      const uint32_t kb = smem_base + AttnSmem::K + st * 2 * TA_KREGION, vb = smem_base + AttnSmem::V + st * 2 * TA_KREGION;
       for (int i = lt; i < TA_BN * CH; i += NL) {
         const int r = i / CH, c = i % CH;
         const __nv_bfloat16* ks = fe.k_row(j, r);
         const __nv_bfloat16* vs = fe.v_row(j, r);
-        const uint32_t off = (c >> 3) * TA_REGION + sw128_off(r, c & 7);
+        const uint32_t off = (c >> 3) * TA_KREGION + sw128_off(r, c & 7);
         cp_async16(kb + off, ks ? ks + c * 8 : fe.any_ptr(), ks ? 16 : 0);
         cp_async16(vb + off, vs ? vs + c * 8 : fe.any_ptr(), vs ? 16 : 0);
       }
-      cp_async_wait_all();
+      cp_async_commit();
+      if (j == 0) {            // Q (first group) has landed once at most one group (tile 0) is pending
+        cp_async_wait<1>();
+        fence_proxy_async_smem();
+        mbar_arrive(bar(BAR_Q_FULL));
+      } else {
+        cp_async_wait<1>();    // tile j-1 has landed, tile j may still be in flight
+        publish(j - 1);
+      }
+    }
+    cp_async_wait<0>();
+    if (n_tiles == 0) {
       fence_proxy_async_smem();
-      mbar_arrive(bar(BAR_KV_FULL + st));
+      mbar_arrive(bar(BAR_Q_FULL));
+    } else {
+      publish(n_tiles - 1);
     }
   } else if (warp == TA_SOFTMAX_WARPS + TA_LOADER_WARPS) {
     // ======================= MMA issuer =======================
     if (elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(TA_BM, TA_BN);
       constexpr uint32_t idesc_pv = umma_idesc_bf16_mn_b(TA_BM, DHP);
-      const uint32_t sQ = smem_base + AttnSmem::Q, sP = smem_base + AttnSmem::P;
-      auto issue_qk = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(bar(BAR_KV_FULL + st), (j >> 1) & 1);
-        mbar_wait(bar(BAR_S_EMPTY + st), ((j >> 1) & 1) ^ 1);
+      auto issue_qk = [&](int qi, int j) {
+        const int st = j % TA_RING, sb = j & 1;
+        mbar_wait(bar(BAR_K_FULL + st), (j / TA_RING) & 1);
+        mbar_wait(bar(BAR_S_EMPTY + qi * 2 + sb), ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t sK = smem_base + AttnSmem::K0 + st * AttnSmem::STAGE;
+        const uint32_t sQ = smem_base + AttnSmem::Q + qi * 2 * TA_QREGION;
+        const uint32_t sK = smem_base + AttnSmem::K + st * 2 * TA_KREGION;
 #pragma unroll
         for (int k = 0; k < DHP / 16; ++k) {
-          const uint64_t da = umma_desc_k_sw128(sQ + (k >> 2) * TA_REGION) + 2u * (k & 3);
-          const uint64_t db = umma_desc_k_sw128(sK + (k >> 2) * TA_REGION) + 2u * (k & 3);
-          umma_f16(tmem_base + st * TA_BN, da, db, idesc_qk, k > 0 ? 1u : 0u);
+          const uint64_t da = umma_desc_k_sw128(sQ + (k >> 2) * TA_QREGION) + 2u * (k & 3);
+          const uint64_t db = umma_desc_k_sw128(sK + (k >> 2) * TA_KREGION) + 2u * (k & 3);
+          umma_f16(tmem_base + qi * TA_TMEM_PER_Q + sb * TA_BN, da, db, idesc_qk, k > 0 ? 1u : 0u);
         }
-        umma_commit(bar(BAR_S_FULL + st));
+        umma_commit(bar(BAR_S_FULL + qi * 2 + sb));
+        if (qi == TA_QT - 1) umma_commit(bar(BAR_K_EMPTY + st));   // both q tiles have consumed K_j
       };
       mbar_wait(bar(BAR_Q_FULL), 0);
-      if (n_tiles > 0) issue_qk(0);
-      if (n_tiles > 1) issue_qk(1);
+      for (int j = 0; j < 2 && j < n_tiles; ++j)
+        for (int qi = 0; qi < TA_QT; ++qi) issue_qk(qi, j);
       for (int j = 0; j < n_tiles; ++j) {
-        const int st = j & 1;
-        mbar_wait(bar(BAR_P_FULL), j & 1);
-        mbar_wait(bar(BAR_O_EMPTY), (j & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t sV = smem_base + AttnSmem::K0 + st * AttnSmem::STAGE + 2 * TA_REGION;
+        const int st = j % TA_RING;
+        for (int qi = 0; qi < TA_QT; ++qi) {
+          mbar_wait(bar(BAR_P_FULL + qi), j & 1);
+          if (qi == 0) mbar_wait(bar(BAR_V_FULL + st), (j / TA_RING) & 1);
+          tc_fence_after();
+          const uint32_t sP = smem_base + AttnSmem::P + qi * TA_QREGION;
+          const uint32_t sV = smem_base + AttnSmem::V + st * 2 * TA_KREGION;
 #pragma unroll
-        for (int k = 0; k < TA_BN / 16; ++k) {
-          const uint64_t da = umma_desc_k_sw128(sP + (k >> 2) * TA_REGION) + 2u * (k & 3);
-          const uint64_t db = umma_desc_mn_sw128(sV, TA_REGION) + (uint64_t)((k * 2048) >> 4);
-          umma_f16(tmem_base + 2 * TA_BN, da, db, idesc_pv, k > 0 ? 1u : 0u);
+          for (int k = 0; k < TA_BN / 16; ++k) {
+            const uint64_t da = umma_desc_k_sw128(sP) + 2u * k;
+            const uint64_t db = umma_desc_mn_sw128(sV, TA_KREGION) + (uint64_t)((k * 2048) >> 4);
+            umma_f16(tmem_base + qi * TA_TMEM_PER_Q + 2 * TA_BN, da, db, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(bar(BAR_O_FULL + qi));
+          if (qi == TA_QT - 1) umma_commit(bar(BAR_V_EMPTY + st));
+          if (j + 2 < n_tiles) issue_qk(qi, j + 2);
         }
-        umma_commit(bar(BAR_O_FULL));
-        umma_commit(bar(BAR_P_EMPTY));
-        umma_commit(bar(BAR_KV_EMPTY + st));
-        if (j + 2 < n_tiles) issue_qk(j + 2);
       }
     }
     __syncwarp();
   } else {
-    // ======================= softmax: one thread per query row =======================
-    const int row = warp * 32 + lane;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    float o_run[DHP];
-#pragma unroll
-    for (int i = 0; i < DHP; ++i) o_run[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f, c_prev = 1.f;
-    const int key_lim = fe.key_limit(row);    // keys with index > key_lim are masked for this row
+    // ======================= softmax: one thread per query row, one warpgroup per query tile =======================
+    const int qi = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;                 // row within the query tile = TMEM lane
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + qi * TA_TMEM_PER_Q;
+    const uint32_t sP = smem_base + AttnSmem::P + qi * TA_QREGION;
+    float m_ref = -INFINITY, l_run = 0.f;
+    const int key_lim = fe.key_limit(qi * TA_BM + row);    // tile-local key indices > key_lim are masked for this row
     const float sl2 = fe.scale_log2e();
-    auto fold_o = [&](int j) {                // O_run = O_run * corr_j + O_j (O_j read from TMEM)
-      mbar_wait(bar(BAR_O_FULL), j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < DHP; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(t_row + 2 * TA_BN + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o_run[c0 + i] = fmaf(o_run[c0 + i], c_prev, __uint_as_float(v[i]));
-      }
-      tc_fence_before();
-      mbar_arrive(bar(BAR_O_EMPTY));
-    };
     for (int j = 0; j < n_tiles; ++j) {
-      const int st = j & 1;
-      mbar_wait(bar(BAR_S_FULL + st), (j >> 1) & 1);
+      const int sb = j & 1;
+      mbar_wait(bar(BAR_S_FULL + qi * 2 + sb), (j >> 1) & 1);
       tc_fence_after();
       const int k0 = j * TA_BN;
       const bool need_mask = k0 + TA_BN - 1 > key_lim;
-      // pass 1: row maximum
+      // pass 1: row maximum of this tile
       float mx = -INFINITY;
-#pragma unroll
-      for (int c0 = 0; c0 < TA_BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + st * TA_BN + c0, v);
+      {
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32b_x32(t_row + sb * TA_BN, v0);
+        tmem_ld_32x32b_x32(t_row + sb * TA_BN + 32, v1);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(v[i]);
-          if (need_mask && k0 + c0 + i > key_lim) s = -INFINITY;
-          mx = fmaxf(mx, s);
+          float a = __uint_as_float(v0[i]), b = __uint_as_float(v1[i]);
+          if (need_mask) {
+            if (k0 + i > key_lim) a = -INFINITY;
+            if (k0 + 32 + i > key_lim) b = -INFINITY;
+          }
+          mx = fmaxf(mx, fmaxf(a, b));
         }
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float corr = exp2f((m_run - m_use) * sl2);
-      const float msc = m_use * sl2;
-      // the P buffer is free once PV_{j-1} has completed
-      mbar_wait(bar(BAR_P_EMPTY), (j & 1) ^ 1);
+      // PV_{j-1} must have completed before P is overwritten or O is rescaled
+      if (j > 0) {
+        mbar_wait(bar(BAR_O_FULL + qi), (j - 1) & 1);
+        tc_fence_after();
+      }
+      const float m_new = fmaxf(m_ref, mx);
+      if (j == 0) {
+        m_ref = m_new;
+      } else if (m_new > m_ref && (m_ref == -INFINITY || (m_new - m_ref) * sl2 > 8.0f)) {
+        // lazy rescaling: O (TMEM) and l move to the new exponent base
+        const float f = (m_ref == -INFINITY) ? 0.f : exp2f((m_ref - m_new) * sl2);
+#pragma unroll
+        for (int c0 = 0; c0 < DHP; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_row + 2 * TA_BN + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+          tmem_st_32x32b_x16(t_row + 2 * TA_BN + c0, v);
+        }
+        tmem_st_wait();
+        l_run *= f;
+        m_ref = m_new;
+      }
+      const float msc = (m_ref == -INFINITY) ? 0.f : m_ref * sl2;
       // pass 2: probabilities -> bf16 P tile (swizzled K-major), row sum
       float rs = 0.f;
 #pragma unroll
       for (int c0 = 0; c0 < TA_BN; c0 += 32) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + st * TA_BN + c0, v);
+        tmem_ld_32x32b_x32(t_row + sb * TA_BN + c0, v);
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
@@ -242,24 +291,35 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {   // four 16-B chunks of this 32-column group
-          const int c = (c0 >> 3) + q;  // chunk index 0..15 along the keys
-          const uint32_t addr = smem_base + AttnSmem::P + (c >> 3) * TA_REGION + sw128_off(row, c & 7);
+        for (int q = 0; q < 4; ++q) {   // four 16-B chunks of this 32-key group
+          const uint32_t addr = sP + sw128_off(row, (c0 >> 3) + q);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]),
                        "r"(pk[4 * q + 3]) : "memory");
         }
       }
-      l_run = l_run * corr + rs;
+      l_run += rs;
       fence_proxy_async_smem();
-      mbar_arrive(bar(BAR_P_FULL));
       tc_fence_before();
-      mbar_arrive(bar(BAR_S_EMPTY + st));
-      if (j >= 1) fold_o(j - 1);
-      c_prev = corr;
-      m_run = m_new;
+      mbar_arrive(bar(BAR_P_FULL + qi));
+      mbar_arrive(bar(BAR_S_EMPTY + qi * 2 + sb));
     }
-    if (n_tiles > 0) fold_o(n_tiles - 1);
-    fe.store(row, o_run, m_run, l_run);
+    float o[DHP];
+    if (n_tiles > 0) {
+      mbar_wait(bar(BAR_O_FULL + qi), (n_tiles - 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < DHP; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_row + 2 * TA_BN + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[c0 + i] = __uint_as_float(v[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < DHP; ++i) o[i] = 0.f;
+    }
+    fe.store(qi * TA_BM + row, o, m_ref, l_run);
   }
 }
 
@@ -273,7 +333,7 @@ struct VitFront {
   const __nv_bfloat16 *gQ, *gK, *gV;
   int row_stride;
   __device__ VitFront(const VitAttnParams& p_) : p(p_) {
-    q0 = blockIdx.x * TA_BM; h = blockIdx.y; t = blockIdx.z;
+    q0 = blockIdx.x * TA_BM * TA_QT; h = blockIdx.y; t = blockIdx.z;
     row_stride = 3 * p.H * DH;
     const __nv_bfloat16* base = p.qkv + (long long)t * p.S * row_stride;
     gQ = base + h * DH; gK = base + (p.H + h) * DH; gV = base + (2 * p.H + h) * DH;
@@ -327,17 +387,18 @@ struct PagedFront {
     q_start = p.stream_desc[st * 4 + 0]; n_q = p.stream_desc[st * 4 + 1]; kv_len = p.stream_desc[st * 4 + 2];
     table = p.block_tables + p.stream_desc[st * 4 + 3];
     R = n_q * G;
-    r_base = qt * TA_BM;
+    r_base = qt * TA_BM * TA_QT;
     past = kv_len - n_q;
-    const int last_row = min(R, r_base + TA_BM) - 1;
-    const int max_pos = r_base < R ? past + last_row / G : -1;
-    const int vis = r_base < R ? min((kv_len + TA_BN - 1) / TA_BN, max_pos / TA_BN + 1) : 0;
+    int vis = 0;
+    if (r_base < R) {
+      const int last_row = min(R, r_base + TA_BM * TA_QT) - 1;
+      vis = min((kv_len + TA_BN - 1) / TA_BN, (past + last_row / G) / TA_BN + 1);
+    }
     const int per = (vis + p.n_splits - 1) / p.n_splits;
     t_begin = sp * per;
     t_end = min(vis, t_begin + per);
     if (t_end < t_begin) t_end = t_begin;
   }
-  __device__ bool active() const { return r_base < R; }
   __device__ int n_tiles() const { return t_end - t_begin; }
   __device__ const __nv_bfloat16* any_ptr() const { return p.q; }
   __device__ const __nv_bfloat16* q_row(int r) const {
@@ -346,15 +407,14 @@ struct PagedFront {
     return p.q + ((long long)(q_start + rr / G) * p.Hq + kvh * G + rr % G) * DH;
   }
   __device__ const __nv_bfloat16* kv_row(int j, int r, int is_v) const {
-    const int key = (t_begin + j) * TA_BN + r;
-    if (key >= kv_len) return nullptr;
-    const int page = table[key / PAGE];
-    return p.kv_layer + ((((long long)page * 2 + is_v) * p.Hkv + kvh) * PAGE + key % PAGE) * DH;
+    const int tile = t_begin + j;                       // one key tile == one 64-token page
+    if (tile * TA_BN + r >= kv_len) return nullptr;     // pool memory past the end may hold anything: zero-fill
+    return p.kv_layer + ((((long long)table[tile] * 2 + is_v) * p.Hkv + kvh) * PAGE + r) * DH;
   }
   __device__ const __nv_bfloat16* k_row(int j, int r) const { return kv_row(j, r, 0); }
   __device__ const __nv_bfloat16* v_row(int j, int r) const { return kv_row(j, r, 1); }
   // masking works on tile-local key indices j*TA_BN + c: shift the causal limit into that frame
-  __device__ int key_limit(int row) const { return past + min(r_base + row, R - 1) / G - t_begin * TA_BN; }
+  __device__ int key_limit(int row) const { return past + min(r_base + row, max(R - 1, 0)) / G - t_begin * TA_BN; }
   __device__ float scale_log2e() const { return p.scale_log2e; }
   template <int DHP>
   __device__ void store(int row, const float (&o)[DHP], float m, float l) const {
@@ -379,18 +439,22 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attn_tcgen05_kernel(const Param
   const int warp = threadIdx.x >> 5;
   griddep_launch_dependents();
   if (threadIdx.x == 0) {
-    constexpr uint32_t NLOAD = 32 * TA_LOADER_WARPS, NSOFT = 32 * TA_SOFTMAX_WARPS;
+    constexpr uint32_t NLOAD = 32 * TA_LOADER_WARPS;
     mbar_init(bars + 8u * BAR_Q_FULL, NLOAD);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(bars + 8u * (BAR_KV_FULL + s), NLOAD);
-      mbar_init(bars + 8u * (BAR_KV_EMPTY + s), 1);
-      mbar_init(bars + 8u * (BAR_S_FULL + s), 1);
-      mbar_init(bars + 8u * (BAR_S_EMPTY + s), NSOFT);
+    for (int s = 0; s < TA_RING; ++s) {
+      mbar_init(bars + 8u * (BAR_K_FULL + s), NLOAD);
+      mbar_init(bars + 8u * (BAR_K_EMPTY + s), 1);
+      mbar_init(bars + 8u * (BAR_V_FULL + s), NLOAD);
+      mbar_init(bars + 8u * (BAR_V_EMPTY + s), 1);
     }
-    mbar_init(bars + 8u * BAR_P_FULL, NSOFT);
-    mbar_init(bars + 8u * BAR_P_EMPTY, 1);
-    mbar_init(bars + 8u * BAR_O_FULL, 1);
-    mbar_init(bars + 8u * BAR_O_EMPTY, NSOFT);
+    for (int i = 0; i < 2 * TA_QT; ++i) {
+      mbar_init(bars + 8u * (BAR_S_FULL + i), 1);
+      mbar_init(bars + 8u * (BAR_S_EMPTY + i), 128);
+    }
+    for (int i = 0; i < TA_QT; ++i) {
+      mbar_init(bars + 8u * (BAR_P_FULL + i), 128);
+      mbar_init(bars + 8u * (BAR_O_FULL + i), 1);
+    }
     fence_mbar_init();
   }
   // zero the operand regions once: padding chunks (head dim 72 -> 80, unused chunks) are never written by the loaders
@@ -430,7 +494,7 @@ int launch_vit_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int T,
   VitAttnParams p;
   p.qkv = qkv; p.out = out; p.S = S; p.H = H; p.split_hi_lo = split_hi_lo;
   p.scale_log2e = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
-  dim3 grid((S + TA_BM - 1) / TA_BM, H, T);
+  dim3 grid((S + TA_BM * TA_QT - 1) / (TA_BM * TA_QT), H, T);
   if (launch_k(kern, grid, dim3(TA_THREADS), AttnSmem::TOTAL, s, p) != cudaSuccess) return -5;
   return 0;
 }
@@ -449,9 +513,11 @@ int launch_kv_attention_tc_main(const __nv_bfloat16* q, const __nv_bfloat16* kv_
   p.Hq = Hq; p.Hkv = Hkv; p.n_splits = n_splits; p.part_stride_rows = (long long)total_q * Hq;
   p.scale_log2e = (1.0f / sqrtf(128.f)) * 1.4426950408889634f;
   const int G = Hq / Hkv;
-  dim3 grid(((max_n_q * G + TA_BM - 1) / TA_BM) * Hkv, n_splits, n_streams);
+  dim3 grid(((max_n_q * G + TA_BM * TA_QT - 1) / (TA_BM * TA_QT)) * Hkv, n_splits, n_streams);
   if (launch_k(kern, grid, dim3(TA_THREADS), AttnSmem::TOTAL, s, p) != cudaSuccess) return -5;
   return 0;
 }
+
+int kv_attention_tc_q_rows_per_cta() { return TA_BM * TA_QT; }
 
 }  // namespace mmd

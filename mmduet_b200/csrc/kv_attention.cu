@@ -268,10 +268,11 @@ int launch_kv_attention_tc_main(const __nv_bfloat16* q, const __nv_bfloat16* kv_
                                 cudaStream_t s);
 
 int kv_attention_pick_splits(int max_rows, int Hkv, int n_streams, int max_kv_len, int num_sms) {
-  const int q_tiles = (max_rows + KA_BM - 1) / KA_BM;
+  // mma.sync kernel: 128 query rows per CTA, two CTAs per SM; tcgen05 kernel: 256 rows per CTA, one CTA per SM
+  const int rows_per_cta = g_attention_impl == 1 ? 2 * KA_BM : KA_BM;
+  const int q_tiles = (max_rows + rows_per_cta - 1) / rows_per_cta;
   const int base = q_tiles * Hkv * n_streams;
   const int kv_tiles = (max_kv_len + KA_BN - 1) / KA_BN;
-  // mma.sync kernel: two CTAs per SM; tcgen05 kernel: one CTA per SM
   int splits = ((g_attention_impl == 1 ? 1 : 2) * num_sms + base - 1) / base;
   const int max_by_work = (kv_tiles + 3) / 4;  // at least ~4 key tiles (256 keys) per split
   if (splits > max_by_work) splits = max_by_work;
