@@ -46,6 +46,9 @@ MMD_API int mmd_num_sms(mmd_ctx*);
  * csrc/kv_attention.cu); 1 = tcgen05.mma / TMEM flash attention (csrc/attn_tcgen05.cu).  Both are parity-tested.
  * Process-wide. */
 MMD_API int mmd_set_attention_impl(int impl);
+/* 1 (default): large-M GEMMs (ViT, projector) run on CTA pairs (tcgen05.mma.cta_group::2, UMMA M = 256); 0: single-CTA
+ * kernel everywhere.  Process-wide. */
+MMD_API int mmd_set_gemm_2cta(int on);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * GEMM (tcgen05.mma, TMA operands, TMEM accumulators) — every nn.Linear on the path.

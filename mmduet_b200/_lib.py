@@ -76,6 +76,7 @@ SIGNATURES = {
     "mmd_gemm_splits": (c_int, [c_int64, c_int]),
     "mmd_num_sms": (c_int, [c_void_p]),
     "mmd_set_attention_impl": (c_int, [c_int]),
+    "mmd_set_gemm_2cta": (c_int, [c_int]),
     "mmd_launch_count": (ctypes.c_ulonglong, [c_void_p]),
     "mmd_profile_num_tags": (c_int, []),
     "mmd_profile_tag_name": (ctypes.c_char_p, [c_int]),

@@ -170,6 +170,11 @@ void mmd_destroy(mmd_ctx* c) {
 
 int mmd_num_sms(mmd_ctx* c) { return c ? c->num_sms : 0; }
 
+int mmd_set_gemm_2cta(int on) {
+  mmd::g_gemm_use_2cta = on ? 1 : 0;
+  return 0;
+}
+
 int mmd_set_attention_impl(int impl) {
   if (impl != 0 && impl != 1) return fail(MMD_ERR_ARG, "mmd_set_attention_impl: 0 (mma.sync) or 1 (tcgen05)");
   mmd::g_attention_impl = impl;

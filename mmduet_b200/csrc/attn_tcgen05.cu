@@ -137,9 +137,17 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
       mbar_arrive(bar(BAR_K_FULL + j % TA_RING));
       mbar_arrive(bar(BAR_V_FULL + j % TA_RING));
     };
+    int published = -1;   // last tile handed to the MMA warp by this thread
     for (int j = 0; j < n_tiles; ++j) {
       const int st = j % TA_RING;
       const uint32_t par = ((j / TA_RING) & 1) ^ 1;
+      if (j >= 1 && !(mbar_try_wait(bar(BAR_K_EMPTY + st), par) && mbar_try_wait(bar(BAR_V_EMPTY + st), par))) {
+        // The ring slot is still in use.  Never block on it while holding back a tile that has already been requested:
+        // the MMA warp may need tile j-1 before it can release this slot (deadlock otherwise).
+        cp_async_wait<0>();
+        publish(j - 1);
+        published = j - 1;
+      }
       mbar_wait(bar(BAR_K_EMPTY + st), par);
       mbar_wait(bar(BAR_V_EMPTY + st), par);
       const uint32_t kb = smem_base + AttnSmem::K + st * 2 * TA_KREGION, vb = smem_base + AttnSmem::V + st * 2 * TA_KREGION;
@@ -156,16 +164,17 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
         cp_async_wait<1>();
         fence_proxy_async_smem();
         mbar_arrive(bar(BAR_Q_FULL));
-      } else {
+      } else if (published < j - 1) {
         cp_async_wait<1>();    // tile j-1 has landed, tile j may still be in flight
         publish(j - 1);
+        published = j - 1;
       }
     }
     cp_async_wait<0>();
     if (n_tiles == 0) {
       fence_proxy_async_smem();
       mbar_arrive(bar(BAR_Q_FULL));
-    } else {
+    } else if (published < n_tiles - 1) {
       publish(n_tiles - 1);
     }
   } else if (warp == TA_SOFTMAX_WARPS + TA_LOADER_WARPS) {
@@ -251,11 +260,13 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
         tc_fence_after();
       }
       const float m_new = fmaxf(m_ref, mx);
+      const bool need = j > 0 && m_new > m_ref && (m_ref == -INFINITY || (m_new - m_ref) * sl2 > 8.0f);
       if (j == 0) {
         m_ref = m_new;
-      } else if (m_new > m_ref && (m_ref == -INFINITY || (m_new - m_ref) * sl2 > 8.0f)) {
-        // lazy rescaling: O (TMEM) and l move to the new exponent base
-        const float f = (m_ref == -INFINITY) ? 0.f : exp2f((m_ref - m_new) * sl2);
+      } else if (__any_sync(0xffffffffu, need)) {
+        // lazy rescaling: O (TMEM) and l move to the new exponent base.  tcgen05.ld/st are .sync.aligned, so the whole
+        // warp takes this path together; rows that do not need it rescale by 1.
+        const float f = !need ? 1.f : ((m_ref == -INFINITY) ? 0.f : exp2f((m_ref - m_new) * sl2));
 #pragma unroll
         for (int c0 = 0; c0 < DHP; c0 += 16) {
           uint32_t v[16];
@@ -266,8 +277,10 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
           tmem_st_32x32b_x16(t_row + 2 * TA_BN + c0, v);
         }
         tmem_st_wait();
-        l_run *= f;
-        m_ref = m_new;
+        if (need) {
+          l_run *= f;
+          m_ref = m_new;
+        }
       }
       const float msc = (m_ref == -INFINITY) ? 0.f : m_ref * sl2;
       // pass 2: probabilities -> bf16 P tile (swizzled K-major), row sum
@@ -286,9 +299,12 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
             if (k0 + c0 + i + 1 > key_lim) s1 = -INFINITY;
           }
           const float p0 = exp2f(s0 * sl2 - msc), p1 = exp2f(s1 * sl2 - msc);
-          rs += p0 + p1;
           __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
           pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+          // the row sum uses the ROUNDED probabilities, so numerator (P V on bf16 P) and denominator stay consistent even
+          // when the stale exponent base makes the dominant term differ from exactly 1.0
+          const float2 hr = __bfloat1622float2(h);
+          rs += hr.x + hr.y;
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {   // four 16-B chunks of this 32-key group

@@ -79,6 +79,72 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Normal-orientation epilogue of one accumulator tile: TMEM lane = output row `xi`, TMEM columns [c_begin, c_end) =
+// output columns y0 + c.  Shared by the 1-CTA and the 2-CTA (cta_group::2) kernels.
+template <int EPI, int ACT>
+__device__ __forceinline__ void epilogue_normal(const GemmKernelParams& p, uint32_t t_row, int xi, int y0, int c_begin, int c_end) {
+    // normal orientation: lane = output row m, columns = n (contiguous in memory)
+    const bool row_ok = xi < p.x_rows;
+#pragma unroll 1
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+      if (y0 + c0 >= p.y_rows) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(t_row + c0, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int n = y0 + c0 + g * 8;
+          if (n < p.y_rows) {  // y_rows % 8 == 0 is enforced by the launcher
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+            if (p.bias != nullptr) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_HILO) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = apply_act<ACT>(f[j]);
+              uint4 o;
+              o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+              o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)xi * p.ldo + n;
+              *reinterpret_cast<uint4*>(dst) = o;
+              if constexpr (EPI == EPI_BF16_HILO) {
+                const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&o);
+                uint4 lo;
+                uint32_t* lw = reinterpret_cast<uint32_t*>(&lo);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 hf = __bfloat1622float2(hp[j]);
+                  lw[j] = pack_bf16(f[2 * j] - hf.x, f[2 * j + 1] - hf.y);
+                }
+                *reinterpret_cast<uint4*>(dst + p.y_rows) = lo;
+              }
+            } else {
+              float* dst = reinterpret_cast<float*>(p.out) + (long long)xi * p.ldo + n;
+              float4 r0, r1;
+              if constexpr (EPI == EPI_RESID_F32) {
+                r0 = *reinterpret_cast<const float4*>(dst);
+                r1 = *reinterpret_cast<const float4*>(dst + 4);
+              } else {
+                r0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                r1 = r0;
+              }
+              r0.x += f[0]; r0.y += f[1]; r0.z += f[2]; r0.w += f[3];
+              r1.x += f[4]; r1.y += f[5]; r1.z += f[6]; r1.w += f[7];
+              *reinterpret_cast<float4*>(dst) = r0;
+              *reinterpret_cast<float4*>(dst + 4) = r1;
+            }
+          }
+        }
+      }
+    }
+}
+
 template <int BN, bool DUAL, int EPI, int ACT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
@@ -241,66 +307,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int y0 = yt * BN;             // first index along Y rows (TMEM column 0)
 
       if constexpr (EPI == EPI_BF16 || EPI == EPI_RESID_F32 || EPI == EPI_F32 || EPI == EPI_BF16_HILO) {
-        // normal orientation: lane = output row m, columns = n (contiguous in memory)
-        const bool row_ok = xi < p.x_rows;
-#pragma unroll 1
-        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
-          if (y0 + c0 >= p.y_rows) break;  // warp-uniform
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(t_row + c0, v);
-          tmem_ld_wait();
-          if (row_ok) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int n = y0 + c0 + g * 8;
-              if (n < p.y_rows) {  // y_rows % 8 == 0 is enforced by the launcher
-                float f[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-                if (p.bias != nullptr) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-                }
-                if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_HILO) {
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) f[j] = apply_act<ACT>(f[j]);
-                  uint4 o;
-                  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
-                  o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-                  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)xi * p.ldo + n;
-                  *reinterpret_cast<uint4*>(dst) = o;
-                  if constexpr (EPI == EPI_BF16_HILO) {
-                    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&o);
-                    uint4 lo;
-                    uint32_t* lw = reinterpret_cast<uint32_t*>(&lo);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                      const float2 hf = __bfloat1622float2(hp[j]);
-                      lw[j] = pack_bf16(f[2 * j] - hf.x, f[2 * j + 1] - hf.y);
-                    }
-                    *reinterpret_cast<uint4*>(dst + p.y_rows) = lo;
-                  }
-                } else {
-                  float* dst = reinterpret_cast<float*>(p.out) + (long long)xi * p.ldo + n;
-                  float4 r0, r1;
-                  if constexpr (EPI == EPI_RESID_F32) {
-                    r0 = *reinterpret_cast<const float4*>(dst);
-                    r1 = *reinterpret_cast<const float4*>(dst + 4);
-                  } else {
-                    r0 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    r1 = r0;
-                  }
-                  r0.x += f[0]; r0.y += f[1]; r0.z += f[2]; r0.w += f[3];
-                  r1.x += f[4]; r1.y += f[5]; r1.z += f[6]; r1.w += f[7];
-                  *reinterpret_cast<float4*>(dst) = r0;
-                  *reinterpret_cast<float4*>(dst + 4) = r1;
-                }
-              }
-            }
-          }
-        }
+        epilogue_normal<EPI, ACT>(p, t_row, xi, y0, c_begin, c_end);
       } else if constexpr (EPI == EPI_T_F32) {
         // swap-AB: lane = n (weight row), column = token. Lanes of a warp write 32 consecutive n -> 128-B stores.
         const bool n_ok = xi < p.x_rows;
@@ -352,6 +359,237 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// Epilogue through shared memory and TMA: the warp's 32 accumulator rows x 32 (fp32) / 64 (bf16) columns are staged in a
+// 128-B-swizzled 4 KB tile and written by ONE bulk tensor store (or an fp32 reduce-add performed in L2 for the residual
+// stream).  Replaces 16-B per-thread stores to 32 different rows per instruction, whose request stream kept the
+// SM<->crossbar port 60% busy (ncu l1tex__m_l1tex2xbar_req_cycles_active) and starved the TMA operand loads.
+// Rows / columns beyond the tensor are clipped by the TMA unit.
+__device__ __forceinline__ uint32_t stage_sw128_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+template <int EPI, int ACT>
+__device__ __forceinline__ void epilogue_normal_tma(const GemmKernelParams& p, const CUtensorMap* tmOut, uint32_t t_row, int m_warp,
+                                                    int y0, int c_begin, int c_end, uint32_t stage) {
+  const int lane = (int)lane_id();
+  if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_F32) {
+#pragma unroll 1
+    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+      if (y0 + c0 >= p.y_rows) break;
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(t_row + c0, v);
+      tmem_ld_wait();
+      if (lane == 0) bulk_wait_group_read0();     // the previous store has finished reading the staging tile
+      __syncwarp();
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const int n = y0 + c0 + g * 4;
+        float4 f = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+        if (p.bias != nullptr && n < p.y_rows) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+          f.x += b.x; f.y += b.y; f.z += b.z; f.w += b.w;
+        }
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage + stage_sw128_off(lane, g)), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w) : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (EPI == EPI_RESID_F32) tma_reduce_add_2d(tmOut, stage, y0 + c0, m_warp);
+        else tma_store_2d(tmOut, stage, y0 + c0, m_warp);
+        bulk_commit_group();
+      }
+    }
+  } else {
+    // bf16 outputs: 64 columns (128 B per row) per store; EPI_BF16_HILO writes a second tile p.y_rows columns further right
+#pragma unroll 1
+    for (int c0 = c_begin; c0 < c_end; c0 += 64) {
+      if (y0 + c0 >= p.y_rows) break;
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + c0 + 32 * h, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int n = y0 + c0 + 32 * h + g * 4;
+          float f[4] = {__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])};
+          if (p.bias != nullptr && n < p.y_rows) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            f[0] += b.x; f[1] += b.y; f[2] += b.z; f[3] += b.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) f[j] = apply_act<ACT>(f[j]);
+          hi[16 * h + 2 * g] = pack_bf16(f[0], f[1]);
+          hi[16 * h + 2 * g + 1] = pack_bf16(f[2], f[3]);
+          if constexpr (EPI == EPI_BF16_HILO) {
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi[16 * h + 2 * g]));
+            const float2 b2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hi[16 * h + 2 * g + 1]));
+            lo[16 * h + 2 * g] = pack_bf16(f[0] - a.x, f[1] - a.y);
+            lo[16 * h + 2 * g + 1] = pack_bf16(f[2] - b2.x, f[3] - b2.y);
+          }
+        }
+      }
+      constexpr int NPASS = (EPI == EPI_BF16_HILO) ? 2 : 1;
+#pragma unroll
+      for (int pass = 0; pass < NPASS; ++pass) {
+        if (lane == 0) bulk_wait_group_read0();
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t* src = pass == 0 ? &hi[4 * c] : &lo[4 * c];
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + stage_sw128_off(lane, c)), "r"(src[0]), "r"(src[1]), "r"(src[2]),
+                       "r"(src[3]) : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmOut, stage, y0 + c0 + pass * p.y_rows, m_warp);
+          bulk_commit_group();
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for the large-M GEMMs of the ViT / projector: two CTAs of a cluster (one TPC) share
+// one UMMA of 256 x BN2 x 16.  Each CTA stages its own 128 rows of A and HALF of the B tile (BN2/2 rows), so the
+// shared-memory traffic per MMA drops by a third compared with the single-CTA kernel, whose tensor pipe ncu shows only
+// 63% active at 128 x 256 tiles.  The leader CTA (rank 0) issues the MMAs; both CTAs run a TMA producer (completion bytes
+// are credited to the LEADER's full barrier) and their own epilogue over their 128 accumulator lanes; tcgen05.commit
+// multicasts the "slot free" / "accumulator ready" arrivals to both CTAs.
+// ------------------------------------------------------------------------------------------------------------
+template <int BN2>
+struct Gemm2Cfg {
+  static constexpr int A_BYTES = BM * BK * 2;                 // 16 KB: this CTA's 128 rows
+  static constexpr int B_BYTES = (BN2 / 2) * BK * 2;          // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TMEM_COLS = 512;                       // 2 accumulators of BN2 columns
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int EPI_STAGE_BYTES = 4096 * GEMM_EPI_WARPS;   // one swizzled 32-row x 128-B staging tile per epilogue warp
+  static constexpr int STAGES_RAW = (SMEM_BUDGET - 1024 - BAR_BYTES - EPI_STAGE_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + BAR_BYTES + 1024;
+  static_assert(2 * BN2 <= 512 && BN2 % 32 == 0, "accumulator columns");
+};
+
+template <int BN2, int EPI, int ACT>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const __grid_constant__ CUtensorMap tmOut, const GemmKernelParams p) {
+  using Cfg = Gemm2Cfg<BN2>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t epi_stage_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = epi_stage_base + Cfg::EPI_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int m_tiles = (p.x_rows + 2 * BM - 1) / (2 * BM);
+  const int n_tiles = (p.y_rows + BN2 - 1) / BN2;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * 32 * GEMM_EPI_WARPS);   // the epilogue threads of BOTH CTAs arrive on the leader's barrier
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        const int mt = tile % m_tiles, nt = tile / m_tiles;
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sB = sA + Cfg::A_BYTES;
+          const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_2cta(sA, &tmA, lead_full, kb * BK, mt * 2 * BM + (int)rank * BM);
+          tma_load_2d_2cta(sB, &tmB, lead_full, kb * BK, nt * BN2 + (int)rank * (BN2 / 2));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA, single thread) =====================
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN2);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN2;
+        for (int kb = 0; kb < p.kb_total; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t dA = umma_desc_k_sw128(sA);
+          const uint64_t dB = umma_desc_k_sw128(sA + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_f16_2cta(d_tmem, dA + 2u * k, dB + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2cta(empty_bar(stage), 0x3);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2cta(tfull_bar(acc), 0x3);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps (both CTAs, own 128 accumulator lanes) =====================
+    const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    const int c_begin = chalf * (BN2 / 2), c_end = c_begin + BN2 / 2;
+    const int lane_row = q * 32 + (int)lane_id();
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+      const int mt = tile % m_tiles, nt = tile / m_tiles;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN2;
+      const int m_warp = mt * 2 * BM + (int)rank * BM + q * 32;   // first output row of this warp's 32 lanes
+      epilogue_normal_tma<EPI, ACT>(p, &tmOut, t_row, m_warp, nt * BN2, c_begin, c_end, epi_stage_base + (warp - 2) * 4096);
+      tc_fence_before();
+      mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (lane_id() == 0) bulk_wait_group0();   // the staging tiles must outlive the last bulk stores
+    (void)lane_row;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // neither CTA may free its TMEM / leave while the pair's MMAs or remote arrivals are in flight
+  if (warp == 1) tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -436,6 +674,41 @@ static int get_map(GemmContext* c, const void* ptr, int rows, int K, long long l
   {
     std::lock_guard<std::mutex> lk(c->mu);
     if (c->maps.size() > 65536) c->maps.clear();
+    c->maps.emplace(key, m);
+  }
+  *out = m;
+  return 0;
+}
+
+// Output tensor map for the TMA-store epilogue: [rows, width] fp32 (box 32 x 32) or bf16 (box 64 x 32), 128-B swizzle.
+static int get_out_map(GemmContext* c, const void* ptr, int rows, int width, long long ld, bool f32, CUtensorMap* out) {
+  MapKey key{ptr, rows, width, ld, f32 ? -2 : -3};
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    auto it = c->maps.find(key);
+    if (it != c->maps.end()) { *out = it->second; return 0; }
+  }
+  const int esz = f32 ? 4 : 2;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * esz) % 16 != 0) {
+    g_gemm_err = "gemm output must be 16-B aligned with a 16-B aligned row stride";
+    return -2;
+  }
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(f32 ? 32 : 64), 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = c->encode(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[160];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(out) failed (%d) rows=%d width=%d ld=%lld", (int)r, rows, width, ld);
+    g_gemm_err = buf;
+    return -3;
+  }
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
     c->maps.emplace(key, m);
   }
   *out = m;
@@ -528,9 +801,64 @@ static int launch_cfg(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
   return 0;
 }
 
+int g_gemm_use_2cta = 1;   // CTA-pair kernel for the large-M normal-orientation GEMMs (mmd_set_gemm_2cta)
+
+template <int BN2, int EPI, int ACT>
+static int launch_2cta(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN2>;
+  auto kern = gemm_tcgen05_2cta_kernel<BN2, EPI, ACT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { g_gemm_err = std::string("cudaFuncSetAttribute(2cta): ") + cudaGetErrorString(e); return -4; }
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmB, tmOut;
+  int rc;
+  if ((rc = get_map(c, a.X, a.x_rows, a.K, a.ldx, BM, &tmA)) != 0) return rc;
+  if ((rc = get_map(c, a.Y, a.y_rows, a.K, a.ldy, BN2 / 2, &tmB)) != 0) return rc;
+  {
+    const bool f32 = (EPI == EPI_RESID_F32 || EPI == EPI_F32);
+    const int width = a.y_rows * (EPI == EPI_BF16_HILO ? 2 : 1);
+    if ((rc = get_out_map(c, a.out, a.x_rows, width, a.ldo, f32, &tmOut)) != 0) return rc;
+  }
+  GemmKernelParams p;
+  p.x_rows = a.x_rows; p.y_rows = a.y_rows;
+  p.x_tiles = (a.x_rows + 2 * BM - 1) / (2 * BM);
+  p.y_tiles = (a.y_rows + BN2 - 1) / BN2;
+  p.kb_total = (a.K + BK - 1) / BK;
+  p.k_splits = 1; p.kb_per_split = p.kb_total;
+  p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.split_stride = 0; p.pdl_prefetch_x = 0; p.x_blocked = 0;
+  const long long tiles = (long long)p.x_tiles * p.y_tiles;
+  const int max_clusters = (a.max_ctas > 0 ? a.max_ctas : c->num_sms) / 2;
+  const int clusters = (int)(tiles < max_clusters ? tiles : max_clusters);
+  if (clusters <= 0) return 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmOut, p);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { g_gemm_err = std::string("gemm 2cta launch: ") + cudaGetErrorString(e); return -5; }
+  return 0;
+}
+
 template <int EPI, int ACT>
 static int launch_normal(GemmContext* c, const GemmArgs& a, cudaStream_t s) {
   if (a.y_rows % 8 != 0) { g_gemm_err = "normal-orientation GEMM needs N % 8 == 0"; return -2; }
+  if (g_gemm_use_2cta && a.x_rows >= 1024 && a.y_rows >= 192) {
+    // N = 1152 (out_proj / fc2 / patch embed) tiles exactly by 192
+    if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_F32) {
+      if (a.y_rows % 192 == 0 && a.y_rows % 256 != 0 && a.y_rows <= 1536) return launch_2cta<192, EPI, ACT>(c, a, s);
+    }
+    return launch_2cta<256, EPI, ACT>(c, a, s);
+  }
   if (a.y_rows <= 128) return launch_cfg<128, false, EPI, ACT>(c, a, s);
   // N = 1152 (SigLIP out_proj / fc2 / patch embed) tiles exactly by 192 and wastes 10% of the MMAs with 256-wide tiles
   if (a.y_rows % 192 == 0 && a.y_rows % 256 != 0 && a.y_rows <= 1536) return launch_cfg<192, false, EPI, ACT>(c, a, s);

@@ -47,5 +47,6 @@ int gemm_launch(GemmContext*, const GemmArgs&, cudaStream_t stream);
 const char* gemm_last_error();
 // Effective number of split-K planes the launch will write for (K, requested splits).
 int gemm_effective_splits(int K, int k_splits);
+extern int g_gemm_use_2cta;  // 1 (default): cta_group::2 kernel for the large-M normal-orientation GEMMs
 
 }  // namespace mmd

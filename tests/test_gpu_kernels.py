@@ -31,7 +31,8 @@ def test_library_refuses_nothing_silently(env):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 1152, 1152), (729, 4304, 1152), (729, 1152, 4304), (1000, 1152, 592),
-                                   (77, 144, 328), (2000, 288, 1000)])
+                                   (77, 144, 328), (2000, 288, 1000), (4096, 1152, 1152), (3000, 4304, 1152), (2500, 3456, 2304),
+                                   (1111, 192, 64), (23328, 1152, 4304)])
 def test_gemm_normal(env, M, N, K):
     _lib, ops, lib, ctx = env
     torch.manual_seed(M + N + K)
@@ -133,8 +134,9 @@ def test_vit_attention(env, attn_impl, T, S, H):
     _lib.check(lib.mmd_vit_attention(qkv.data_ptr(), out2.data_ptr(), T, S, H, dh, 1, _s()))
     assert torch.equal(out2[:, :H * dh], out)
     hi_lo = out2[:, :H * dh].float() + out2[:, H * dh:].float()
-    # hi+lo removes the output rounding: what is left is the bf16 rounding of P inside the kernel
-    assert (hi_lo - ref).abs().max() < 4e-3
+    # hi+lo removes the output rounding: what is left is the bf16 rounding of P inside the kernel (the tcgen05 kernel's
+    # lazy rescaling keeps a stale exponent base, so its dominant probability is not exactly 1.0: slightly larger)
+    assert (hi_lo - ref).abs().max() < (4e-3 if attn_impl == 0 else 1.5e-2)
 
 
 def test_resid_add_rmsnorm(env):
