@@ -16,6 +16,7 @@
 #include <string>
 #include <unordered_map>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace mmd {
@@ -151,9 +152,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                     const __grid_constant__ CUtensorMap tmY, const GemmKernelParams p) {
   using Cfg = GemmCfg<BN, DUAL>;
   constexpr int STAGES = Cfg::STAGES;
-  // swap-AB: X holds the weights.  Token tiles (y) are then the fastest-varying tile index, so the CTAs that share a
-  // weight tile run at the same time and the second reader hits L2 instead of streaming the weights twice from HBM.
-  constexpr bool kWeightsOnX = (EPI == EPI_T_F32 || EPI == EPI_T_SWIGLU);
+  // Tile order: the Y tile index varies fastest.  Swap-AB (weights on X): the CTAs that share a weight tile run at the
+  // same time, so the second reader hits L2 instead of streaming the weights twice from HBM.  Normal orientation
+  // (activations on X): all weight tiles of an activation row block are consumed together, so a large A (fc2: 200 MB,
+  // more than L2) is streamed once instead of once per weight tile.
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
@@ -198,8 +200,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (tile < total_tiles) {
           const int ks = tile % p.k_splits;
           const int rest = tile / p.k_splits;
-          if constexpr (kWeightsOnX) { yt = rest % p.y_tiles; xt = rest / p.y_tiles; }
-          else { xt = rest % p.x_tiles; yt = rest / p.x_tiles; }
+          yt = rest % p.y_tiles; xt = rest / p.y_tiles;
           kb = ks * p.kb_per_split;
           kb1 = min(p.kb_total, kb + p.kb_per_split);
         }
@@ -298,8 +299,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int ks = tile % p.k_splits;
       const int rest = tile / p.k_splits;
-      const int xt = kWeightsOnX ? rest / p.y_tiles : rest % p.x_tiles;
-      const int yt = kWeightsOnX ? rest % p.y_tiles : rest / p.x_tiles;
+      const int xt = rest / p.y_tiles, yt = rest % p.y_tiles;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_COLS;
@@ -525,7 +525,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-        const int mt = tile % m_tiles, nt = tile / m_tiles;
+        const int nt = tile % n_tiles, mt = tile / n_tiles;   // weight tiles fastest: an A row block is read once from HBM
         for (int kb = 0; kb < p.kb_total; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
@@ -572,7 +572,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int lane_row = q * 32 + (int)lane_id();
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-      const int mt = tile % m_tiles, nt = tile / m_tiles;
+      const int nt = tile % n_tiles, mt = tile / n_tiles;   // weight tiles fastest: an A row block is read once from HBM
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN2;
@@ -855,7 +855,8 @@ static int launch_normal(GemmContext* c, const GemmArgs& a, cudaStream_t s) {
   if (g_gemm_use_2cta && a.x_rows >= 1024 && a.y_rows >= 192) {
     // N = 1152 (out_proj / fc2 / patch embed) tiles exactly by 192
     if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_F32) {
-      if (a.y_rows % 192 == 0 && a.y_rows % 256 != 0 && a.y_rows <= 1536) return launch_2cta<192, EPI, ACT>(c, a, s);
+      static const bool no192 = getenv("MMD_NO_BN192") != nullptr;
+      if (!no192 && a.y_rows % 192 == 0 && a.y_rows % 256 != 0 && a.y_rows <= 1536) return launch_2cta<192, EPI, ACT>(c, a, s);
     }
     return launch_2cta<256, EPI, ACT>(c, a, s);
   }
