@@ -81,3 +81,26 @@ def test_config_validation():
         ModelConfig(vit_dim=1024).validate()                 # head_dim 64: no kernel instantiation
     with pytest.raises(ValueError):
         ModelConfig(pool_mode="nearest").validate()
+
+
+def test_merge_lora_matches_peft_formula():
+    from mmduet_b200.checkpoint import merge_lora
+    g = torch.Generator().manual_seed(0)
+    W = torch.randn(12, 8, generator=g).bfloat16()
+    A = torch.randn(4, 8, generator=g) * 0.1
+    B = torch.randn(12, 4, generator=g) * 0.1
+    base = {"model.layers.0.self_attn.q_proj.weight": W, "model.norm.weight": torch.ones(8)}
+    lora = {"base_model.model.model.layers.0.self_attn.q_proj.lora_A.weight": A,
+            "base_model.model.model.layers.0.self_attn.q_proj.lora_B.weight": B}
+    merged = merge_lora(base, lora, lora_r=4, lora_alpha=8)
+    want = (W.float() + 2.0 * (B @ A)).bfloat16()
+    assert torch.equal(merged["model.layers.0.self_attn.q_proj.weight"], want)
+    assert torch.equal(merged["model.norm.weight"], base["model.norm.weight"])
+    # single dict in peft's in-model layout (base_layer + lora_A/B.default)
+    combo = {"base_model.model.model.layers.0.self_attn.q_proj.base_layer.weight": W,
+             "base_model.model.model.layers.0.self_attn.q_proj.lora_A.default.weight": A,
+             "base_model.model.model.layers.0.self_attn.q_proj.lora_B.default.weight": B}
+    merged2 = merge_lora(combo, None, lora_r=4, lora_alpha=8)
+    assert torch.equal(merged2["model.layers.0.self_attn.q_proj.weight"], want)
+    with pytest.raises(KeyError):
+        merge_lora({"x.weight": W}, lora, 4, 8)

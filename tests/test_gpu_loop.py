@@ -144,3 +144,27 @@ def test_forward_surface_matches_reference_contract(setup):
     assert e.shape == (1, 3, arch.hidden)
     out2 = model(inputs_embeds=e, past_key_values=out.past_key_values, use_cache=True, return_dict=True, logits_to_keep="last")
     assert out2.past_key_values.get_seq_length() == 52 and out2.logits.shape == (1, 1, arch.vocab)
+
+
+def test_benchmark_driver_writes_reference_jsonl(setup, tmp_path):
+    """test/inference.py:332-361 schema: one JSON line per video, debug_data rounded to 3 decimals."""
+    import json
+
+    from mmduet_b200.inference import LiveInferForBenchmark
+    from mmduet_b200.run_benchmark import run
+    arch, w, model, tok, frames = setup
+    infer = LiveInferForBenchmark(_args(stream_end_prob_threshold=1.0), model=model, tokenizer=tok)
+    items = [("vid0", frames[:5], [{"role": "user", "time": 0.0, "content": "what happens"}], 2, 2.5),
+             (None, None, None, None, None),
+             ("vid1", frames[5:9], [], 1, 4.0)]
+    out = tmp_path / "out.jsonl"
+    assert run(infer, items, str(out), grounding_mode=True) == 2
+    lines = [json.loads(l) for l in open(out)]
+    assert [l["question_id"] for l in lines] == ["vid0", "vid1"]
+    assert set(lines[0]) == {"question_id", "model_response_list", "video_duration", "debug_data"}
+    assert lines[0]["model_response_list"] == [{"time": 0.0, "content": "what happens", "role": "user"}]
+    assert len(lines[0]["debug_data"]) == 5 and len(lines[1]["debug_data"]) == 4
+    assert [d["time"] for d in lines[1]["debug_data"]] == [0.0, 1.0, 2.0, 3.0]        # fps 1
+    for d in lines[0]["debug_data"]:
+        assert set(d) == {"time", "informative_score", "relevance_score"}
+        assert round(d["informative_score"], 3) == d["informative_score"]
