@@ -162,21 +162,26 @@ def workload_config(args, extra=None):
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
 def algorithmic_work(tag, cfg, M_dec, T_enc):
-    """(kind, amount per launch): 'bytes' for the HBM-bound weight-streaming GEMMs of the decoder (weights + activations
-    read/written once), 'flops' for the tensor-bound ViT GEMMs / attention.  DESIGN.md §roofline states the same formulas."""
+    """(bytes, flops) one launch of `tag` must move / perform (DESIGN.md §4 states the same formulas): weights + activations
+    read/written once, 2*M*N*K FLOP.  The binding roof is whichever of bytes/HBM-peak and flops/tensor-peak is larger: the
+    decoder's weight-streaming GEMMs are HBM-bound at M=49 and tensor-bound from ~4 frames per pass (M >= 207)."""
     H, I, D, Dm = cfg.hidden, cfg.mlp, cfg.vit_dim, cfg.vit_mlp
     nqkv = (cfg.q_heads + 2 * cfg.kv_heads) * cfg.head_dim
     Mv = T_enc * cfg.patches
+    L_avg = (PREFIX_LEN + N_FRAMES * 49) / 2.0
     table = {
-        "gate_up_swiglu": ("bytes", 2 * I * H * 2 + M_dec * H * 2 + M_dec * I * 2),
-        "down_proj": ("bytes", H * I * 2 + M_dec * I * 2),
-        "qkv_proj": ("bytes", nqkv * H * 2 + M_dec * H * 2),
-        "o_proj": ("bytes", H * H * 2 + M_dec * H * 2),
-        "fc1": ("flops", 2.0 * Mv * Dm * D), "fc2": ("flops", 2.0 * Mv * Dm * D),
-        "qkv": ("flops", 2.0 * Mv * 3 * D * D), "out_proj": ("flops", 2.0 * Mv * D * D),
-        "vit_attention": ("flops", 4.0 * T_enc * cfg.vit_heads * cfg.patches * cfg.patches * cfg.vit_head_dim),
-        # KV-append attention: average over the stream's passes of 4 * M * (keys visible) * Hq * dh
-        "kv_attention": ("flops", 4.0 * M_dec * (PREFIX_LEN + N_FRAMES * 49) / 2.0 * cfg.q_heads * cfg.head_dim),
+        "gate_up_swiglu": (2 * I * H * 2 + M_dec * H * 2 + M_dec * I * 2, 2.0 * M_dec * 2 * I * H),
+        "down_proj": (H * I * 2 + M_dec * I * 2 + M_dec * H * 4, 2.0 * M_dec * H * I),
+        "qkv_proj": (nqkv * H * 2 + M_dec * H * 2 + M_dec * nqkv * 4, 2.0 * M_dec * nqkv * H),
+        "o_proj": (H * H * 2 + M_dec * H * 2 + M_dec * H * 4, 2.0 * M_dec * H * H),
+        "fc1": (Mv * D * 2 + Dm * D * 2 + Mv * Dm * 2, 2.0 * Mv * Dm * D),
+        "fc2": (Mv * Dm * 2 + Dm * D * 2 + 2 * Mv * D * 4, 2.0 * Mv * Dm * D),
+        "qkv": (Mv * D * 2 + 3 * D * D * 2 + Mv * 3 * D * 2, 2.0 * Mv * 3 * D * D),
+        "out_proj": (Mv * 2 * D * 2 + 2 * D * D * 2 + 2 * Mv * D * 4, 2.0 * Mv * D * 2 * D),
+        "vit_attention": (Mv * 3 * D * 2 + Mv * 2 * D * 2, 4.0 * T_enc * cfg.vit_heads * cfg.patches * cfg.patches * cfg.vit_head_dim),
+        # KV-append attention: average over the stream's passes (keys visible ~ half the final context)
+        "kv_attention": (2 * L_avg * cfg.kv_heads * cfg.head_dim * 2 + 2 * M_dec * cfg.q_heads * cfg.head_dim * 2,
+                         4.0 * M_dec * L_avg * cfg.q_heads * cfg.head_dim),
     }
     return table.get(tag)
 
@@ -250,6 +255,7 @@ def run_gpu_arm(args):
     stage = _lib.profile_stop(local)
     stage_ms = {k: round(v[0], 3) for k, v in sorted(stage.items(), key=lambda kv: -kv[1][0])}
     known = {k: v for k, v in stage.items() if algorithmic_work(k, cfg, 49, 32) is not None}
+    roof_tags = {}
     dominant = max(known.items(), key=lambda kv: kv[1][0])[0]
 
     # ---- timed region: value ----
@@ -344,16 +350,35 @@ def run_gpu_arm(args):
     roofline = None
     if work is not None and dom_n > 0:
         per_launch_s = dom_ms / dom_n / 1e3
-        if work[0] == "bytes":
-            ach = work[1] / per_launch_s / 1e9
-            roofline = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                        "traffic": ncu_traffic(dominant), "peak_source": pk["source"], "launches_timed": dom_n, "avg_launch_us": per_launch_s * 1e6,
-                        "algorithmic_bytes_per_launch": work[1]}
+        nbytes, nflops = work
+        t_hbm, t_tc = nbytes / (pk["hbm_gbs"] * 1e9), nflops / (pk["bf16_tflops_sustained"] * 1e12)
+        common = {"kernel": dominant, "traffic": ncu_traffic(dominant), "launches_timed": dom_n, "avg_launch_us": per_launch_s * 1e6,
+                  "algorithmic_bytes_per_launch": nbytes, "algorithmic_flops_per_launch": nflops,
+                  "share_of_stream": round(stage[dominant][0] / sum(v[0] for v in stage.values()), 3)}
+        if t_hbm >= t_tc:
+            ach = nbytes / per_launch_s / 1e9
+            roofline = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                        "peak_source": pk["source"], **common}
         else:
-            ach = work[1] / per_launch_s / 1e12
-            roofline = {"bound": "tensor", "kernel": dominant, "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                        "frac": ach / pk["bf16_tflops_sustained"], "traffic": ncu_traffic(dominant), "peak_source": pk["source"] + " (sustained)",
-                        "launches_timed": dom_n, "avg_launch_us": per_launch_s * 1e6, "algorithmic_flops_per_launch": work[1]}
+            ach = nflops / per_launch_s / 1e12
+            roofline = {"bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                        "frac": ach / pk["bf16_tflops_sustained"], "peak_source": pk["source"] + " (sustained, kernel timed inside a long step)",
+                        **common}
+    # informative: the same roofline arithmetic for every kernel with a formula, from the profiling pass (not the timed region)
+    roof_all = []
+    tot_ms = sum(v[0] for v in stage.values())
+    for tag, (ms_t, n_t) in sorted(stage.items(), key=lambda kv: -kv[1][0]):
+        wk = algorithmic_work(tag, cfg, 49 * max(args.chunk, 1), 32)
+        if wk is None or n_t == 0:
+            continue
+        sec = ms_t / n_t / 1e3
+        t_hbm, t_tc = wk[0] / (pk["hbm_gbs"] * 1e9), wk[1] / (pk["bf16_tflops_sustained"] * 1e12)
+        if t_hbm >= t_tc:
+            roof_all.append({"kernel": tag, "share": round(ms_t / tot_ms, 3), "bound": "hbm", "achieved_GBps": round(wk[0] / sec / 1e9, 1),
+                             "frac": round(wk[0] / sec / 1e9 / pk["hbm_gbs"], 3)})
+        else:
+            roof_all.append({"kernel": tag, "share": round(ms_t / tot_ms, 3), "bound": "tensor", "achieved_TFLOPs": round(wk[1] / sec / 1e12, 1),
+                             "frac": round(wk[1] / sec / 1e12 / pk["bf16_tflops_sustained"], 3)})
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(args),
@@ -363,7 +388,7 @@ def run_gpu_arm(args):
             "latency_ms": {"decoder_frames_per_pass": 1, "p50_frame_step": lat_sorted[len(lat_sorted) // 2], "p99_frame_step": lat_sorted[int(len(lat_sorted) * 0.99) - 1],
                            "single_frame_encode": enc1_ms, "note": "frame step = decoder KV-append + heads + score D2H, host wall clock; "
                            "encode = SigLIP+projector+pool for ONE frame (live mode)"},
-            "stage_ms_per_stream": stage_ms, "threshold_crossings": crossings[:16], "value_vs_e2e_score_maxdiff": path_diff}
+            "stage_ms_per_stream": stage_ms, "roofline_by_kernel": roof_all, "threshold_crossings": crossings[:16], "value_vs_e2e_score_maxdiff": path_diff}
     if args.cpu_baseline and world == 1:
         try:
             torch.set_num_threads(os.cpu_count() or 1)

@@ -176,7 +176,7 @@ int mmd_set_gemm_2cta(int on) {
 }
 
 int mmd_set_attention_impl(int impl) {
-  if (impl != 0 && impl != 1) return fail(MMD_ERR_ARG, "mmd_set_attention_impl: 0 (mma.sync) or 1 (tcgen05)");
+  if (impl < 0 || impl > 2) return fail(MMD_ERR_ARG, "mmd_set_attention_impl: 0 (mma.sync), 1 (tcgen05) or 2 (auto)");
   mmd::g_attention_impl = impl;
   return 0;
 }
@@ -247,7 +247,7 @@ int mmd_kv_attention(mmd_ctx* c, const void* q, const void* kv_layer, const int*
   CHECK_CTX(c);
   if (n_splits <= 0) n_splits = mmd_kv_attention_splits(c, max_n_q, Hq, Hkv, n_streams, max_kv_len);
   RUNK(mmd::launch_kv_attention(static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(kv_layer), stream_desc,
-                                block_tables, n_streams, max_n_q, total_q, o_part, ml_part, static_cast<__nv_bfloat16*>(out),
+                                block_tables, n_streams, max_n_q, total_q, max_kv_len, o_part, ml_part, static_cast<__nv_bfloat16*>(out),
                                 Hq, Hkv, dh, MMD_PAGE_TOKENS, n_splits, S(stream)), "mmd_kv_attention (head_dim must be 128)");
   return check_launch("mmd_kv_attention");
 }
@@ -446,7 +446,7 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
     __nv_bfloat16* kv_layer = static_cast<__nv_bfloat16*>(pool->pool) + (int64_t)l * pool->layer_stride;
     PRUNK(mmd::launch_qkv_finish(buf.planes, eff, (int64_t)M * NQKV, L.qkv_b, w->rope_cos, w->rope_sin, st->tok_pos, st->tok_slot,
                                 buf.q, kv_layer, M, Hq, Hkv, dh, MMD_PAGE_TOKENS, s), "qkv_finish");
-    PRUNK2(mmd::launch_kv_attention(buf.q, kv_layer, st->stream_desc, st->block_tables, st->n_streams, st->max_n_q, M, buf.o_part,
+    PRUNK2(mmd::launch_kv_attention(buf.q, kv_layer, st->stream_desc, st->block_tables, st->n_streams, st->max_n_q, M, st->max_kv_len, buf.o_part,
                                   buf.ml_part, buf.attn, Hq, Hkv, dh, MMD_PAGE_TOKENS, attn_splits, s), "kv_attention");
     PRUN(gemm_T_partials(c, buf.attn, M, L.o_w, H, QD, s_o, buf.planes, s, &eff), "o_proj");
     PRUNK(mmd::launch_resid_add_rmsnorm(buf.resid, buf.planes, eff, (int64_t)M * H, L.ln2_w, buf.x, nullptr, M, H, w->rms_eps, s),

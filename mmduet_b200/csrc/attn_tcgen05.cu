@@ -34,7 +34,7 @@ constexpr int TA_QT = 2;                   // query tiles per CTA
 constexpr int TA_BN = 64;                  // keys per tile
 constexpr int TA_QREGION = TA_BM * 128;    // one 64-column swizzled region of a 128-row operand (16 KB)
 constexpr int TA_KREGION = TA_BN * 128;    // same for a 64-row operand (8 KB)
-constexpr int TA_RING = 3;                 // K and V ring depth
+constexpr int TA_KRING = 4, TA_VRING = 3;   // K is consumed two tiles ahead of V (QK^T runs ahead of the softmax)
 constexpr int TA_SOFTMAX_WARPS = 4 * TA_QT, TA_LOADER_WARPS = 4;
 constexpr int TA_THREADS = 32 * (TA_SOFTMAX_WARPS + TA_LOADER_WARPS + 1);
 constexpr int TA_TMEM_PER_Q = 256;         // S0 [0,64) S1 [64,128) O [128, 128+DHP)
@@ -79,15 +79,15 @@ struct AttnSmem {  // byte offsets from the 1024-B aligned base
   static constexpr int Q = 0;                                   // [qi][2 regions]
   static constexpr int P = Q + TA_QT * 2 * TA_QREGION;          // [qi][1 region: 64 keys]
   static constexpr int K = P + TA_QT * TA_QREGION;              // ring of [2 regions]
-  static constexpr int V = K + TA_RING * 2 * TA_KREGION;
-  static constexpr int BARS = V + TA_RING * 2 * TA_KREGION;
+  static constexpr int V = K + TA_KRING * 2 * TA_KREGION;
+  static constexpr int BARS = V + TA_VRING * 2 * TA_KREGION;
   static constexpr int TOTAL = BARS + 512 + 1024;               // barriers + alignment slack
 };
 
 // barrier indices
 constexpr int BAR_Q_FULL = 0;
-constexpr int BAR_K_FULL = 1, BAR_K_EMPTY = BAR_K_FULL + TA_RING, BAR_V_FULL = BAR_K_EMPTY + TA_RING, BAR_V_EMPTY = BAR_V_FULL + TA_RING;
-constexpr int BAR_S_FULL = BAR_V_EMPTY + TA_RING;   // [qi][2]
+constexpr int BAR_K_FULL = 1, BAR_K_EMPTY = BAR_K_FULL + TA_KRING, BAR_V_FULL = BAR_K_EMPTY + TA_KRING, BAR_V_EMPTY = BAR_V_FULL + TA_VRING;
+constexpr int BAR_S_FULL = BAR_V_EMPTY + TA_VRING;   // [qi][2]
 constexpr int BAR_S_EMPTY = BAR_S_FULL + 2 * TA_QT; // [qi][2]
 constexpr int BAR_P_FULL = BAR_S_EMPTY + 2 * TA_QT; // [qi]
 constexpr int BAR_O_FULL = BAR_P_FULL + TA_QT;      // [qi]
@@ -116,6 +116,10 @@ template <int DH, typename Front>
 __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base, uint32_t tmem_base) {
   constexpr int DHP = (DH + 15) / 16 * 16;      // head dim padded to the UMMA K/N granularity
   constexpr int CH = DH / 8;                     // 16-B chunks per row
+  // When the head dim has padding columns (72 -> 80), column DH of V holds 1.0 for every key, so O[:, DH] accumulates
+  // the row sum of the bf16-ROUNDED probabilities on the tensor core: no FADDs in the softmax, and the sum is rescaled
+  // together with O.
+  constexpr bool ONES_COL = (DHP > DH);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bars = smem_base + AttnSmem::BARS;
   auto bar = [&](int i) { return bars + 8u * i; };
@@ -123,47 +127,55 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
 
   if (warp >= TA_SOFTMAX_WARPS && warp < TA_SOFTMAX_WARPS + TA_LOADER_WARPS) {
     // ======================= loaders =======================
+    // Two independent streams of 64 threads (one thread per tile row): warps 0-1 load Q once and then the K ring, warps
+    // 2-3 the V ring.  K tiles are needed two rounds before the matching V tile, so decoupling the rings lets each
+    // stream run as far ahead as its own ring depth allows.
     const int lt = threadIdx.x - 32 * TA_SOFTMAX_WARPS;      // 0..127
-    constexpr int NL = 32 * TA_LOADER_WARPS;
-    for (int i = lt; i < TA_QT * TA_BM * CH; i += NL) {
-      const int r = i / CH, c = i % CH;                      // r: row within the CTA's 256 query rows
-      const __nv_bfloat16* src = fe.q_row(r);
-      const uint32_t dst = smem_base + AttnSmem::Q + (r / TA_BM) * 2 * TA_QREGION + (c >> 3) * TA_QREGION + sw128_off(r % TA_BM, c & 7);
-      cp_async16(dst, src ? src + c * 8 : fe.any_ptr(), src ? 16 : 0);
+    const bool is_v = lt >= 64;
+    const int lrow = lt & 63;
+    const int ring = is_v ? TA_VRING : TA_KRING;
+    const int bar_full = is_v ? BAR_V_FULL : BAR_K_FULL, bar_empty = is_v ? BAR_V_EMPTY : BAR_K_EMPTY;
+    const uint32_t ring_base = smem_base + (is_v ? AttnSmem::V : AttnSmem::K);
+    if (!is_v) {
+#pragma unroll
+      for (int i = 0; i < TA_QT * TA_BM / 64; ++i) {
+        const int r = i * 64 + lrow;                         // row within the CTA's 256 query rows
+        const __nv_bfloat16* src = fe.q_row(r);
+        const uint32_t dst = smem_base + AttnSmem::Q + (r / TA_BM) * 2 * TA_QREGION;
+#pragma unroll
+        for (int c = 0; c < CH; ++c)
+          cp_async16(dst + (c >> 3) * TA_QREGION + sw128_off(r % TA_BM, c & 7), src ? src + c * 8 : fe.any_ptr(), src ? 16 : 0);
+      }
     }
     cp_async_commit();
     auto publish = [&](int j) {   // tile j's copies of this thread have landed
       fence_proxy_async_smem();
-      mbar_arrive(bar(BAR_K_FULL + j % TA_RING));
-      mbar_arrive(bar(BAR_V_FULL + j % TA_RING));
+      mbar_arrive(bar(bar_full + j % ring));
+    };
+    auto q_ready = [&]() {
+      if (!is_v) { fence_proxy_async_smem(); mbar_arrive(bar(BAR_Q_FULL)); }
     };
     int published = -1;   // last tile handed to the MMA warp by this thread
     for (int j = 0; j < n_tiles; ++j) {
-      const int st = j % TA_RING;
-      const uint32_t par = ((j / TA_RING) & 1) ^ 1;
-      if (j >= 1 && !(mbar_try_wait(bar(BAR_K_EMPTY + st), par) && mbar_try_wait(bar(BAR_V_EMPTY + st), par))) {
+      const int st = j % ring;
+      const uint32_t par = ((j / ring) & 1) ^ 1;
+      if (j >= 1 && !mbar_try_wait(bar(bar_empty + st), par)) {
         // The ring slot is still in use.  Never block on it while holding back a tile that has already been requested:
         // the MMA warp may need tile j-1 before it can release this slot (deadlock otherwise).
         cp_async_wait<0>();
         publish(j - 1);
         published = j - 1;
       }
-      mbar_wait(bar(BAR_K_EMPTY + st), par);
-      mbar_wait(bar(BAR_V_EMPTY + st), par);
-      const uint32_t kb = smem_base + AttnSmem::K + st * 2 * TA_KREGION, vb = smem_base + AttnSmem::V + st * 2 * TA_KREGION;
-      for (int i = lt; i < TA_BN * CH; i += NL) {
-        const int r = i / CH, c = i % CH;
-        const __nv_bfloat16* ks = fe.k_row(j, r);
-        const __nv_bfloat16* vs = fe.v_row(j, r);
-        const uint32_t off = (c >> 3) * TA_KREGION + sw128_off(r, c & 7);
-        cp_async16(kb + off, ks ? ks + c * 8 : fe.any_ptr(), ks ? 16 : 0);
-        cp_async16(vb + off, vs ? vs + c * 8 : fe.any_ptr(), vs ? 16 : 0);
-      }
+      mbar_wait(bar(bar_empty + st), par);
+      const uint32_t dstb = ring_base + st * 2 * TA_KREGION;
+      const __nv_bfloat16* src = is_v ? fe.v_row(j, lrow) : fe.k_row(j, lrow);
+#pragma unroll
+      for (int c = 0; c < CH; ++c)
+        cp_async16(dstb + (c >> 3) * TA_KREGION + sw128_off(lrow, c & 7), src ? src + c * 8 : fe.any_ptr(), src ? 16 : 0);
       cp_async_commit();
       if (j == 0) {            // Q (first group) has landed once at most one group (tile 0) is pending
         cp_async_wait<1>();
-        fence_proxy_async_smem();
-        mbar_arrive(bar(BAR_Q_FULL));
+        q_ready();
       } else if (published < j - 1) {
         cp_async_wait<1>();    // tile j-1 has landed, tile j may still be in flight
         publish(j - 1);
@@ -171,20 +183,16 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
       }
     }
     cp_async_wait<0>();
-    if (n_tiles == 0) {
-      fence_proxy_async_smem();
-      mbar_arrive(bar(BAR_Q_FULL));
-    } else if (published < n_tiles - 1) {
-      publish(n_tiles - 1);
-    }
+    if (n_tiles == 0) q_ready();
+    else if (published < n_tiles - 1) publish(n_tiles - 1);
   } else if (warp == TA_SOFTMAX_WARPS + TA_LOADER_WARPS) {
     // ======================= MMA issuer =======================
     if (elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(TA_BM, TA_BN);
       constexpr uint32_t idesc_pv = umma_idesc_bf16_mn_b(TA_BM, DHP);
       auto issue_qk = [&](int qi, int j) {
-        const int st = j % TA_RING, sb = j & 1;
-        mbar_wait(bar(BAR_K_FULL + st), (j / TA_RING) & 1);
+        const int st = j % TA_KRING, sb = j & 1;
+        mbar_wait(bar(BAR_K_FULL + st), (j / TA_KRING) & 1);
         mbar_wait(bar(BAR_S_EMPTY + qi * 2 + sb), ((j >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t sQ = smem_base + AttnSmem::Q + qi * 2 * TA_QREGION;
@@ -202,10 +210,10 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
       for (int j = 0; j < 2 && j < n_tiles; ++j)
         for (int qi = 0; qi < TA_QT; ++qi) issue_qk(qi, j);
       for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % TA_RING;
+        const int st = j % TA_VRING;
         for (int qi = 0; qi < TA_QT; ++qi) {
           mbar_wait(bar(BAR_P_FULL + qi), j & 1);
-          if (qi == 0) mbar_wait(bar(BAR_V_FULL + st), (j / TA_RING) & 1);
+          if (qi == 0) mbar_wait(bar(BAR_V_FULL + st), (j / TA_VRING) & 1);
           tc_fence_after();
           const uint32_t sP = smem_base + AttnSmem::P + qi * TA_QREGION;
           const uint32_t sV = smem_base + AttnSmem::V + st * 2 * TA_KREGION;
@@ -236,24 +244,26 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
       mbar_wait(bar(BAR_S_FULL + qi * 2 + sb), (j >> 1) & 1);
       tc_fence_after();
       const int k0 = j * TA_BN;
-      const bool need_mask = k0 + TA_BN - 1 > key_lim;
-      // pass 1: row maximum of this tile
-      float mx = -INFINITY;
+      float sv[TA_BN];
       {
         uint32_t v0[32], v1[32];
         tmem_ld_32x32b_x32(t_row + sb * TA_BN, v0);
         tmem_ld_32x32b_x32(t_row + sb * TA_BN + 32, v1);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float a = __uint_as_float(v0[i]), b = __uint_as_float(v1[i]);
-          if (need_mask) {
-            if (k0 + i > key_lim) a = -INFINITY;
-            if (k0 + 32 + i > key_lim) b = -INFINITY;
-          }
-          mx = fmaxf(mx, fmaxf(a, b));
-        }
+        for (int i = 0; i < 32; ++i) { sv[i] = __uint_as_float(v0[i]); sv[32 + i] = __uint_as_float(v1[i]); }
       }
+      // S_j now lives in registers: the buffer can take QK_{j+2}
+      tc_fence_before();
+      mbar_arrive(bar(BAR_S_EMPTY + qi * 2 + sb));
+      // masking only in the tiles that reach beyond some row's limit (warp-uniform test; ISETP/FSEL per element only there)
+      if (__any_sync(0xffffffffu, k0 + TA_BN - 1 > key_lim)) {
+#pragma unroll
+        for (int i = 0; i < TA_BN; ++i) sv[i] = (k0 + i > key_lim) ? -INFINITY : sv[i];
+      }
+      float mx = fmaxf(sv[0], sv[1]);
+#pragma unroll
+      for (int i = 2; i < TA_BN; i += 2) mx = fmaxf(mx, fmaxf(sv[i], sv[i + 1]));
       // PV_{j-1} must have completed before P is overwritten or O is rescaled
       if (j > 0) {
         mbar_wait(bar(BAR_O_FULL + qi), (j - 1) & 1);
@@ -283,41 +293,28 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
         }
       }
       const float msc = (m_ref == -INFINITY) ? 0.f : m_ref * sl2;
-      // pass 2: probabilities -> bf16 P tile (swizzled K-major), row sum
+      // probabilities -> bf16 P tile (swizzled K-major)
       float rs = 0.f;
 #pragma unroll
-      for (int c0 = 0; c0 < TA_BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_row + sb * TA_BN + c0, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+      for (int c = 0; c < TA_BN / 8; ++c) {          // one 16-B chunk = 8 keys
+        uint32_t pk[4];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-          if (need_mask) {
-            if (k0 + c0 + i > key_lim) s0 = -INFINITY;
-            if (k0 + c0 + i + 1 > key_lim) s1 = -INFINITY;
-          }
-          const float p0 = exp2f(s0 * sl2 - msc), p1 = exp2f(s1 * sl2 - msc);
+        for (int i = 0; i < 4; ++i) {
+          const float p0 = exp2f(fmaf(sv[8 * c + 2 * i], sl2, -msc)), p1 = exp2f(fmaf(sv[8 * c + 2 * i + 1], sl2, -msc));
           __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-          pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
-          // the row sum uses the ROUNDED probabilities, so numerator (P V on bf16 P) and denominator stay consistent even
-          // when the stale exponent base makes the dominant term differ from exactly 1.0
-          const float2 hr = __bfloat1622float2(h);
-          rs += hr.x + hr.y;
+          pk[i] = *reinterpret_cast<uint32_t*>(&h);
+          if constexpr (!ONES_COL) {
+            // row sum of the ROUNDED probabilities (numerator and denominator stay consistent under the stale base)
+            rs += __uint_as_float(pk[i] << 16) + __uint_as_float(pk[i] & 0xffff0000u);
+          }
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {   // four 16-B chunks of this 32-key group
-          const uint32_t addr = sP + sw128_off(row, (c0 >> 3) + q);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]),
-                       "r"(pk[4 * q + 3]) : "memory");
-        }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + sw128_off(row, c)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                     : "memory");
       }
       l_run += rs;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(bar(BAR_P_FULL + qi));
-      mbar_arrive(bar(BAR_S_EMPTY + qi * 2 + sb));
     }
     float o[DHP];
     if (n_tiles > 0) {
@@ -331,6 +328,7 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[c0 + i] = __uint_as_float(v[i]);
       }
+      if constexpr (ONES_COL) l_run = o[DH];
     } else {
 #pragma unroll
       for (int i = 0; i < DHP; ++i) o[i] = 0.f;
@@ -455,11 +453,13 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attn_tcgen05_kernel(const Param
   const int warp = threadIdx.x >> 5;
   griddep_launch_dependents();
   if (threadIdx.x == 0) {
-    constexpr uint32_t NLOAD = 32 * TA_LOADER_WARPS;
+    constexpr uint32_t NLOAD = 32 * TA_LOADER_WARPS / 2;   // one 64-thread stream per ring
     mbar_init(bars + 8u * BAR_Q_FULL, NLOAD);
-    for (int s = 0; s < TA_RING; ++s) {
+    for (int s = 0; s < TA_KRING; ++s) {
       mbar_init(bars + 8u * (BAR_K_FULL + s), NLOAD);
       mbar_init(bars + 8u * (BAR_K_EMPTY + s), 1);
+    }
+    for (int s = 0; s < TA_VRING; ++s) {
       mbar_init(bars + 8u * (BAR_V_FULL + s), NLOAD);
       mbar_init(bars + 8u * (BAR_V_EMPTY + s), 1);
     }
@@ -478,6 +478,15 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attn_tcgen05_kernel(const Param
     uint4* z = reinterpret_cast<uint4*>(smem_raw + (smem_base - smem_u32(smem_raw)));
     const uint4 zero = make_uint4(0, 0, 0, 0);
     for (int i = threadIdx.x; i < AttnSmem::BARS / 16; i += TA_THREADS) z[i] = zero;
+  }
+  __syncthreads();
+  if constexpr (((DH + 15) / 16 * 16) > DH) {
+    // ones column (see attention_pipeline): V[key][DH] = 1.0 in every ring stage; cp.async never touches that chunk
+    for (int i = threadIdx.x; i < TA_VRING * TA_BN; i += TA_THREADS) {
+      const int st = i / TA_BN, r = i % TA_BN;
+      const uint32_t off = AttnSmem::V + st * 2 * TA_KREGION + (DH / 64) * TA_KREGION + sw128_off(r, (DH % 64) / 8) + (DH % 8) * 2;
+      *reinterpret_cast<__nv_bfloat16*>(smem_raw + (smem_base - smem_u32(smem_raw)) + off) = __float2bfloat16_rn(1.0f);
+    }
   }
   if (warp == TA_SOFTMAX_WARPS + TA_LOADER_WARPS) tmem_alloc<512>(tmem_slot);
   fence_proxy_async_smem();

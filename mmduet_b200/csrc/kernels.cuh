@@ -35,7 +35,7 @@ int launch_vit_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int T, in
 extern int g_attention_impl;  // 0 = mma.sync attention kernels (default), 1 = tcgen05/TMEM attention kernels
 int kv_attention_pick_splits(int max_rows, int Hkv, int n_streams, int max_kv_len, int num_sms);
 int launch_kv_attention(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, const int* stream_desc, const int* block_tables,
-                        int n_streams, int max_n_q, int total_q, float* o_part, float* ml_part, __nv_bfloat16* out, int Hq,
-                        int Hkv, int dh, int page_tokens, int n_splits, cudaStream_t s);
+                        int n_streams, int max_n_q, int total_q, int max_kv_len, float* o_part, float* ml_part, __nv_bfloat16* out,
+                        int Hq, int Hkv, int dh, int page_tokens, int n_splits, cudaStream_t s);
 
 }  // namespace mmd

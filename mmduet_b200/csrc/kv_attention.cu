@@ -261,7 +261,14 @@ __global__ void kv_attention_combine_kernel(const float* __restrict__ o_part, co
 
 }  // namespace
 
-int g_attention_impl = 0;  // 0 = mma.sync kernels (currently the faster ones), 1 = tcgen05/TMEM kernels (attn_tcgen05.cu)
+// 0 = mma.sync kernels, 1 = tcgen05/TMEM kernels (attn_tcgen05.cu), 2 = auto: tcgen05 for the ViT and for decoder steps
+// with >= 1024 stacked query rows or >= 16k context (where it is 1.2-1.5x faster), mma.sync for short single-frame steps.
+int g_attention_impl = 2;
+
+static bool kv_use_tc(int max_rows, int max_kv_len) {
+  if (g_attention_impl == 2) return max_rows >= 1024 || max_kv_len >= 16384;
+  return g_attention_impl == 1;
+}
 
 int launch_kv_attention_tc_main(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, const int* stream_desc, const int* block_tables,
                                 int n_streams, int max_n_q, int total_q, float* o_part, float* ml_part, int Hq, int Hkv, int n_splits,
@@ -269,11 +276,12 @@ int launch_kv_attention_tc_main(const __nv_bfloat16* q, const __nv_bfloat16* kv_
 
 int kv_attention_pick_splits(int max_rows, int Hkv, int n_streams, int max_kv_len, int num_sms) {
   // mma.sync kernel: 128 query rows per CTA, two CTAs per SM; tcgen05 kernel: 256 rows per CTA, one CTA per SM
-  const int rows_per_cta = g_attention_impl == 1 ? 2 * KA_BM : KA_BM;
+  const bool tc = kv_use_tc(max_rows, max_kv_len);
+  const int rows_per_cta = tc ? 2 * KA_BM : KA_BM;
   const int q_tiles = (max_rows + rows_per_cta - 1) / rows_per_cta;
   const int base = q_tiles * Hkv * n_streams;
   const int kv_tiles = (max_kv_len + KA_BN - 1) / KA_BN;
-  int splits = ((g_attention_impl == 1 ? 1 : 2) * num_sms + base - 1) / base;
+  int splits = ((tc ? 1 : 2) * num_sms + base - 1) / base;
   const int max_by_work = (kv_tiles + 3) / 4;  // at least ~4 key tiles (256 keys) per split
   if (splits > max_by_work) splits = max_by_work;
   if (splits > 32) splits = 32;
@@ -282,8 +290,8 @@ int kv_attention_pick_splits(int max_rows, int Hkv, int n_streams, int max_kv_le
 }
 
 int launch_kv_attention(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, const int* stream_desc, const int* block_tables,
-                        int n_streams, int max_n_q, int total_q, float* o_part, float* ml_part, __nv_bfloat16* out, int Hq,
-                        int Hkv, int dh, int page_tokens, int n_splits, cudaStream_t s) {
+                        int n_streams, int max_n_q, int total_q, int max_kv_len, float* o_part, float* ml_part, __nv_bfloat16* out,
+                        int Hq, int Hkv, int dh, int page_tokens, int n_splits, cudaStream_t s) {
   if (n_streams <= 0 || total_q <= 0) return 0;
   if (dh != KA_DH || page_tokens != KA_BN || Hq % Hkv != 0) return -2;
   constexpr int SMEM = (KA_BM + 4 * KA_BN) * KA_LDS * 2;
@@ -297,7 +305,7 @@ int launch_kv_attention(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, c
   dim3 grid(q_tiles * Hkv, n_splits, n_streams);
   const float scale_log2e = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
   const long long part_rows = (long long)total_q * Hq;
-  if (g_attention_impl == 1) {
+  if (kv_use_tc(max_n_q * G, max_kv_len)) {
     const int rc = launch_kv_attention_tc_main(q, kv_layer, stream_desc, block_tables, n_streams, max_n_q, total_q, o_part, ml_part, Hq,
                                                Hkv, n_splits, s);
     if (rc != 0) return rc;

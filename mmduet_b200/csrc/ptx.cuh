@@ -59,15 +59,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-// Bounded wait: a protocol bug must trap (-> CUDA error at the next sync) instead of hanging the GPU box.
+// Bounded wait: a protocol bug must trap (-> CUDA error at the next sync) instead of hanging the GPU box.  The timer is
+// read only once every 1024 failed probes, so the common spin loop is try_wait + a counter.
 #ifndef MMD_MBAR_TIMEOUT_NS
 #define MMD_MBAR_TIMEOUT_NS 4000000000ull
 #endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > MMD_MBAR_TIMEOUT_NS) __trap();
+    if ((++spins & 1023u) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > MMD_MBAR_TIMEOUT_NS) __trap();
+    }
   }
 }
 

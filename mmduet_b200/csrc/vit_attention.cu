@@ -232,7 +232,7 @@ int launch_vit_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int T,
 
 int launch_vit_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int T, int S, int H, int dh, int split_hi_lo, cudaStream_t s) {
   if (T <= 0) return 0;
-  if (g_attention_impl == 1) return launch_vit_attention_tc(qkv, out, T, S, H, dh, split_hi_lo, s);
+  if (g_attention_impl != 0) return launch_vit_attention_tc(qkv, out, T, S, H, dh, split_hi_lo, s);
   if (dh != 72) return -2;  // SigLIP-so400m head_dim; other sizes need another instantiation
   constexpr int DH = 72, DPAD = 80, LDS = 88;
   constexpr int SMEM = (VA_BM + 4 * VA_BN) * LDS * 2;

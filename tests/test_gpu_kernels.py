@@ -115,7 +115,7 @@ def attn_impl(env, request):
     _lib, ops, lib, ctx = env
     _lib.check(lib.mmd_set_attention_impl(request.param))
     yield request.param
-    lib.mmd_set_attention_impl(0)
+    lib.mmd_set_attention_impl(2)
 
 
 @pytest.mark.parametrize("T,S,H", [(2, 729, 16), (1, 729, 4), (3, 100, 2), (1, 64, 2), (1, 129, 1)])

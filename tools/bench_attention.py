@@ -43,5 +43,5 @@ for n_q, L in ((49, 3000), (49, 30000), (392, 3000), (392, 6000), (1, 6000)):
                                                  o_part.data_ptr(), ml.data_ptr(), outd.data_ptr(), Hq, Hkv, dh, ns, s()))
         res.append({"kernel": "kv_attention", "n_q": n_q, "L": L, "impl": impl, "splits": ns, "us": us, "tflops": fl / us / 1e6,
                     "kv_GBs": L * Hkv * dh * 2 * 2 / us / 1e3}); print(res[-1], flush=True)
-lib.mmd_set_attention_impl(0)
+lib.mmd_set_attention_impl(2)
 json.dump(res, open("gpurun_out/bench_attention.json", "w"), indent=1)
