@@ -64,6 +64,7 @@ MMD_API int mmd_set_gemm_2cta(int on);
 #define MMD_EPI_T_F32 2     /* out_f32[split][m][n] = acc                          */
 #define MMD_EPI_T_SWIGLU 3  /* out_bf16[m][n] = silu(acc_gate) * acc_up            */
 #define MMD_EPI_F32 4       /* out_f32 = acc + bias[n]                             */
+#define MMD_EPI_SWIGLU_PAIR 6 /* interleaved gate/up weight rows: out_bf16[m,j] = silu(acc[2j]) * acc[2j+1] (CTA-pair kernel) */
 #define MMD_EPI_BF16_HILO 5 /* v = act(acc + bias[n]); out[m,n] = bf16(v), out[m,N+n] = bf16(v - bf16(v)) */
 #define MMD_ACT_NONE 0
 #define MMD_ACT_GELU_TANH 1
@@ -173,7 +174,7 @@ typedef struct {
   const void* qkv_w; const float* qkv_b; /* bf16 [(Hq+2Hkv)*dh, H] (q;k;v stacked), fp32 */
   const void* o_w;                   /* bf16 [H, Hq*dh] */
   const float* ln2_w;                /* post_attention_layernorm */
-  const void* gate_w; const void* up_w;  /* bf16 [mlp, H] */
+  const void* gate_up_w;             /* bf16 [2*mlp, H], rows interleaved: row 2j = gate_proj row j, row 2j+1 = up_proj row j */
   const void* down_w;                /* bf16 [H, mlp] */
 } mmd_dec_layer;
 

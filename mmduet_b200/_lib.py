@@ -42,7 +42,7 @@ class ProjectorWeights(ctypes.Structure):
 
 
 class DecLayer(ctypes.Structure):
-    _fields_ = [(n, c_void_p) for n in ("ln1_w", "qkv_w", "qkv_b", "o_w", "ln2_w", "gate_w", "up_w", "down_w")]
+    _fields_ = [(n, c_void_p) for n in ("ln1_w", "qkv_w", "qkv_b", "o_w", "ln2_w", "gate_up_w", "down_w")]
 
 
 class DecWeights(ctypes.Structure):

@@ -439,26 +439,46 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
   const int s_down = choose_splits(c->num_sms, H, I, M);
   int attn_splits = mmd::kv_attention_pick_splits(st->max_n_q * (Hq / Hkv), Hkv, st->n_streams, st->max_kv_len, c->num_sms);
   if (attn_splits > kMaxAttnSplits) attn_splits = kMaxAttnSplits;
+  // Swap-AB + split-K (weights on the 128 UMMA rows, all SMs busy) wins up to ~1200 tokens per pass on this model
+  // (measured: 8/10/24-frame passes, profiles/r01_decoder_paths.md); the normal-orientation CTA-pair path (UMMA M = 256,
+  // TMA-store epilogue, interleaved gate/up + pairwise SwiGLU) only pays off for much larger multi-stream batches.
+  const bool big = M >= 2048;
+  auto gemm_big_f32 = [&](const void* act, const void* wt, int N, int K, int splits, int* eff) -> int {
+    mmd::GemmArgs a;
+    a.X = static_cast<const __nv_bfloat16*>(act); a.x_rows = M; a.ldx = K;
+    a.Y = static_cast<const __nv_bfloat16*>(wt); a.y_rows = N; a.ldy = K; a.K = K;
+    a.epi = mmd::EPI_F32; a.out = buf.planes; a.ldo = N; a.k_splits = splits; a.split_stride = (int64_t)M * N; a.force_2cta = 1;
+    *eff = mmd::gemm_effective_splits(K, splits);
+    return mmd::gemm_launch(c->gemm, a, s);
+  };
   for (int l = 0; l < w->n_layers; ++l) {
     const mmd_dec_layer& L = w->layers[l];
     int eff = 1;
-    PRUN(gemm_T_partials(c, buf.x, M, L.qkv_w, NQKV, H, s_qkv, buf.planes, s, &eff), "qkv_proj");
+    if (big) PRUN(gemm_big_f32(buf.x, L.qkv_w, NQKV, H, 1, &eff), "qkv_proj");
+    else PRUN(gemm_T_partials(c, buf.x, M, L.qkv_w, NQKV, H, s_qkv, buf.planes, s, &eff), "qkv_proj");
     __nv_bfloat16* kv_layer = static_cast<__nv_bfloat16*>(pool->pool) + (int64_t)l * pool->layer_stride;
     PRUNK(mmd::launch_qkv_finish(buf.planes, eff, (int64_t)M * NQKV, L.qkv_b, w->rope_cos, w->rope_sin, st->tok_pos, st->tok_slot,
                                 buf.q, kv_layer, M, Hq, Hkv, dh, MMD_PAGE_TOKENS, s), "qkv_finish");
     PRUNK2(mmd::launch_kv_attention(buf.q, kv_layer, st->stream_desc, st->block_tables, st->n_streams, st->max_n_q, M, st->max_kv_len, buf.o_part,
                                   buf.ml_part, buf.attn, Hq, Hkv, dh, MMD_PAGE_TOKENS, attn_splits, s), "kv_attention");
-    PRUN(gemm_T_partials(c, buf.attn, M, L.o_w, H, QD, s_o, buf.planes, s, &eff), "o_proj");
+    if (big) PRUN(gemm_big_f32(buf.attn, L.o_w, H, QD, 1, &eff), "o_proj");
+    else PRUN(gemm_T_partials(c, buf.attn, M, L.o_w, H, QD, s_o, buf.planes, s, &eff), "o_proj");
     PRUNK(mmd::launch_resid_add_rmsnorm(buf.resid, buf.planes, eff, (int64_t)M * H, L.ln2_w, buf.x, nullptr, M, H, w->rms_eps, s),
          "post_attention_layernorm");
     {
       mmd::GemmArgs a;
-      a.X = static_cast<const __nv_bfloat16*>(L.gate_w); a.X2 = static_cast<const __nv_bfloat16*>(L.up_w);
-      a.x_rows = I; a.ldx = H; a.Y = buf.x; a.y_rows = M; a.ldy = H; a.K = H;
-      a.epi = mmd::EPI_T_SWIGLU; a.out = buf.h; a.ldo = I;
+      const __nv_bfloat16* gu = static_cast<const __nv_bfloat16*>(L.gate_up_w);
+      if (big) {   // interleaved (gate, up) columns, SwiGLU on adjacent accumulator columns
+        a.X = buf.x; a.x_rows = M; a.ldx = H; a.Y = gu; a.y_rows = 2 * I; a.ldy = H; a.K = H;
+        a.epi = mmd::EPI_SWIGLU_PAIR; a.out = buf.h; a.ldo = I; a.force_2cta = 1;
+      } else {     // swap-AB: gate rows and up rows of the interleaved matrix as two strided operands
+        a.X = gu; a.X2 = gu + H; a.x_rows = I; a.ldx = 2 * (int64_t)H; a.Y = buf.x; a.y_rows = M; a.ldy = H; a.K = H;
+        a.epi = mmd::EPI_T_SWIGLU; a.out = buf.h; a.ldo = I;
+      }
       PRUN(mmd::gemm_launch(c->gemm, a, s), "gate_up_swiglu");
     }
-    PRUN(gemm_T_partials(c, buf.h, M, L.down_w, H, I, s_down, buf.planes, s, &eff), "down_proj");
+    if (big) PRUN(gemm_big_f32(buf.h, L.down_w, H, I, 3, &eff), "down_proj");
+    else PRUN(gemm_T_partials(c, buf.h, M, L.down_w, H, I, s_down, buf.planes, s, &eff), "down_proj");
     const bool last = (l + 1 == w->n_layers);
     const float* next_w = last ? w->final_norm_w : w->layers[l + 1].ln1_w;
     PRUNK(mmd::launch_resid_add_rmsnorm(buf.resid, buf.planes, eff, (int64_t)M * H, next_w, buf.x, last ? buf.hidden_f32 : nullptr, M,

@@ -370,8 +370,41 @@ __device__ __forceinline__ uint32_t stage_sw128_off(int r, int c) { return (uint
 
 template <int EPI, int ACT>
 __device__ __forceinline__ void epilogue_normal_tma(const GemmKernelParams& p, const CUtensorMap* tmOut, uint32_t t_row, int m_warp,
-                                                    int y0, int c_begin, int c_end, uint32_t stage) {
+                                                    int y0, int c_begin, int c_end, uint32_t stage, int plane) {
   const int lane = (int)lane_id();
+  if constexpr (EPI == EPI_SWIGLU_PAIR) {
+    // 128 accumulator columns = 64 (gate, up) pairs -> 64 bf16 outputs = one 128-B staging row
+#pragma unroll 1
+    for (int c0 = c_begin; c0 < c_end; c0 += 128) {
+      if (y0 + c0 >= p.y_rows) break;
+      uint32_t o[32];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_row + c0 + 32 * h, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {   // 4 accumulator columns -> 2 outputs -> one packed word
+          const float g0 = __uint_as_float(v[4 * g]), u0 = __uint_as_float(v[4 * g + 1]);
+          const float g1 = __uint_as_float(v[4 * g + 2]), u1 = __uint_as_float(v[4 * g + 3]);
+          o[8 * h + g] = pack_bf16(g0 / (1.0f + __expf(-g0)) * u0, g1 / (1.0f + __expf(-g1)) * u1);
+        }
+      }
+      if (lane == 0) bulk_wait_group_read0();
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stage + stage_sw128_off(lane, c)), "r"(o[4 * c]), "r"(o[4 * c + 1]),
+                     "r"(o[4 * c + 2]), "r"(o[4 * c + 3]) : "memory");
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmOut, stage, (y0 + c0) >> 1, m_warp);
+        bulk_commit_group();
+      }
+    }
+    return;
+  }
   if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_F32) {
 #pragma unroll 1
     for (int c0 = c_begin; c0 < c_end; c0 += 32) {
@@ -395,7 +428,7 @@ __device__ __forceinline__ void epilogue_normal_tma(const GemmKernelParams& p, c
       __syncwarp();
       if (lane == 0) {
         if constexpr (EPI == EPI_RESID_F32) tma_reduce_add_2d(tmOut, stage, y0 + c0, m_warp);
-        else tma_store_2d(tmOut, stage, y0 + c0, m_warp);
+        else tma_store_3d(tmOut, stage, y0 + c0, m_warp, plane);
         bulk_commit_group();
       }
     }
@@ -496,7 +529,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
   const int m_tiles = (p.x_rows + 2 * BM - 1) / (2 * BM);
   const int n_tiles = (p.y_rows + BN2 - 1) / BN2;
-  const int total_tiles = m_tiles * n_tiles;
+  const int total_tiles = m_tiles * n_tiles * p.k_splits;   // split-K (EPI_F32 only): plane ks of a 3-D output map
+  (void)m_tiles;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -525,8 +559,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (elect_one()) {
       uint32_t stage = 0, phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-        const int nt = tile % n_tiles, mt = tile / n_tiles;   // weight tiles fastest: an A row block is read once from HBM
-        for (int kb = 0; kb < p.kb_total; ++kb) {
+        const int ks = tile % p.k_splits, rest = tile / p.k_splits;
+        const int nt = rest % n_tiles, mt = rest / n_tiles;   // weight tiles fastest: an A row block is read once from HBM
+        const int kb_end = min(p.kb_total, (ks + 1) * p.kb_per_split);
+        for (int kb = ks * p.kb_per_split; kb < kb_end; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sB = sA + Cfg::A_BYTES;
@@ -548,14 +584,16 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN2;
-        for (int kb = 0; kb < p.kb_total; ++kb) {
+        const int ks = tile % p.k_splits;
+        const int kb0 = ks * p.kb_per_split, kb_end = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb_end; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
           const uint64_t dA = umma_desc_k_sw128(sA);
           const uint64_t dB = umma_desc_k_sw128(sA + Cfg::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) umma_f16_2cta(d_tmem, dA + 2u * k, dB + 2u * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) umma_f16_2cta(d_tmem, dA + 2u * k, dB + 2u * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit_2cta(empty_bar(stage), 0x3);
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -572,12 +610,13 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int lane_row = q * 32 + (int)lane_id();
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
-      const int nt = tile % n_tiles, mt = tile / n_tiles;   // weight tiles fastest: an A row block is read once from HBM
+      const int ks = tile % p.k_splits, rest = tile / p.k_splits;
+      const int nt = rest % n_tiles, mt = rest / n_tiles;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN2;
       const int m_warp = mt * 2 * BM + (int)rank * BM + q * 32;   // first output row of this warp's 32 lanes
-      epilogue_normal_tma<EPI, ACT>(p, &tmOut, t_row, m_warp, nt * BN2, c_begin, c_end, epi_stage_base + (warp - 2) * 4096);
+      epilogue_normal_tma<EPI, ACT>(p, &tmOut, t_row, m_warp, nt * BN2, c_begin, c_end, epi_stage_base + (warp - 2) * 4096, ks);
       tc_fence_before();
       mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -681,8 +720,9 @@ static int get_map(GemmContext* c, const void* ptr, int rows, int K, long long l
 }
 
 // Output tensor map for the TMA-store epilogue: [rows, width] fp32 (box 32 x 32) or bf16 (box 64 x 32), 128-B swizzle.
-static int get_out_map(GemmContext* c, const void* ptr, int rows, int width, long long ld, bool f32, CUtensorMap* out) {
-  MapKey key{ptr, rows, width, ld, f32 ? -2 : -3};
+static int get_out_map(GemmContext* c, const void* ptr, int rows, int width, long long ld, bool f32, CUtensorMap* out, int planes = 0,
+                       long long plane_stride = 0) {
+  MapKey key{ptr, rows, width, ld, (f32 ? -2 : -3) - 16 * planes};
   {
     std::lock_guard<std::mutex> lk(c->mu);
     auto it = c->maps.find(key);
@@ -694,11 +734,12 @@ static int get_out_map(GemmContext* c, const void* ptr, int rows, int width, lon
     return -2;
   }
   CUtensorMap m;
-  cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
-  cuuint32_t box[2] = {(cuuint32_t)(f32 ? 32 : 64), 32};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = c->encode(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+  const int rank = planes > 0 ? 3 : 2;   // planes > 0: split-K partial planes [planes][rows][width]
+  cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)rows, (cuuint64_t)(planes > 0 ? planes : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * esz, (cuuint64_t)plane_stride * esz};
+  cuuint32_t box[3] = {(cuuint32_t)(f32 ? 32 : 64), 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = c->encode(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims,
                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -817,19 +858,22 @@ static int launch_2cta(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
   int rc;
   if ((rc = get_map(c, a.X, a.x_rows, a.K, a.ldx, BM, &tmA)) != 0) return rc;
   if ((rc = get_map(c, a.Y, a.y_rows, a.K, a.ldy, BN2 / 2, &tmB)) != 0) return rc;
+  const int splits = (EPI == EPI_F32) ? gemm_effective_splits(a.K, a.k_splits) : 1;
   {
     const bool f32 = (EPI == EPI_RESID_F32 || EPI == EPI_F32);
-    const int width = a.y_rows * (EPI == EPI_BF16_HILO ? 2 : 1);
-    if ((rc = get_out_map(c, a.out, a.x_rows, width, a.ldo, f32, &tmOut)) != 0) return rc;
+    const int width = EPI == EPI_BF16_HILO ? a.y_rows * 2 : (EPI == EPI_SWIGLU_PAIR ? a.y_rows / 2 : a.y_rows);
+    // EPI_F32 always uses the 3-D form (plane coordinate = split index; one plane when there is no split-K)
+    if ((rc = get_out_map(c, a.out, a.x_rows, width, a.ldo, f32, &tmOut, EPI == EPI_F32 ? splits : 0,
+                          splits > 1 ? a.split_stride : (long long)a.x_rows * a.ldo)) != 0) return rc;
   }
   GemmKernelParams p;
   p.x_rows = a.x_rows; p.y_rows = a.y_rows;
   p.x_tiles = (a.x_rows + 2 * BM - 1) / (2 * BM);
   p.y_tiles = (a.y_rows + BN2 - 1) / BN2;
   p.kb_total = (a.K + BK - 1) / BK;
-  p.k_splits = 1; p.kb_per_split = p.kb_total;
+  p.k_splits = splits; p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.split_stride = 0; p.pdl_prefetch_x = 0; p.x_blocked = 0;
-  const long long tiles = (long long)p.x_tiles * p.y_tiles;
+  const long long tiles = (long long)p.x_tiles * p.y_tiles * splits;
   const int max_clusters = (a.max_ctas > 0 ? a.max_ctas : c->num_sms) / 2;
   const int clusters = (int)(tiles < max_clusters ? tiles : max_clusters);
   if (clusters <= 0) return 0;
@@ -852,7 +896,7 @@ static int launch_2cta(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
 template <int EPI, int ACT>
 static int launch_normal(GemmContext* c, const GemmArgs& a, cudaStream_t s) {
   if (a.y_rows % 8 != 0) { g_gemm_err = "normal-orientation GEMM needs N % 8 == 0"; return -2; }
-  if (g_gemm_use_2cta && a.x_rows >= 1024 && a.y_rows >= 192) {
+  if (g_gemm_use_2cta && (a.x_rows >= 1024 || a.force_2cta) && a.y_rows >= 192) {
     // N = 1152 (out_proj / fc2 / patch embed) tiles exactly by 192
     if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_F32) {
       static const bool no192 = getenv("MMD_NO_BN192") != nullptr;
@@ -883,6 +927,9 @@ int gemm_launch(GemmContext* c, const GemmArgs& a, cudaStream_t s) {
       if (a.act == ACT_GELU_ERF) return launch_normal<EPI_BF16_HILO, ACT_GELU_ERF>(c, a, s);
       if (a.act == ACT_NONE) return launch_normal<EPI_BF16_HILO, ACT_NONE>(c, a, s);
       break;
+    case EPI_SWIGLU_PAIR:
+      if (a.y_rows % 256 != 0) { g_gemm_err = "swiglu-pair gemm needs N % 256 == 0"; return -2; }
+      return launch_2cta<256, EPI_SWIGLU_PAIR, ACT_NONE>(c, a, s);
     case EPI_RESID_F32: return launch_normal<EPI_RESID_F32, ACT_NONE>(c, a, s);
     case EPI_F32: return launch_normal<EPI_F32, ACT_NONE>(c, a, s);
     case EPI_T_F32:

@@ -17,6 +17,7 @@ enum GemmEpi : int {
   EPI_T_F32 = 2,     // out_f32[split][m, n] = acc                (split-K partial planes, no bias)
   EPI_T_SWIGLU = 3,  // out_bf16[m, n] = silu(acc_gate) * acc_up  (two X operands: gate rows, up rows)
   EPI_F32 = 4,       // out_f32[m, n] = acc + bias[n]
+  EPI_SWIGLU_PAIR = 6, // normal orientation, weights interleaved (row 2j = gate_j, row 2j+1 = up_j): out_bf16[m, j] = silu(acc[2j]) * acc[2j+1]
   EPI_BF16_HILO = 5, // v = act(acc + bias[n]); out_bf16[m, n] = hi = bf16(v); out_bf16[m, N + n] = bf16(v - hi)  (ldo >= 2N)
 };
 enum GemmAct : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2 };
@@ -37,6 +38,7 @@ struct GemmArgs {
   int k_splits = 1;                   // only EPI_T_F32
   int64_t split_stride = 0;           // elements between partial planes
   int max_ctas = 0;                   // 0 = number of SMs
+  int force_2cta = 0;                 // use the CTA-pair kernel even for M < 1024 (decoder passes with >= ~200 tokens)
 };
 
 struct GemmContext;  // tensor-map cache + device properties

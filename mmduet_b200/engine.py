@@ -270,7 +270,9 @@ class DecoderEngine:
                      qkv_b=_f32(torch.cat([sd[p + f"self_attn.{n}_proj.bias"] for n in "qkv"], 0), dev),
                      o_w=_bf16(sd[p + "self_attn.o_proj.weight"], dev),
                      ln2_w=_f32(sd[p + "post_attention_layernorm.weight"], dev),
-                     gate_w=_bf16(sd[p + "mlp.gate_proj.weight"], dev), up_w=_bf16(sd[p + "mlp.up_proj.weight"], dev),
+                     # gate/up rows interleaved (2j = gate_j, 2j+1 = up_j): one weight stream, SwiGLU pairs adjacent
+                     gate_up_w=_bf16(torch.stack([sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]], 1)
+                                     .reshape(2 * cfg.mlp, H), dev),
                      down_w=_bf16(sd[p + "mlp.down_proj.weight"], dev))
             for k, v in t.items():
                 setattr(layers[i], k, v.data_ptr())
