@@ -195,7 +195,7 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the single JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not land on stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     from mmduet_b200 import _lib
     from mmduet_b200.arguments_live import LiveTestArguments
