@@ -234,49 +234,68 @@ __global__ void qkv_finish_kernel(const float* __restrict__ partial, int n_plane
                                   const float* __restrict__ sin_tab, const int* __restrict__ tok_pos,
                                   const int* __restrict__ tok_slot, __nv_bfloat16* __restrict__ q_out,
                                   __nv_bfloat16* __restrict__ kv_layer, int Hq, int Hkv, int dh, int page_tokens) {
-  // grid: (token, head) with head in [0, Hq + 2*Hkv); block: dh/2 threads, thread d handles the pair (d, d + dh/2)
+  // one block per token; 8 threads per head, thread t handles the 8 rotation pairs (d, d + dh/2) with d in [8t', 8t'+8)
+  // (dh = 128: half = 64 = 8 threads x 8 elements): 32-B vector loads of the split-K planes, 16-B bf16 stores
   pdl_prologue();
   const int tok = blockIdx.x;
-  const int head = blockIdx.y;
-  const int d = threadIdx.x;
+  const int head = threadIdx.x >> 3;
+  const int d0 = (threadIdx.x & 7) * 8;
   const int half = dh >> 1;
   const int N = (Hq + 2 * Hkv) * dh;
-  const int col0 = head * dh + d, col1 = col0 + half;
-  float x0 = bias ? __ldg(bias + col0) : 0.f, x1 = bias ? __ldg(bias + col1) : 0.f;
+  const int col0 = head * dh + d0, col1 = col0 + half;
+  float x0[8], x1[8];
+  if (bias != nullptr) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(bias + col0)), b = __ldg(reinterpret_cast<const float4*>(bias + col0 + 4));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(bias + col1)), d = __ldg(reinterpret_cast<const float4*>(bias + col1 + 4));
+    x0[0] = a.x; x0[1] = a.y; x0[2] = a.z; x0[3] = a.w; x0[4] = b.x; x0[5] = b.y; x0[6] = b.z; x0[7] = b.w;
+    x1[0] = c.x; x1[1] = c.y; x1[2] = c.z; x1[3] = c.w; x1[4] = d.x; x1[5] = d.y; x1[6] = d.z; x1[7] = d.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { x0[i] = 0.f; x1[i] = 0.f; }
+  }
   for (int p = 0; p < n_planes; ++p) {
     const float* pl = partial + p * plane_stride + (long long)tok * N;
-    x0 += __ldg(pl + col0);
-    x1 += __ldg(pl + col1);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(pl + col0)), b = __ldg(reinterpret_cast<const float4*>(pl + col0 + 4));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(pl + col1)), d = __ldg(reinterpret_cast<const float4*>(pl + col1 + 4));
+    x0[0] += a.x; x0[1] += a.y; x0[2] += a.z; x0[3] += a.w; x0[4] += b.x; x0[5] += b.y; x0[6] += b.z; x0[7] += b.w;
+    x1[0] += c.x; x1[1] += c.y; x1[2] += c.z; x1[3] += c.w; x1[4] += d.x; x1[5] += d.y; x1[6] += d.z; x1[7] += d.w;
   }
-  const int pos = tok_pos[tok];
-  if (head < Hq + Hkv) {  // q and k are rotated
-    const float c = __ldg(cos_tab + (long long)pos * half + d), sn = __ldg(sin_tab + (long long)pos * half + d);
-    const float r0 = x0 * c - x1 * sn;
-    const float r1 = x1 * c + x0 * sn;
-    x0 = r0;
-    x1 = r1;
+  if (head < Hq + Hkv) {  // q and k are rotated (rotate_half convention)
+    const int pos = tok_pos[tok];
+    const float* cp = cos_tab + (long long)pos * half + d0;
+    const float* sp = sin_tab + (long long)pos * half + d0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float c = __ldg(cp + i), sn = __ldg(sp + i);
+      const float r0 = x0[i] * c - x1[i] * sn;
+      const float r1 = x1[i] * c + x0[i] * sn;
+      x0[i] = r0;
+      x1[i] = r1;
+    }
   }
+  uint4 o0, o1;
+  o0.x = pack2(x0[0], x0[1]); o0.y = pack2(x0[2], x0[3]); o0.z = pack2(x0[4], x0[5]); o0.w = pack2(x0[6], x0[7]);
+  o1.x = pack2(x1[0], x1[1]); o1.y = pack2(x1[2], x1[3]); o1.z = pack2(x1[4], x1[5]); o1.w = pack2(x1[6], x1[7]);
+  __nv_bfloat16* dst;
   if (head < Hq) {
-    __nv_bfloat16* dst = q_out + ((long long)tok * Hq + head) * dh;
-    dst[d] = __float2bfloat16_rn(x0);
-    dst[d + half] = __float2bfloat16_rn(x1);
+    dst = q_out + ((long long)tok * Hq + head) * dh;
   } else {
     const int is_v = head >= Hq + Hkv;
     const int kvh = head - Hq - (is_v ? Hkv : 0);
     const int slot = tok_slot[tok];
     const int page = slot / page_tokens, off = slot % page_tokens;
-    __nv_bfloat16* dst = kv_layer + ((((long long)page * 2 + is_v) * Hkv + kvh) * page_tokens + off) * dh;
-    dst[d] = __float2bfloat16_rn(x0);
-    dst[d + half] = __float2bfloat16_rn(x1);
+    dst = kv_layer + ((((long long)page * 2 + is_v) * Hkv + kvh) * page_tokens + off) * dh;
   }
+  *reinterpret_cast<uint4*>(dst + d0) = o0;
+  *reinterpret_cast<uint4*>(dst + half + d0) = o1;
 }
 int launch_qkv_finish(const float* partial, int n_planes, long long plane_stride, const float* bias, const float* cos_tab,
                       const float* sin_tab, const int* tok_pos, const int* tok_slot, __nv_bfloat16* q_out,
                       __nv_bfloat16* kv_layer, int M, int Hq, int Hkv, int dh, int page_tokens, cudaStream_t s) {
   if (M <= 0) return 0;
-  if (dh % 2 || dh / 2 > 1024) return -2;
-  dim3 grid(M, Hq + 2 * Hkv);
-  launch_k(qkv_finish_kernel, grid, dim3(dh / 2), 0, s, partial, n_planes, plane_stride, bias, cos_tab, sin_tab, tok_pos, tok_slot,
+  const int heads = Hq + 2 * Hkv;
+  if (dh != 128 || heads * 8 > 1024) return -2;
+  launch_k(qkv_finish_kernel, dim3(M), dim3(heads * 8), 0, s, partial, n_planes, plane_stride, bias, cos_tab, sin_tab, tok_pos, tok_slot,
            q_out, kv_layer, Hq, Hkv, dh, page_tokens);
   return 0;
 }
