@@ -5,7 +5,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmduet_b200.so")
+LIB_PATH = os.environ.get("MMD_LIB_PATH") or os.path.join(_HERE, "libmmduet_b200.so")   # override: debug builds only
 
 c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 

@@ -4,10 +4,12 @@
 // scores, the tensor pipe computes the other tile's products.  Keys/values stream in 64-key tiles shared by both.
 //
 //   S = Q K^T   : UMMA 128 x 64 x 16, A = Q tile (smem, K-major), B = K tile (smem, K-major)  -> TMEM, 2 buffers per q tile
-//   O += P V    : UMMA 128 x DH x 16, A = P tile (smem, K-major), B = V tile (smem, MN-major: the same [key][d] image
-//                 the loader writes for K, no transpose)                                        -> TMEM, accumulated there
+//   O += P V    : UMMA 128 x DH x 16, A = P tile read FROM TMEM (bf16 pairs written over the S buffer it came from),
+//                 B = V tile (smem, MN-major: the same [key][d] image the loader writes for K, no transpose)
+//                                                                                               -> TMEM, accumulated there
 //   softmax     : 2 x 4 warps, ONE THREAD PER QUERY ROW (TMEM lane): tcgen05.ld the score row, running max/sum in
-//                 registers with no shuffles, P stored to shared memory as bf16 in the 128-B-swizzled K-major layout.
+//                 registers with no shuffles, P stored back to TMEM with tcgen05.st (no shared-memory round trip, and
+//                 no wait for the previous PV: the only loop-carried dependency left is S_j itself).
 //                 O stays in TMEM across tiles; it is rescaled (tcgen05.ld / st) only when the running maximum grows by
 //                 more than 2^8 ("lazy rescaling"), otherwise the stale maximum keeps serving as the exponent base.
 //   loaders     : 4 warps, 16-B cp.async into the swizzled operand layout (zero fill for rows past the end and for the
@@ -34,9 +36,9 @@ constexpr int TA_QT = 2;                   // query tiles per CTA
 constexpr int TA_BN = 64;                  // keys per tile
 constexpr int TA_QREGION = TA_BM * 128;    // one 64-column swizzled region of a 128-row operand (16 KB)
 constexpr int TA_KREGION = TA_BN * 128;    // same for a 64-row operand (8 KB)
-constexpr int TA_KRING = 4, TA_VRING = 3;   // K is consumed two tiles ahead of V (QK^T runs ahead of the softmax)
+constexpr int TA_KRING = 4, TA_VRING = 4;
 constexpr int TA_SOFTMAX_WARPS = 4 * TA_QT, TA_LOADER_WARPS = 4;
-constexpr int TA_THREADS = 32 * (TA_SOFTMAX_WARPS + TA_LOADER_WARPS + 1);
+constexpr int TA_THREADS = 32 * (TA_SOFTMAX_WARPS + TA_LOADER_WARPS + 4);   // MMA warp + 3 idle warps: setmaxnreg works on whole warpgroups
 constexpr int TA_TMEM_PER_Q = 256;         // S0 [0,64) S1 [64,128) O [128, 128+DHP)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
@@ -74,11 +76,46 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// warpgroup register reallocation: the kernel starts with 128 registers per thread (512 threads); the loader warpgroup
+// and the MMA warpgroup hand most of theirs to the two softmax warpgroups (64 scores + 64..128 outputs per thread).
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// named barriers (ids 1, 2; id 0 is __syncthreads): the two softmax groups hand the MUFU to each other
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Debug timeline (only in builds with -DMMD_ATTN_TRACE, see tools/trace_attn.py): CTA (0,0,0) records %clock at the
+// pipeline's hand-over points, [role][tile][event].
+#ifdef MMD_ATTN_TRACE
+__device__ uint32_t* g_attn_trace = nullptr;
+__device__ __forceinline__ uint32_t* trace_base() {
+  return (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? g_attn_trace : nullptr;
+}
+__device__ __forceinline__ void trace_ev(uint32_t* tr, int role, int j, int e) {
+  if (tr != nullptr && j < 64) {
+    uint32_t c;
+    asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+    tr[(role * 64 + j) * 8 + e] = c;
+  }
+}
+#define TRACE_INIT uint32_t* const trace_ptr = trace_base()
+#define TRACE_EV(role, j, e) trace_ev(trace_ptr, role, j, e)
+#else
+#define TRACE_INIT
+#define TRACE_EV(role, j, e)
+#endif
 
 struct AttnSmem {  // byte offsets from the 1024-B aligned base
   static constexpr int Q = 0;                                   // [qi][2 regions]
-  static constexpr int P = Q + TA_QT * 2 * TA_QREGION;          // [qi][1 region: 64 keys]
-  static constexpr int K = P + TA_QT * TA_QREGION;              // ring of [2 regions]
+  static constexpr int K = Q + TA_QT * 2 * TA_QREGION;          // ring of [2 regions]
   static constexpr int V = K + TA_KRING * 2 * TA_KREGION;
   static constexpr int BARS = V + TA_VRING * 2 * TA_KREGION;
   static constexpr int TOTAL = BARS + 512 + 1024;               // barriers + alignment slack
@@ -88,8 +125,7 @@ struct AttnSmem {  // byte offsets from the 1024-B aligned base
 constexpr int BAR_Q_FULL = 0;
 constexpr int BAR_K_FULL = 1, BAR_K_EMPTY = BAR_K_FULL + TA_KRING, BAR_V_FULL = BAR_K_EMPTY + TA_KRING, BAR_V_EMPTY = BAR_V_FULL + TA_VRING;
 constexpr int BAR_S_FULL = BAR_V_EMPTY + TA_VRING;   // [qi][2]
-constexpr int BAR_S_EMPTY = BAR_S_FULL + 2 * TA_QT; // [qi][2]
-constexpr int BAR_P_FULL = BAR_S_EMPTY + 2 * TA_QT; // [qi]
+constexpr int BAR_P_FULL = BAR_S_FULL + 2 * TA_QT;  // [qi]
 constexpr int BAR_O_FULL = BAR_P_FULL + TA_QT;      // [qi]
 constexpr int BAR_COUNT = BAR_O_FULL + TA_QT;
 
@@ -124,36 +160,37 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
   const uint32_t bars = smem_base + AttnSmem::BARS;
   auto bar = [&](int i) { return bars + 8u * i; };
   const int n_tiles = fe.n_tiles();
+  TRACE_INIT;
 
   if (warp >= TA_SOFTMAX_WARPS && warp < TA_SOFTMAX_WARPS + TA_LOADER_WARPS) {
     // ======================= loaders =======================
-    // Two independent streams of 64 threads (one thread per tile row): warps 0-1 load Q once and then the K ring, warps
-    // 2-3 the V ring.  K tiles are needed two rounds before the matching V tile, so decoupling the rings lets each
-    // stream run as far ahead as its own ring depth allows.
+    // Two independent streams of 64 threads: warps 0-1 feed the K ring, warps 2-3 the V ring (K tiles are needed two
+    // rounds before the matching V tile, so each stream runs as far ahead as its own ring allows); all four load Q first.
+    // Work is split in 16-B units with consecutive lanes on consecutive chunks of a row, so one warp instruction reads
+    // whole rows (full sectors) instead of one chunk from each of 32 rows.
+    reg_dec<72>();
     const int lt = threadIdx.x - 32 * TA_SOFTMAX_WARPS;      // 0..127
     const bool is_v = lt >= 64;
     const int lrow = lt & 63;
     const int ring = is_v ? TA_VRING : TA_KRING;
     const int bar_full = is_v ? BAR_V_FULL : BAR_K_FULL, bar_empty = is_v ? BAR_V_EMPTY : BAR_K_EMPTY;
     const uint32_t ring_base = smem_base + (is_v ? AttnSmem::V : AttnSmem::K);
-    if (!is_v) {
-#pragma unroll
-      for (int i = 0; i < TA_QT * TA_BM / 64; ++i) {
-        const int r = i * 64 + lrow;                         // row within the CTA's 256 query rows
-        const __nv_bfloat16* src = fe.q_row(r);
-        const uint32_t dst = smem_base + AttnSmem::Q + (r / TA_BM) * 2 * TA_QREGION;
-#pragma unroll
-        for (int c = 0; c < CH; ++c)
-          cp_async16(dst + (c >> 3) * TA_QREGION + sw128_off(r % TA_BM, c & 7), src ? src + c * 8 : fe.any_ptr(), src ? 16 : 0);
-      }
+#pragma unroll 4
+    for (int u = lt; u < TA_QT * TA_BM * CH; u += 32 * TA_LOADER_WARPS) {
+      const int r = u / CH, c = u % CH;                      // row within the CTA's 256 query rows, 16-B chunk
+      const __nv_bfloat16* src = fe.q_row(r);
+      const uint32_t dst = smem_base + AttnSmem::Q + (r / TA_BM) * 2 * TA_QREGION + (c >> 3) * TA_QREGION + sw128_off(r % TA_BM, c & 7);
+      cp_async16(dst, src ? src + c * 8 : fe.any_ptr(), src ? 16 : 0);
     }
     cp_async_commit();
     auto publish = [&](int j) {   // tile j's copies of this thread have landed
       fence_proxy_async_smem();
       mbar_arrive(bar(bar_full + j % ring));
+      if (lrow == 0) TRACE_EV(4 + is_v, j, 2);
     };
     auto q_ready = [&]() {
-      if (!is_v) { fence_proxy_async_smem(); mbar_arrive(bar(BAR_Q_FULL)); }
+      fence_proxy_async_smem();
+      mbar_arrive(bar(BAR_Q_FULL));
     };
     int published = -1;   // last tile handed to the MMA warp by this thread
     for (int j = 0; j < n_tiles; ++j) {
@@ -166,12 +203,19 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
         publish(j - 1);
         published = j - 1;
       }
+      if (lrow == 0) TRACE_EV(4 + is_v, j, 0);
       mbar_wait(bar(bar_empty + st), par);
+      if (lrow == 0) TRACE_EV(4 + is_v, j, 1);
       const uint32_t dstb = ring_base + st * 2 * TA_KREGION;
-      const __nv_bfloat16* src = is_v ? fe.v_row(j, lrow) : fe.k_row(j, lrow);
+      int valid;                                             // rows past `valid` are zero-filled
+      const __nv_bfloat16* tile = fe.kv_tile(j, is_v, valid);
+      const long long rstride = fe.kv_row_stride();
 #pragma unroll
-      for (int c = 0; c < CH; ++c)
-        cp_async16(dstb + (c >> 3) * TA_KREGION + sw128_off(lrow, c & 7), src ? src + c * 8 : fe.any_ptr(), src ? 16 : 0);
+      for (int i = 0; i < CH; ++i) {
+        const int u = i * 64 + lrow, r = u / CH, c = u % CH;
+        const bool ok = r < valid;
+        cp_async16(dstb + (c >> 3) * TA_KREGION + sw128_off(r, c & 7), ok ? tile + r * rstride + c * 8 : fe.any_ptr(), ok ? 16 : 0);
+      }
       cp_async_commit();
       if (j == 0) {            // Q (first group) has landed once at most one group (tile 0) is pending
         cp_async_wait<1>();
@@ -185,15 +229,19 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
     cp_async_wait<0>();
     if (n_tiles == 0) q_ready();
     else if (published < n_tiles - 1) publish(n_tiles - 1);
-  } else if (warp == TA_SOFTMAX_WARPS + TA_LOADER_WARPS) {
-    // ======================= MMA issuer =======================
-    if (elect_one()) {
+  } else if (warp >= TA_SOFTMAX_WARPS + TA_LOADER_WARPS) {
+    // ======================= MMA issuer (first warp of the last warpgroup; the other three only give up registers) ====
+    reg_dec<56>();
+    if (warp == TA_SOFTMAX_WARPS + TA_LOADER_WARPS && elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(TA_BM, TA_BN);
       constexpr uint32_t idesc_pv = umma_idesc_bf16_mn_b(TA_BM, DHP);
       auto issue_qk = [&](int qi, int j) {
         const int st = j % TA_KRING, sb = j & 1;
+        TRACE_EV(2 + qi, j, 4);
         mbar_wait(bar(BAR_K_FULL + st), (j / TA_KRING) & 1);
-        mbar_wait(bar(BAR_S_EMPTY + qi * 2 + sb), ((j >> 1) & 1) ^ 1);
+        TRACE_EV(2 + qi, j, 5);
+        // No "S buffer free" barrier: QK_j is issued after PV_{j-2} (which read P_{j-2} from this buffer, itself written
+        // after S_{j-2} had been read), and the tensor pipe executes this thread's MMAs in issue order.
         tc_fence_after();
         const uint32_t sQ = smem_base + AttnSmem::Q + qi * 2 * TA_QREGION;
         const uint32_t sK = smem_base + AttnSmem::K + st * 2 * TA_KREGION;
@@ -205,6 +253,7 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
         }
         umma_commit(bar(BAR_S_FULL + qi * 2 + sb));
         if (qi == TA_QT - 1) umma_commit(bar(BAR_K_EMPTY + st));   // both q tiles have consumed K_j
+        TRACE_EV(2 + qi, j, 6);
       };
       mbar_wait(bar(BAR_Q_FULL), 0);
       for (int j = 0; j < 2 && j < n_tiles; ++j)
@@ -212,19 +261,23 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % TA_VRING;
         for (int qi = 0; qi < TA_QT; ++qi) {
+          TRACE_EV(2 + qi, j, 0);
           mbar_wait(bar(BAR_P_FULL + qi), j & 1);
+          TRACE_EV(2 + qi, j, 1);
           if (qi == 0) mbar_wait(bar(BAR_V_FULL + st), (j / TA_VRING) & 1);
+          TRACE_EV(2 + qi, j, 2);
           tc_fence_after();
-          const uint32_t sP = smem_base + AttnSmem::P + qi * TA_QREGION;
+          // P_j (bf16) sits in TMEM over the first 32 columns of the S buffer it was computed from: 8 columns per K=16 step
+          const uint32_t tP = tmem_base + qi * TA_TMEM_PER_Q + (j & 1) * TA_BN;
           const uint32_t sV = smem_base + AttnSmem::V + st * 2 * TA_KREGION;
 #pragma unroll
           for (int k = 0; k < TA_BN / 16; ++k) {
-            const uint64_t da = umma_desc_k_sw128(sP) + 2u * k;
             const uint64_t db = umma_desc_mn_sw128(sV, TA_KREGION) + (uint64_t)((k * 2048) >> 4);
-            umma_f16(tmem_base + qi * TA_TMEM_PER_Q + 2 * TA_BN, da, db, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+            umma_f16_ts(tmem_base + qi * TA_TMEM_PER_Q + 2 * TA_BN, tP + 8 * k, db, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(bar(BAR_O_FULL + qi));
           if (qi == TA_QT - 1) umma_commit(bar(BAR_V_EMPTY + st));
+          TRACE_EV(2 + qi, j, 3);
           if (j + 2 < n_tiles) issue_qk(qi, j + 2);
         }
       }
@@ -232,16 +285,24 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
     __syncwarp();
   } else {
     // ======================= softmax: one thread per query row, one warpgroup per query tile =======================
+    reg_inc<192>();
     const int qi = warp >> 2;
     const int row = (warp & 3) * 32 + lane;                 // row within the query tile = TMEM lane
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + qi * TA_TMEM_PER_Q;
-    const uint32_t sP = smem_base + AttnSmem::P + qi * TA_QREGION;
     float m_ref = -INFINITY, l_run = 0.f;
     const int key_lim = fe.key_limit(qi * TA_BM + row);    // tile-local key indices > key_lim are masked for this row
     const float sl2 = fe.scale_log2e();
+    // MUFU.EX2 runs at 16 lanes/clk/SM: the exponentials of one key tile (2 x 128 x 64) keep it busy for >= 1024 clk, as
+    // long as both tiles' tensor work.  The groups therefore take turns in the exponential phase (named barriers 1 + qi:
+    // "group qi may go"), so one group's TMEM loads, max and rescale overlap the other group's MUFU stream instead of
+    // both queueing on it and then both leaving it idle.
+    constexpr int NSM = 32 * TA_SOFTMAX_WARPS;
+    if (qi == 1 && n_tiles > 0) named_bar_arrive(1, NSM);
     for (int j = 0; j < n_tiles; ++j) {
       const int sb = j & 1;
+      if (row == 0) TRACE_EV(qi, j, 0);
       mbar_wait(bar(BAR_S_FULL + qi * 2 + sb), (j >> 1) & 1);
+      if (row == 0) TRACE_EV(qi, j, 1);
       tc_fence_after();
       const int k0 = j * TA_BN;
       float sv[TA_BN];
@@ -253,29 +314,25 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
 #pragma unroll
         for (int i = 0; i < 32; ++i) { sv[i] = __uint_as_float(v0[i]); sv[32 + i] = __uint_as_float(v1[i]); }
       }
-      // S_j now lives in registers: the buffer can take QK_{j+2}
-      tc_fence_before();
-      mbar_arrive(bar(BAR_S_EMPTY + qi * 2 + sb));
       // masking only in the tiles that reach beyond some row's limit (warp-uniform test; ISETP/FSEL per element only there)
       if (__any_sync(0xffffffffu, k0 + TA_BN - 1 > key_lim)) {
 #pragma unroll
         for (int i = 0; i < TA_BN; ++i) sv[i] = (k0 + i > key_lim) ? -INFINITY : sv[i];
       }
+      if (row == 0) TRACE_EV(qi, j, 2);
       float mx = fmaxf(sv[0], sv[1]);
 #pragma unroll
       for (int i = 2; i < TA_BN; i += 2) mx = fmaxf(mx, fmaxf(sv[i], sv[i + 1]));
-      // PV_{j-1} must have completed before P is overwritten or O is rescaled
-      if (j > 0) {
-        mbar_wait(bar(BAR_O_FULL + qi), (j - 1) & 1);
-        tc_fence_after();
-      }
       const float m_new = fmaxf(m_ref, mx);
       const bool need = j > 0 && m_new > m_ref && (m_ref == -INFINITY || (m_new - m_ref) * sl2 > 8.0f);
       if (j == 0) {
         m_ref = m_new;
       } else if (__any_sync(0xffffffffu, need)) {
         // lazy rescaling: O (TMEM) and l move to the new exponent base.  tcgen05.ld/st are .sync.aligned, so the whole
-        // warp takes this path together; rows that do not need it rescale by 1.
+        // warp takes this path together; rows that do not need it rescale by 1.  PV_{j-1} must have completed first
+        // (it is the newest PV that can have been issued, so the barrier is at most one phase ahead of this parity).
+        mbar_wait(bar(BAR_O_FULL + qi), (j - 1) & 1);
+        tc_fence_after();
         const float f = !need ? 1.f : ((m_ref == -INFINITY) ? 0.f : exp2f((m_ref - m_new) * sl2));
 #pragma unroll
         for (int c0 = 0; c0 < DHP; c0 += 16) {
@@ -292,15 +349,19 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
           m_ref = m_new;
         }
       }
+      named_bar_sync(1 + qi, NSM);
+      if (row == 0) TRACE_EV(qi, j, 3);
       const float msc = (m_ref == -INFINITY) ? 0.f : m_ref * sl2;
-      // probabilities -> bf16 P tile (swizzled K-major)
+      // probabilities -> bf16 P tile, written back into TMEM over the S buffer just read (two keys per 32-bit column).
+      // PV_{j-2}, the last reader of these columns, completed before S_j was produced, so no wait is needed here, and
+      // the softmax of tile j+1 can start while PV_j is still running.
       float rs = 0.f;
 #pragma unroll
-      for (int c = 0; c < TA_BN / 8; ++c) {          // one 16-B chunk = 8 keys
-        uint32_t pk[4];
+      for (int c = 0; c < TA_BN / 32; ++c) {         // 16 columns = 32 keys per store
+        uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float p0 = exp2f(fmaf(sv[8 * c + 2 * i], sl2, -msc)), p1 = exp2f(fmaf(sv[8 * c + 2 * i + 1], sl2, -msc));
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = exp2f(fmaf(sv[32 * c + 2 * i], sl2, -msc)), p1 = exp2f(fmaf(sv[32 * c + 2 * i + 1], sl2, -msc));
           __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
           pk[i] = *reinterpret_cast<uint32_t*>(&h);
           if constexpr (!ONES_COL) {
@@ -308,14 +369,21 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
             rs += __uint_as_float(pk[i] << 16) + __uint_as_float(pk[i] & 0xffff0000u);
           }
         }
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sP + sw128_off(row, c)), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
-                     : "memory");
+        tmem_st_32x32b_x16(t_row + sb * TA_BN + 16 * c, pk);
       }
       l_run += rs;
-      fence_proxy_async_smem();
+      if (qi == 0 || j + 1 < n_tiles) named_bar_arrive(2 - qi, NSM);
+      if (row == 0) TRACE_EV(qi, j, 4);
+      tmem_st_wait();
+      if (row == 0) TRACE_EV(qi, j, 5);
+      // The MMA thread must have consumed P_FULL phase j-1 before phase j can complete (it waits on parities, so a
+      // barrier two phases ahead would look unfinished): PV_{j-1} done implies that, one whole softmax iteration later.
+      if (j > 0) mbar_wait(bar(BAR_O_FULL + qi), (j - 1) & 1);
       tc_fence_before();
       mbar_arrive(bar(BAR_P_FULL + qi));
+      if (row == 0) TRACE_EV(qi, j, 6);
     }
+    if (row == 0) TRACE_EV(6, qi, 2);
     float o[DHP];
     if (n_tiles > 0) {
       mbar_wait(bar(BAR_O_FULL + qi), (n_tiles - 1) & 1);
@@ -333,7 +401,11 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
 #pragma unroll
       for (int i = 0; i < DHP; ++i) o[i] = 0.f;
     }
-    fe.store(qi * TA_BM + row, o, m_ref, l_run);
+    if (row == 0) TRACE_EV(6, qi, 3);
+    // Output goes through the group's own (now idle) Q region so that global stores are whole rows per warp
+    // instruction instead of one 16-B piece from each of 32 rows; named barrier 3 + qi synchronises the group.
+    fe.store(qi, row, o, m_ref, l_run, smem_base + AttnSmem::Q + qi * 2 * TA_QREGION, 3 + qi);
+    if (row == 0) TRACE_EV(6, qi, 4);
   }
 }
 
@@ -355,31 +427,42 @@ struct VitFront {
   __device__ int n_tiles() const { return (p.S + TA_BN - 1) / TA_BN; }
   __device__ const __nv_bfloat16* any_ptr() const { return p.qkv; }
   __device__ const __nv_bfloat16* q_row(int r) const { return q0 + r < p.S ? gQ + (long long)(q0 + r) * row_stride : nullptr; }
-  __device__ const __nv_bfloat16* k_row(int j, int r) const { const int k = j * TA_BN + r; return k < p.S ? gK + (long long)k * row_stride : nullptr; }
-  __device__ const __nv_bfloat16* v_row(int j, int r) const { const int k = j * TA_BN + r; return k < p.S ? gV + (long long)k * row_stride : nullptr; }
+  __device__ const __nv_bfloat16* kv_tile(int j, bool is_v, int& valid) const {
+    valid = min(TA_BN, p.S - j * TA_BN);
+    return (is_v ? gV : gK) + (long long)j * TA_BN * row_stride;
+  }
+  __device__ long long kv_row_stride() const { return row_stride; }
   __device__ int key_limit(int) const { return p.S - 1; }
   __device__ float scale_log2e() const { return p.scale_log2e; }
   template <int DHP>
-  __device__ void store(int row, const float (&o)[DHP], float, float l) const {
-    const int qr = q0 + row;
-    if (qr >= p.S) return;
+  __device__ void store(int qi, int row, const float (&o)[DHP], float, float l, uint32_t stage, int bar_id) const {
+    constexpr int CHO = DH / 8, PITCH = DH * 2;              // 16-B chunks and bytes per staged row
     const float inv = 1.f / l;
     const int out_stride = (p.split_hi_lo ? 2 : 1) * p.H * DH;
-    __nv_bfloat16* ob = p.out + ((long long)t * p.S + qr) * out_stride + h * DH;
+    const int halves = p.split_hi_lo ? 2 : 1;
+    for (int half = 0; half < halves; ++half) {
 #pragma unroll
-    for (int c = 0; c < DH; c += 8) {
-      uint32_t hi[4], lo[4];
+      for (int c = 0; c < CHO; ++c) {
+        uint32_t w[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float a = o[c + 2 * i] * inv, b = o[c + 2 * i + 1] * inv;
-        __nv_bfloat162 hv = __floats2bfloat162_rn(a, b);
-        hi[i] = *reinterpret_cast<uint32_t*>(&hv);
-        const float2 hf = __bfloat1622float2(hv);
-        __nv_bfloat162 lv = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-        lo[i] = *reinterpret_cast<uint32_t*>(&lv);
+        for (int i = 0; i < 4; ++i) {
+          const float a = o[c * 8 + 2 * i] * inv, b = o[c * 8 + 2 * i + 1] * inv;
+          __nv_bfloat162 hv = __floats2bfloat162_rn(a, b);
+          if (half == 1) {                                   // lo = what the bf16 rounding of hi dropped
+            const float2 hf = __bfloat1622float2(hv);
+            hv = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+          }
+          w[i] = *reinterpret_cast<uint32_t*>(&hv);
+        }
+        sts128(stage + row * PITCH + c * 16, w[0], w[1], w[2], w[3]);
       }
-      *reinterpret_cast<uint4*>(ob + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-      if (p.split_hi_lo) *reinterpret_cast<uint4*>(ob + p.H * DH + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      named_bar_sync(bar_id, TA_BM);
+      __nv_bfloat16* ob = p.out + (long long)t * p.S * out_stride + half * p.H * DH + h * DH;
+      for (int u = row; u < TA_BM * CHO; u += TA_BM) {
+        const int r = u / CHO, c = u % CHO, qr = q0 + qi * TA_BM + r;
+        if (qr < p.S) *reinterpret_cast<uint4*>(ob + (long long)qr * out_stride + c * 8) = lds128(stage + r * PITCH + c * 16);
+      }
+      if (half + 1 < halves) named_bar_sync(bar_id, TA_BM);  // staging is reused for the lo half
     }
   }
 };
@@ -415,32 +498,51 @@ struct PagedFront {
   }
   __device__ int n_tiles() const { return t_end - t_begin; }
   __device__ const __nv_bfloat16* any_ptr() const { return p.q; }
+  // stacked row rr = token * G + head-in-group  ->  row of the [total_q * Hq] query / output matrices
+  __device__ long long grow_of(int rr) const {
+    const int tok = (G == 7) ? rr / 7 : rr / G;         // Qwen2-7B: 28 query heads on 4 KV heads (constant division)
+    return (long long)(q_start + tok) * p.Hq + kvh * G + (rr - tok * G);
+  }
   __device__ const __nv_bfloat16* q_row(int r) const {
     const int rr = r_base + r;
-    if (rr >= R) return nullptr;
-    return p.q + ((long long)(q_start + rr / G) * p.Hq + kvh * G + rr % G) * DH;
+    return rr < R ? p.q + grow_of(rr) * DH : nullptr;
   }
-  __device__ const __nv_bfloat16* kv_row(int j, int r, int is_v) const {
+  __device__ const __nv_bfloat16* kv_tile(int j, bool is_v, int& valid) const {
     const int tile = t_begin + j;                       // one key tile == one 64-token page
-    if (tile * TA_BN + r >= kv_len) return nullptr;     // pool memory past the end may hold anything: zero-fill
-    return p.kv_layer + ((((long long)table[tile] * 2 + is_v) * p.Hkv + kvh) * PAGE + r) * DH;
+    valid = min(TA_BN, kv_len - tile * TA_BN);          // pool memory past the end may hold anything: zero-fill
+    return p.kv_layer + (((long long)table[tile] * 2 + (is_v ? 1 : 0)) * p.Hkv + kvh) * PAGE * DH;
   }
-  __device__ const __nv_bfloat16* k_row(int j, int r) const { return kv_row(j, r, 0); }
-  __device__ const __nv_bfloat16* v_row(int j, int r) const { return kv_row(j, r, 1); }
+  __device__ long long kv_row_stride() const { return DH; }
   // masking works on tile-local key indices j*TA_BN + c: shift the causal limit into that frame
   __device__ int key_limit(int row) const { return past + min(r_base + row, max(R - 1, 0)) / G - t_begin * TA_BN; }
   __device__ float scale_log2e() const { return p.scale_log2e; }
   template <int DHP>
-  __device__ void store(int row, const float (&o)[DHP], float m, float l) const {
-    const int rr = r_base + row;
-    if (rr >= R) return;
-    const long long grow = (long long)(q_start + rr / G) * p.Hq + kvh * G + rr % G;
-    float* op = p.o_part + ((long long)sp * p.part_stride_rows + grow) * DH;
+  __device__ void store(int qi, int row, const float (&o)[DHP], float m, float l, uint32_t stage, int bar_id) const {
+    {
+      const int rr = r_base + qi * TA_BM + row;
+      if (rr < R) {
+        float* mp = p.ml_part + ((long long)sp * p.part_stride_rows + grow_of(rr)) * 2;
+        mp[0] = (m == -INFINITY) ? -INFINITY : m * p.scale_log2e;
+        mp[1] = l;
+      }
+    }
+    // fp32 partial rows, 64 columns per pass (the Q region holds 128 x 256 B); chunks are XOR-swizzled by row so that
+    // both the row-per-thread writes and the chunk-per-lane reads are conflict-free
+    float* ob = p.o_part + (long long)sp * p.part_stride_rows * DH;
 #pragma unroll
-    for (int c = 0; c < DH; c += 4) *reinterpret_cast<float4*>(op + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
-    float* mp = p.ml_part + ((long long)sp * p.part_stride_rows + grow) * 2;
-    mp[0] = (m == -INFINITY) ? -INFINITY : m * p.scale_log2e;
-    mp[1] = l;
+    for (int pass = 0; pass < DH / 64; ++pass) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c)
+        sts128(stage + row * 256 + ((c ^ (row & 15)) << 4), __float_as_uint(o[pass * 64 + 4 * c]), __float_as_uint(o[pass * 64 + 4 * c + 1]),
+               __float_as_uint(o[pass * 64 + 4 * c + 2]), __float_as_uint(o[pass * 64 + 4 * c + 3]));
+      named_bar_sync(bar_id, TA_BM);
+#pragma unroll 4
+      for (int u = row; u < TA_BM * 16; u += TA_BM) {
+        const int r = u >> 4, c = u & 15, rr = r_base + qi * TA_BM + r;
+        if (rr < R) *reinterpret_cast<uint4*>(ob + grow_of(rr) * DH + pass * 64 + c * 4) = lds128(stage + r * 256 + ((c ^ (r & 15)) << 4));
+      }
+      if (pass + 1 < DH / 64) named_bar_sync(bar_id, TA_BM);
+    }
   }
 };
 
@@ -451,10 +553,12 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attn_tcgen05_kernel(const Param
   const uint32_t bars = smem_base + AttnSmem::BARS;
   const uint32_t tmem_slot = bars + 8u * BAR_COUNT;
   const int warp = threadIdx.x >> 5;
+  TRACE_INIT;
   griddep_launch_dependents();
+  if (threadIdx.x == 0) TRACE_EV(6, 0, 0);
   if (threadIdx.x == 0) {
     constexpr uint32_t NLOAD = 32 * TA_LOADER_WARPS / 2;   // one 64-thread stream per ring
-    mbar_init(bars + 8u * BAR_Q_FULL, NLOAD);
+    mbar_init(bars + 8u * BAR_Q_FULL, 32 * TA_LOADER_WARPS);
     for (int s = 0; s < TA_KRING; ++s) {
       mbar_init(bars + 8u * (BAR_K_FULL + s), NLOAD);
       mbar_init(bars + 8u * (BAR_K_EMPTY + s), 1);
@@ -463,29 +567,34 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attn_tcgen05_kernel(const Param
       mbar_init(bars + 8u * (BAR_V_FULL + s), NLOAD);
       mbar_init(bars + 8u * (BAR_V_EMPTY + s), 1);
     }
-    for (int i = 0; i < 2 * TA_QT; ++i) {
-      mbar_init(bars + 8u * (BAR_S_FULL + i), 1);
-      mbar_init(bars + 8u * (BAR_S_EMPTY + i), 128);
-    }
+    for (int i = 0; i < 2 * TA_QT; ++i) mbar_init(bars + 8u * (BAR_S_FULL + i), 1);
     for (int i = 0; i < TA_QT; ++i) {
       mbar_init(bars + 8u * (BAR_P_FULL + i), 128);
       mbar_init(bars + 8u * (BAR_O_FULL + i), 1);
     }
     fence_mbar_init();
   }
-  // zero the operand regions once: padding chunks (head dim 72 -> 80, unused chunks) are never written by the loaders
-  {
-    uint4* z = reinterpret_cast<uint4*>(smem_raw + (smem_base - smem_u32(smem_raw)));
-    const uint4 zero = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < AttnSmem::BARS / 16; i += TA_THREADS) z[i] = zero;
-  }
-  __syncthreads();
+  // Head-dim padding (72 -> 80): the loaders never write those chunks, so they are set once here: zero everywhere, and
+  // 1.0 in column DH of V in every ring stage (the "ones column", see attention_pipeline).
   if constexpr (((DH + 15) / 16 * 16) > DH) {
-    // ones column (see attention_pipeline): V[key][DH] = 1.0 in every ring stage; cp.async never touches that chunk
-    for (int i = threadIdx.x; i < TA_VRING * TA_BN; i += TA_THREADS) {
-      const int st = i / TA_BN, r = i % TA_BN;
-      const uint32_t off = AttnSmem::V + st * 2 * TA_KREGION + (DH / 64) * TA_KREGION + sw128_off(r, (DH % 64) / 8) + (DH % 8) * 2;
-      *reinterpret_cast<__nv_bfloat16*>(smem_raw + (smem_base - smem_u32(smem_raw)) + off) = __float2bfloat16_rn(1.0f);
+    static_assert(DH % 8 == 0 && ((DH + 15) / 16 * 16) - DH == 8, "one 16-B padding chunk");
+    uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
+    constexpr int PC = DH / 8;                                           // index of the padding chunk
+    constexpr int ROWS = TA_QT * TA_BM + (TA_KRING + TA_VRING) * TA_BN;
+    for (int i = threadIdx.x; i < ROWS; i += TA_THREADS) {
+      uint32_t off;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (i < TA_QT * TA_BM) {
+        off = AttnSmem::Q + (i / TA_BM) * 2 * TA_QREGION + (PC >> 3) * TA_QREGION + sw128_off(i % TA_BM, PC & 7);
+      } else if (i < TA_QT * TA_BM + TA_KRING * TA_BN) {
+        const int k = i - TA_QT * TA_BM;
+        off = AttnSmem::K + (k / TA_BN) * 2 * TA_KREGION + (PC >> 3) * TA_KREGION + sw128_off(k % TA_BN, PC & 7);
+      } else {
+        const int k = i - TA_QT * TA_BM - TA_KRING * TA_BN;
+        off = AttnSmem::V + (k / TA_BN) * 2 * TA_KREGION + (PC >> 3) * TA_KREGION + sw128_off(k % TA_BN, PC & 7);
+        val.x = 0x3f80u;                                                 // bf16 1.0 in element 0 of the chunk
+      }
+      *reinterpret_cast<uint4*>(sm + off) = val;
     }
   }
   if (warp == TA_SOFTMAX_WARPS + TA_LOADER_WARPS) tmem_alloc<512>(tmem_slot);
@@ -496,6 +605,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attn_tcgen05_kernel(const Param
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   griddep_wait();
+  if (threadIdx.x == 0) TRACE_EV(6, 0, 1);
   {
     Front fe(p);
     attention_pipeline<DH>(fe, smem_base, tmem_base);
@@ -503,9 +613,16 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attn_tcgen05_kernel(const Param
   tc_fence_before();
   __syncthreads();
   if (warp == TA_SOFTMAX_WARPS + TA_LOADER_WARPS) tmem_dealloc<512>(tmem_base);
+  if (threadIdx.x == 0) TRACE_EV(6, 0, 5);
 }
 
 }  // namespace
+
+#ifdef MMD_ATTN_TRACE
+extern "C" __attribute__((visibility("default"))) int mmd_debug_attn_trace(void* dev_buf) {
+  return cudaMemcpyToSymbol(g_attn_trace, &dev_buf, sizeof(void*)) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 int launch_vit_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int T, int S, int H, int dh, int split_hi_lo, cudaStream_t s) {
   if (T <= 0) return 0;
