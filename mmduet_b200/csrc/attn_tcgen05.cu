@@ -36,13 +36,16 @@ constexpr int TA_QT = 2;                   // query tiles per CTA
 constexpr int TA_BN = 64;                  // keys per tile
 constexpr int TA_QREGION = TA_BM * 128;    // one 64-column swizzled region of a 128-row operand (16 KB)
 constexpr int TA_KREGION = TA_BN * 128;    // same for a 64-row operand (8 KB)
-constexpr int TA_KRING = 4, TA_VRING = 4;
+constexpr int TA_KRING = 5, TA_VRING = 5;
 constexpr int TA_SOFTMAX_WARPS = 4 * TA_QT, TA_LOADER_WARPS = 4;
 constexpr int TA_THREADS = 32 * (TA_SOFTMAX_WARPS + TA_LOADER_WARPS + 4);   // MMA warp + 3 idle warps: setmaxnreg works on whole warpgroups
 constexpr int TA_TMEM_PER_Q = 256;         // S0 [0,64) S1 [64,128) O [128, 128+DHP)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -76,6 +79,26 @@ __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial, max relative error 7.5e-5, far below the bf16
+// rounding of P): MUFU.EX2 runs at 16 lanes/clk/SM, so a share of every tile's exponentials is computed here instead
+// and overlaps the MUFU stream.  Valid for x <= 127; anything below -125 is clamped (2^-125 rounds to nothing in O).
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;                 // 1.5 * 2^23: the low mantissa bits now hold round(x)
+  const float f = x - (t - 12582912.f);           // [-0.5, 0.5]
+  float p = fmaf(f, 0.0551714599f, 0.2426108569f);
+  p = fmaf(p, f, 0.6932609677f);
+  p = fmaf(p, f, 0.9999281168f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+// which of the 16 element pairs of a 32-key block go to the polynomial (3 of every 8)
+#ifndef MMD_EXP_MODE
+#define MMD_EXP_MODE 0
+#endif
+__device__ __forceinline__ constexpr bool exp_on_fma_pipe(int i) {
+  return MMD_EXP_MODE == 2 ? true : (MMD_EXP_MODE == 0 ? false : ((i & 7) == 1 || (i & 7) == 4 || (i & 7) == 6));
+}
+
 // warpgroup register reallocation: the kernel starts with 128 registers per thread (512 threads); the loader warpgroup
 // and the MMA warpgroup hand most of theirs to the two softmax warpgroups (64 scores + 64..128 outputs per thread).
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -125,8 +148,8 @@ struct AttnSmem {  // byte offsets from the 1024-B aligned base
 constexpr int BAR_Q_FULL = 0;
 constexpr int BAR_K_FULL = 1, BAR_K_EMPTY = BAR_K_FULL + TA_KRING, BAR_V_FULL = BAR_K_EMPTY + TA_KRING, BAR_V_EMPTY = BAR_V_FULL + TA_VRING;
 constexpr int BAR_S_FULL = BAR_V_EMPTY + TA_VRING;   // [qi][2]
-constexpr int BAR_P_FULL = BAR_S_FULL + 2 * TA_QT;  // [qi]
-constexpr int BAR_O_FULL = BAR_P_FULL + TA_QT;      // [qi]
+constexpr int BAR_P_FULL = BAR_S_FULL + 2 * TA_QT;  // [qi][2]
+constexpr int BAR_O_FULL = BAR_P_FULL + 2 * TA_QT;  // [qi]
 constexpr int BAR_COUNT = BAR_O_FULL + TA_QT;
 
 struct VitAttnParams {
@@ -182,29 +205,15 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
       const uint32_t dst = smem_base + AttnSmem::Q + (r / TA_BM) * 2 * TA_QREGION + (c >> 3) * TA_QREGION + sw128_off(r % TA_BM, c & 7);
       cp_async16(dst, src ? src + c * 8 : fe.any_ptr(), src ? 16 : 0);
     }
-    cp_async_commit();
-    auto publish = [&](int j) {   // tile j's copies of this thread have landed
-      fence_proxy_async_smem();
-      mbar_arrive(bar(bar_full + j % ring));
-      if (lrow == 0) TRACE_EV(4 + is_v, j, 2);
-    };
-    auto q_ready = [&]() {
-      fence_proxy_async_smem();
-      mbar_arrive(bar(BAR_Q_FULL));
-    };
-    int published = -1;   // last tile handed to the MMA warp by this thread
+    // Completion is tracked by the mbarriers themselves (cp.async.mbarrier.arrive.noinc: the arrival fires when this
+    // thread's copies so far have landed), so a loader thread never waits for data: it only blocks on a free ring slot
+    // and runs up to the ring depth ahead of the MMA threads (a tile takes ~3000 clk to land, one is consumed every
+    // ~1000-1800 clk).
+    cp_async_mbar_arrive(bar(BAR_Q_FULL));
     for (int j = 0; j < n_tiles; ++j) {
       const int st = j % ring;
-      const uint32_t par = ((j / ring) & 1) ^ 1;
-      if (j >= 1 && !mbar_try_wait(bar(bar_empty + st), par)) {
-        // The ring slot is still in use.  Never block on it while holding back a tile that has already been requested:
-        // the MMA warp may need tile j-1 before it can release this slot (deadlock otherwise).
-        cp_async_wait<0>();
-        publish(j - 1);
-        published = j - 1;
-      }
       if (lrow == 0) TRACE_EV(4 + is_v, j, 0);
-      mbar_wait(bar(bar_empty + st), par);
+      mbar_wait(bar(bar_empty + st), ((j / ring) & 1) ^ 1);
       if (lrow == 0) TRACE_EV(4 + is_v, j, 1);
       const uint32_t dstb = ring_base + st * 2 * TA_KREGION;
       int valid;                                             // rows past `valid` are zero-filled
@@ -216,69 +225,71 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
         const bool ok = r < valid;
         cp_async16(dstb + (c >> 3) * TA_KREGION + sw128_off(r, c & 7), ok ? tile + r * rstride + c * 8 : fe.any_ptr(), ok ? 16 : 0);
       }
-      cp_async_commit();
-      if (j == 0) {            // Q (first group) has landed once at most one group (tile 0) is pending
-        cp_async_wait<1>();
-        q_ready();
-      } else if (published < j - 1) {
-        cp_async_wait<1>();    // tile j-1 has landed, tile j may still be in flight
-        publish(j - 1);
-        published = j - 1;
-      }
+      cp_async_mbar_arrive(bar(bar_full + st));
+      if (lrow == 0) TRACE_EV(4 + is_v, j, 2);
     }
-    cp_async_wait<0>();
-    if (n_tiles == 0) q_ready();
-    else if (published < n_tiles - 1) publish(n_tiles - 1);
+    cp_async_commit();
+    cp_async_wait<0>();   // nothing may still be writing this CTA's shared memory when it exits
   } else if (warp >= TA_SOFTMAX_WARPS + TA_LOADER_WARPS) {
-    // ======================= MMA issuer (first warp of the last warpgroup; the other three only give up registers) ====
+    // ======================= MMA issuers: one thread per query tile (warps 12, 13; warps 14, 15 only give up their
+    // registers).  A wait on an mbarrier costs ~200 clk even when it has long completed, so one thread serving both
+    // tiles (6 waits + 24 MMAs per key tile) was slower than the tensor pipe; each thread's own MMAs stay in order,
+    // which is all the S/P buffer reuse relies on. =======================
     reg_dec<56>();
-    if (warp == TA_SOFTMAX_WARPS + TA_LOADER_WARPS && elect_one()) {
+    const int qi = warp - (TA_SOFTMAX_WARPS + TA_LOADER_WARPS);
+    if (qi < TA_QT && elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(TA_BM, TA_BN);
       constexpr uint32_t idesc_pv = umma_idesc_bf16_mn_b(TA_BM, DHP);
-      auto issue_qk = [&](int qi, int j) {
+      // One thread issues everything, so its instruction count per tile is on the critical path: the descriptors' high
+      // words are constants and the low words (start address | LBO) advance by immediates.
+      constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);              // SBO | version 1 | SWIZZLE_128B
+      auto desc = [](uint32_t lo) { return (static_cast<uint64_t>(HI) << 32) | lo; };
+      auto lo_k = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };                       // K-major
+      auto lo_mn = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | ((uint32_t)(TA_KREGION >> 4) << 16); };   // MN-major
+      const uint32_t q_lo = lo_k(smem_base + AttnSmem::Q), k_lo = lo_k(smem_base + AttnSmem::K), v_lo = lo_mn(smem_base + AttnSmem::V);
+      auto issue_qk = [&](int j) {
         const int st = j % TA_KRING, sb = j & 1;
         TRACE_EV(2 + qi, j, 4);
         mbar_wait(bar(BAR_K_FULL + st), (j / TA_KRING) & 1);
+        fence_proxy_async_smem();                            // cp.async (generic proxy) data -> tcgen05.mma operand reads
+        tc_fence_after();
         TRACE_EV(2 + qi, j, 5);
         // No "S buffer free" barrier: QK_j is issued after PV_{j-2} (which read P_{j-2} from this buffer, itself written
         // after S_{j-2} had been read), and the tensor pipe executes this thread's MMAs in issue order.
-        tc_fence_after();
-        const uint32_t sQ = smem_base + AttnSmem::Q + qi * 2 * TA_QREGION;
-        const uint32_t sK = smem_base + AttnSmem::K + st * 2 * TA_KREGION;
+        const uint32_t qa = q_lo + qi * (2 * TA_QREGION >> 4), ka = k_lo + st * (2 * TA_KREGION >> 4);
+        const uint32_t d = tmem_base + qi * TA_TMEM_PER_Q + sb * TA_BN;
 #pragma unroll
-        for (int k = 0; k < DHP / 16; ++k) {
-          const uint64_t da = umma_desc_k_sw128(sQ + (k >> 2) * TA_QREGION) + 2u * (k & 3);
-          const uint64_t db = umma_desc_k_sw128(sK + (k >> 2) * TA_KREGION) + 2u * (k & 3);
-          umma_f16(tmem_base + qi * TA_TMEM_PER_Q + sb * TA_BN, da, db, idesc_qk, k > 0 ? 1u : 0u);
-        }
+        for (int k = 0; k < DHP / 16; ++k)
+          umma_f16(d, desc(qa + (k >> 2) * (TA_QREGION >> 4) + 2 * (k & 3)), desc(ka + (k >> 2) * (TA_KREGION >> 4) + 2 * (k & 3)), idesc_qk,
+                   k > 0 ? 1u : 0u);
         umma_commit(bar(BAR_S_FULL + qi * 2 + sb));
-        if (qi == TA_QT - 1) umma_commit(bar(BAR_K_EMPTY + st));   // both q tiles have consumed K_j
+        umma_commit(bar(BAR_K_EMPTY + st));                  // the slot is free once both tiles' issuers have arrived
         TRACE_EV(2 + qi, j, 6);
       };
       mbar_wait(bar(BAR_Q_FULL), 0);
-      for (int j = 0; j < 2 && j < n_tiles; ++j)
-        for (int qi = 0; qi < TA_QT; ++qi) issue_qk(qi, j);
+      fence_proxy_async_smem();
+      tc_fence_after();
+      for (int j = 0; j < 2 && j < n_tiles; ++j) issue_qk(j);
       for (int j = 0; j < n_tiles; ++j) {
         const int st = j % TA_VRING;
-        for (int qi = 0; qi < TA_QT; ++qi) {
+        {
           TRACE_EV(2 + qi, j, 0);
-          mbar_wait(bar(BAR_P_FULL + qi), j & 1);
+          mbar_wait(bar(BAR_V_FULL + st), (j / TA_VRING) & 1);   // usually long complete: take its latency before P arrives
           TRACE_EV(2 + qi, j, 1);
-          if (qi == 0) mbar_wait(bar(BAR_V_FULL + st), (j / TA_VRING) & 1);
+          mbar_wait(bar(BAR_P_FULL + qi * 2 + (j & 1)), (j >> 1) & 1);
           TRACE_EV(2 + qi, j, 2);
+          fence_proxy_async_smem();
           tc_fence_after();
           // P_j (bf16) sits in TMEM over the first 32 columns of the S buffer it was computed from: 8 columns per K=16 step
           const uint32_t tP = tmem_base + qi * TA_TMEM_PER_Q + (j & 1) * TA_BN;
-          const uint32_t sV = smem_base + AttnSmem::V + st * 2 * TA_KREGION;
+          const uint32_t va = v_lo + st * (2 * TA_KREGION >> 4);
 #pragma unroll
-          for (int k = 0; k < TA_BN / 16; ++k) {
-            const uint64_t db = umma_desc_mn_sw128(sV, TA_KREGION) + (uint64_t)((k * 2048) >> 4);
-            umma_f16_ts(tmem_base + qi * TA_TMEM_PER_Q + 2 * TA_BN, tP + 8 * k, db, idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < TA_BN / 16; ++k)
+            umma_f16_ts(tmem_base + qi * TA_TMEM_PER_Q + 2 * TA_BN, tP + 8 * k, desc(va + k * (2048 >> 4)), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
           umma_commit(bar(BAR_O_FULL + qi));
-          if (qi == TA_QT - 1) umma_commit(bar(BAR_V_EMPTY + st));
+          umma_commit(bar(BAR_V_EMPTY + st));
           TRACE_EV(2 + qi, j, 3);
-          if (j + 2 < n_tiles) issue_qk(qi, j + 2);
+          if (j + 2 < n_tiles) issue_qk(j + 2);
         }
       }
     }
@@ -292,37 +303,54 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
     float m_ref = -INFINITY, l_run = 0.f;
     const int key_lim = fe.key_limit(qi * TA_BM + row);    // tile-local key indices > key_lim are masked for this row
     const float sl2 = fe.scale_log2e();
-    // MUFU.EX2 runs at 16 lanes/clk/SM: the exponentials of one key tile (2 x 128 x 64) keep it busy for >= 1024 clk, as
-    // long as both tiles' tensor work.  The groups therefore take turns in the exponential phase (named barriers 1 + qi:
-    // "group qi may go"), so one group's TMEM loads, max and rescale overlap the other group's MUFU stream instead of
-    // both queueing on it and then both leaving it idle.
+    // MUFU.EX2 (16 lanes/clk/SM) is the slowest pipe of this kernel: one key tile costs 2 x 128 x 64 exponentials =
+    // 1024 clk of it, as much as the tile's tensor work.  A warp issues in order, so while its MUFU instructions queue
+    // nothing else of that warp moves; the second group's TMEM loads / max / barrier traffic fill those slots.
+    struct Tile { uint32_t a[32], b[32]; };
+    auto val = [](const Tile& t, int i) { return __uint_as_float(i < 32 ? t.a[i] : t.b[i - 32]); };
+    auto fetch = [&](int j, Tile& t) {                     // wait for S_j and start reading it (finish: tmem_ld_wait)
+      mbar_wait(bar(BAR_S_FULL + qi * 2 + (j & 1)), (j >> 1) & 1);
+      tc_fence_after();
+      tmem_ld_32x32b_x32(t_row + (j & 1) * TA_BN, t.a);
+      tmem_ld_32x32b_x32(t_row + (j & 1) * TA_BN + 32, t.b);
+    };
+    auto mask_tile = [&](int j, Tile& t) {
+      // masking only in the tiles that reach beyond some row's limit (warp-uniform test; ISETP/SEL per element only there)
+      const int k0 = j * TA_BN;
+      if (__any_sync(0xffffffffu, k0 + TA_BN - 1 > key_lim)) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          t.a[i] = (k0 + i > key_lim) ? 0xff800000u : t.a[i];
+          t.b[i] = (k0 + 32 + i > key_lim) ? 0xff800000u : t.b[i];
+        }
+      }
+    };
+    auto row_max = [&](const Tile& t) {                    // four chains of 3-input FMNMX3
+      float m0 = fmaxf(val(t, 0), val(t, 1)), m1 = fmaxf(val(t, 2), val(t, 3)), m2 = fmaxf(val(t, 4), val(t, 5)), m3 = fmaxf(val(t, 6), val(t, 7));
+#pragma unroll
+      for (int i = 8; i < TA_BN; i += 8) {
+        m0 = fmaxf(m0, fmaxf(val(t, i), val(t, i + 1)));
+        m1 = fmaxf(m1, fmaxf(val(t, i + 2), val(t, i + 3)));
+        m2 = fmaxf(m2, fmaxf(val(t, i + 4), val(t, i + 5)));
+        m3 = fmaxf(m3, fmaxf(val(t, i + 6), val(t, i + 7)));
+      }
+      return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    };
+    // The two groups take turns in the exponential phase (named barriers 1 + qi: "group qi may go"): a group alone
+    // streams its MUFU work almost back to back, and the other group's non-MUFU phases run underneath instead of both
+    // groups queueing on the MUFU and then both leaving it idle.
     constexpr int NSM = 32 * TA_SOFTMAX_WARPS;
     if (qi == 1 && n_tiles > 0) named_bar_arrive(1, NSM);
+    Tile cur;
     for (int j = 0; j < n_tiles; ++j) {
       const int sb = j & 1;
       if (row == 0) TRACE_EV(qi, j, 0);
-      mbar_wait(bar(BAR_S_FULL + qi * 2 + sb), (j >> 1) & 1);
+      fetch(j, cur);
       if (row == 0) TRACE_EV(qi, j, 1);
-      tc_fence_after();
-      const int k0 = j * TA_BN;
-      float sv[TA_BN];
-      {
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32b_x32(t_row + sb * TA_BN, v0);
-        tmem_ld_32x32b_x32(t_row + sb * TA_BN + 32, v1);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { sv[i] = __uint_as_float(v0[i]); sv[32 + i] = __uint_as_float(v1[i]); }
-      }
-      // masking only in the tiles that reach beyond some row's limit (warp-uniform test; ISETP/FSEL per element only there)
-      if (__any_sync(0xffffffffu, k0 + TA_BN - 1 > key_lim)) {
-#pragma unroll
-        for (int i = 0; i < TA_BN; ++i) sv[i] = (k0 + i > key_lim) ? -INFINITY : sv[i];
-      }
+      tmem_ld_wait();
+      mask_tile(j, cur);
       if (row == 0) TRACE_EV(qi, j, 2);
-      float mx = fmaxf(sv[0], sv[1]);
-#pragma unroll
-      for (int i = 2; i < TA_BN; i += 2) mx = fmaxf(mx, fmaxf(sv[i], sv[i + 1]));
+      const float mx = row_max(cur);
       const float m_new = fmaxf(m_ref, mx);
       const bool need = j > 0 && m_new > m_ref && (m_ref == -INFINITY || (m_new - m_ref) * sl2 > 8.0f);
       if (j == 0) {
@@ -352,16 +380,24 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
       named_bar_sync(1 + qi, NSM);
       if (row == 0) TRACE_EV(qi, j, 3);
       const float msc = (m_ref == -INFINITY) ? 0.f : m_ref * sl2;
-      // probabilities -> bf16 P tile, written back into TMEM over the S buffer just read (two keys per 32-bit column).
-      // PV_{j-2}, the last reader of these columns, completed before S_j was produced, so no wait is needed here, and
+      // probabilities -> bf16 P tile, written back into TMEM over the S buffer they came from (two keys per 32-bit
+      // column).  PV_{j-2}, the last reader of these columns, completed before S_j was produced: no wait needed, and
       // the softmax of tile j+1 can start while PV_j is still running.
       float rs = 0.f;
 #pragma unroll
       for (int c = 0; c < TA_BN / 32; ++c) {         // 16 columns = 32 keys per store
+        float x[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x[i] = fmaf(val(cur, 32 * c + i), sl2, -msc);
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = exp2f(fmaf(sv[32 * c + 2 * i], sl2, -msc)), p1 = exp2f(fmaf(sv[32 * c + 2 * i + 1], sl2, -msc));
+#if MMD_EXP_MODE == 3   // timing experiment only: no exponential at all
+          const float p0 = x[2 * i], p1 = x[2 * i + 1];
+#else
+          const float p0 = exp_on_fma_pipe(i) ? exp2_poly(x[2 * i]) : exp2f(x[2 * i]);
+          const float p1 = exp_on_fma_pipe(i) ? exp2_poly(x[2 * i + 1]) : exp2f(x[2 * i + 1]);
+#endif
           __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
           pk[i] = *reinterpret_cast<uint32_t*>(&h);
           if constexpr (!ONES_COL) {
@@ -376,11 +412,10 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
       if (row == 0) TRACE_EV(qi, j, 4);
       tmem_st_wait();
       if (row == 0) TRACE_EV(qi, j, 5);
-      // The MMA thread must have consumed P_FULL phase j-1 before phase j can complete (it waits on parities, so a
-      // barrier two phases ahead would look unfinished): PV_{j-1} done implies that, one whole softmax iteration later.
-      if (j > 0) mbar_wait(bar(BAR_O_FULL + qi), (j - 1) & 1);
       tc_fence_before();
-      mbar_arrive(bar(BAR_P_FULL + qi));
+      // one P_FULL barrier per S buffer: tile j+2's arrivals cannot start before the MMA thread has consumed tile j's
+      // (S_{j+2} is produced after PV_j), so a phase can never be skipped and no wait for PV_{j-1} is needed here
+      mbar_arrive(bar(BAR_P_FULL + qi * 2 + sb));
       if (row == 0) TRACE_EV(qi, j, 6);
     }
     if (row == 0) TRACE_EV(6, qi, 2);
@@ -561,17 +596,17 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attn_tcgen05_kernel(const Param
     mbar_init(bars + 8u * BAR_Q_FULL, 32 * TA_LOADER_WARPS);
     for (int s = 0; s < TA_KRING; ++s) {
       mbar_init(bars + 8u * (BAR_K_FULL + s), NLOAD);
-      mbar_init(bars + 8u * (BAR_K_EMPTY + s), 1);
+      mbar_init(bars + 8u * (BAR_K_EMPTY + s), TA_QT);
     }
     for (int s = 0; s < TA_VRING; ++s) {
       mbar_init(bars + 8u * (BAR_V_FULL + s), NLOAD);
-      mbar_init(bars + 8u * (BAR_V_EMPTY + s), 1);
+      mbar_init(bars + 8u * (BAR_V_EMPTY + s), TA_QT);
     }
-    for (int i = 0; i < 2 * TA_QT; ++i) mbar_init(bars + 8u * (BAR_S_FULL + i), 1);
-    for (int i = 0; i < TA_QT; ++i) {
+    for (int i = 0; i < 2 * TA_QT; ++i) {
+      mbar_init(bars + 8u * (BAR_S_FULL + i), 1);
       mbar_init(bars + 8u * (BAR_P_FULL + i), 128);
-      mbar_init(bars + 8u * (BAR_O_FULL + i), 1);
     }
+    for (int i = 0; i < TA_QT; ++i) mbar_init(bars + 8u * (BAR_O_FULL + i), 1);
     fence_mbar_init();
   }
   // Head-dim padding (72 -> 80): the loaders never write those chunks, so they are set once here: zero everywhere, and
