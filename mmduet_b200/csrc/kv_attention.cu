@@ -244,19 +244,28 @@ __global__ void kv_attention_combine_kernel(const float* __restrict__ o_part, co
                                             __nv_bfloat16* __restrict__ out, int n_splits, long long part_stride_rows) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  const long long grow = blockIdx.x;
-  const int d = threadIdx.x;
+  // one warp per (token, head) row: lane l owns dims 4l..4l+3 (one 16-B load per split, one 8-B store)
+  const long long grow = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (grow >= part_stride_rows) return;
+  const int lane = threadIdx.x & 31;
   float mmax = -INFINITY;
-  for (int s = 0; s < n_splits; ++s) mmax = fmaxf(mmax, ml_part[((long long)s * part_stride_rows + grow) * 2]);
-  float acc = 0.f, lsum = 0.f;
+  for (int s = 0; s < n_splits; ++s) mmax = fmaxf(mmax, __ldg(ml_part + ((long long)s * part_stride_rows + grow) * 2));
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float lsum = 0.f;
   for (int s = 0; s < n_splits; ++s) {
-    const float m = ml_part[((long long)s * part_stride_rows + grow) * 2];
-    if (m == -INFINITY) continue;
-    const float w = exp2f(m - mmax);
-    lsum += w * ml_part[((long long)s * part_stride_rows + grow) * 2 + 1];
-    acc += w * o_part[((long long)s * part_stride_rows + grow) * KA_DH + d];
+    const float2 ml = __ldg(reinterpret_cast<const float2*>(ml_part + ((long long)s * part_stride_rows + grow) * 2));
+    if (ml.x == -INFINITY) continue;
+    const float w = exp2f(ml.x - mmax);
+    lsum += w * ml.y;
+    const float4 o = __ldg(reinterpret_cast<const float4*>(o_part + ((long long)s * part_stride_rows + grow) * KA_DH) + lane);
+    acc.x += w * o.x; acc.y += w * o.y; acc.z += w * o.z; acc.w += w * o.w;
   }
-  out[grow * KA_DH + d] = __float2bfloat16_rn(acc / lsum);
+  const float inv = 1.f / lsum;
+  __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x * inv, acc.y * inv), hi = __floats2bfloat162_rn(acc.z * inv, acc.w * inv);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&lo);
+  pk.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(out + grow * KA_DH + lane * 4) = pk;
 }
 
 }  // namespace
@@ -281,11 +290,22 @@ int kv_attention_pick_splits(int max_rows, int Hkv, int n_streams, int max_kv_le
   const int q_tiles = (max_rows + rows_per_cta - 1) / rows_per_cta;
   const int base = q_tiles * Hkv * n_streams;
   const int kv_tiles = (max_kv_len + KA_BN - 1) / KA_BN;
-  int splits = ((tc ? 1 : 2) * num_sms + base - 1) / base;
-  const int max_by_work = (kv_tiles + 3) / 4;  // at least ~4 key tiles (256 keys) per split
-  if (splits > max_by_work) splits = max_by_work;
-  if (splits > 32) splits = 32;
-  if (splits < 1) splits = 1;
+  // Pick the split count that minimises (waves of CTAs) x (key tiles per CTA + fixed per-CTA cost): a count that spills
+  // a few CTAs into a second wave doubles the kernel time, so "just fill the SMs" is the wrong rule.  Fixed cost in
+  // key-tile units (measured, tools/trace_attn.py): prologue + epilogue of the tcgen05 kernel ~ 8 tiles, mma.sync ~ 2.
+  const int slots = (tc ? 1 : 2) * num_sms;
+  const double fixed = tc ? 8.0 : 2.0;
+  int max_by_work = (kv_tiles + 3) / 4;  // at least ~4 key tiles (256 keys) per split
+  if (max_by_work > 32) max_by_work = 32;
+  if (max_by_work < 1) max_by_work = 1;
+  int splits = 1;
+  double best = 1e30;
+  for (int sp = 1; sp <= max_by_work; ++sp) {
+    const int waves = (base * sp + slots - 1) / slots;
+    const int per = (kv_tiles + sp - 1) / sp;
+    const double cost = waves * (per + fixed) + 0.25 * sp;   // + the combine kernel reading sp partial planes
+    if (cost < best - 1e-9) { best = cost; splits = sp; }
+  }
   return splits;
 }
 
@@ -313,7 +333,7 @@ int launch_kv_attention(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, c
     launch_k(kv_attention_kernel, grid, dim3(KA_THREADS), SMEM, s, q, kv_layer, stream_desc, block_tables, o_part, ml_part, Hq, Hkv,
              n_splits, part_rows, scale_log2e);
   }
-  launch_k(kv_attention_combine_kernel, dim3((unsigned)part_rows), dim3(KA_DH), 0, s, o_part, ml_part, out, n_splits, part_rows);
+  launch_k(kv_attention_combine_kernel, dim3((unsigned)((part_rows + 7) / 8)), dim3(256), 0, s, o_part, ml_part, out, n_splits, part_rows);
   return 0;
 }
 

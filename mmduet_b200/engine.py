@@ -155,25 +155,30 @@ class VisionEngine:
         _lib.check(rc, "mmd_vit_forward")
         return resid
 
-    def visual_embed(self, frames, normalize=False, out_dtype=torch.bfloat16):
+    def visual_embed(self, frames, normalize=False, out_dtype=torch.bfloat16, out=None):
         """frames [T,3,384,384] (already image-processed unless normalize=True) -> [T*tokens_per_frame, hidden] in the model
-        dtype (bf16, what the reference returns) or in fp32 (the same values before the final rounding)."""
+        dtype (bf16, what the reference returns) or in fp32 (the same values before the final rounding).
+        `out`: optional preallocated destination [T*tokens_per_frame, hidden]; it may live in ANOTHER GPU's memory
+        (a symmetric-memory peer mapping, parallel.PeerStoreEncoder): the pooling epilogue then stores over NVLink."""
         assert out_dtype in (torch.bfloat16, torch.float32)
         if self.proj is None:
             raise _lib.MmdError("this VisionEngine was built without the projector")
-        outs = []
-        for b in range(0, frames.shape[0], self.MAX_BATCH):
+        tpf, T_all = self.tokens_per_frame, frames.shape[0]
+        if out is None:
+            out = torch.empty(T_all * tpf, self.cfg.hidden, dtype=out_dtype, device=self.device)
+        elif out.shape != (T_all * tpf, self.cfg.hidden) or out.dtype != out_dtype or not out.is_contiguous():
+            raise _lib.MmdError(f"visual_embed: out must be a contiguous [{T_all * tpf}, {self.cfg.hidden}] {out_dtype} tensor")
+        for b in range(0, T_all, self.MAX_BATCH):
             chunk = frames[b:b + self.MAX_BATCH]
             T = chunk.shape[0]
             resid = self.tower(chunk, normalize)
             ws, _ = self._workspace(T)
-            out = torch.empty(T * self.tokens_per_frame, self.cfg.hidden, dtype=out_dtype, device=self.device)
-            rc = self.lib.mmd_projector_pool(self.ctx, ctypes.byref(self.proj), resid.data_ptr(), T, out.data_ptr(),
+            dst = out[b * tpf:(b + T) * tpf]
+            rc = self.lib.mmd_projector_pool(self.ctx, ctypes.byref(self.proj), resid.data_ptr(), T, dst.data_ptr(),
                                              _lib.DT_BF16 if out_dtype == torch.bfloat16 else _lib.DT_F32, ws.data_ptr(), ws.numel(),
                                              _lib.stream_ptr())
             _lib.check(rc, "mmd_projector_pool")
-            outs.append(out)
-        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+        return out
 
     def legacy_encode(self, frames_0_255, frame_token_pooled=(7, 7)):
         """models/vision_live.py:11-31 semantics: rescale+normalize, all layers, post_layernorm, adaptive_avg_pool2d."""

@@ -4,7 +4,9 @@
   * videos are independent through the decoder   -> round-robin videos per rank (`videos_for_rank`),
   * a single video's decoder stream is sequential -> it lives on ONE owner rank; the only data-path exchange is the
     gather of encoded frame tokens ([n, 49, 3584] bf16, 351,232 B per frame) to that rank (`FrameParallelEncoder`),
-    sent batch by batch so the owner can start decoding the first frames while later ones are still being encoded.
+    sent batch by batch so the owner can start decoding the first frames while later ones are still being encoded
+    (`FrameParallelEncoder`: NCCL send/recv), or stored directly into the owner's memory by the producing kernel
+    (`PeerStoreEncoder`: symmetric memory over NVLink, no collective).
 
 The reference has no multi-GPU inference mode besides accelerate's layer-wise `device_map='auto'`
 (models/modeling_live.py:99), which gives no speed-up; this module is what replaces it.  Backend-agnostic on purpose
@@ -78,6 +80,62 @@ class FrameParallelEncoder:
     def wait_all(ready):
         for r in ready or []:
             r()
+
+
+class PeerStoreEncoder:
+    """Same contract as FrameParallelEncoder with no collective call on the data path: the frame-token buffer is
+    symmetric memory (torch.distributed._symmetric_memory: one allocation per rank, every rank maps every peer's), and
+    each rank's projector + pooling kernel writes its frames STRAIGHT INTO THE OWNER'S HBM through that mapping — the
+    kernel's epilogue is the NVLink transfer, there is no staging copy and no send/recv.  A per-batch signal (symmetric
+    signal pad, release/acquire at system scope, enqueued on the producing stream) tells the owner which frames landed.
+
+    embed_into(frames[b0:b1], dst[(b1-b0)*tokens_per_frame, hidden]) must write the tokens of those frames into dst."""
+
+    def __init__(self, embed_into, tokens_per_frame, hidden, max_frames, device, owner=0, batch=32, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.embed_into, self.tpf, self.hidden, self.device = embed_into, tokens_per_frame, hidden, device
+        self.owner, self.batch, self.max_frames = owner, batch, max_frames
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.buf = symm.empty(max_frames * tokens_per_frame, hidden, dtype=torch.bfloat16, device=device)
+        self.hdl = symm.rendezvous(self.buf, self.group)
+        # the owner's buffer as seen from this rank (a peer mapping unless this rank is the owner)
+        self.dst = self.buf if self.rank == owner else self.hdl.get_buffer(owner, tuple(self.buf.shape), torch.bfloat16)
+
+    def encode(self, n_frames, local_frames):
+        """Returns (tokens, ready) on the owner (tokens is a view of the symmetric buffer, valid until the next encode;
+        ready[i]() makes the current stream wait until frame i has landed) and (None, None) elsewhere."""
+        assert n_frames <= self.max_frames
+        lo, hi = frame_range(n_frames, self.world, self.rank)
+        assert len(local_frames) == hi - lo, (len(local_frames), lo, hi)
+        # nobody may overwrite the owner's buffer while it is still decoding the previous video
+        self.hdl.barrier(channel=0)
+        for b0 in range(lo, hi, self.batch):
+            b1 = min(b0 + self.batch, hi)
+            self.embed_into(local_frames[b0 - lo:b1 - lo], self.dst[b0 * self.tpf:b1 * self.tpf])
+            if self.rank != self.owner:
+                self.hdl.put_signal(self.owner, channel=1)     # stream-ordered after the kernel that stored the batch
+        if self.rank != self.owner:
+            return None, None
+        pending = {}                                           # src rank -> list of its batches, in sending order
+        for src in range(self.world):
+            if src != self.owner:
+                s_lo, s_hi = frame_range(n_frames, self.world, src)
+                pending[src] = [(b0, min(b0 + self.batch, s_hi)) for b0 in range(s_lo, s_hi, self.batch)]
+
+        def ready_fn(i):
+            def wait():
+                for src, batches in pending.items():
+                    if batches and any(b0 <= i < b1 for b0, b1 in batches):
+                        while batches:                        # signals of one source arrive in order: consume up to frame i
+                            b0, b1 = batches.pop(0)
+                            self.hdl.wait_signal(src, channel=1)
+                            if b0 <= i < b1:
+                                break
+            return wait
+        return self.buf[:n_frames * self.tpf], [ready_fn(i) for i in range(n_frames)]
+
+    wait_all = staticmethod(FrameParallelEncoder.wait_all)
 
 
 def gather_results(obj, dst=0, group=None):

@@ -152,9 +152,10 @@ class KVCache:
                 self.v[i] = self.v[i][:, :length]
 
 
-def decoder_forward(w, arch, inputs_embeds, cache):
+def decoder_forward(w, arch, inputs_embeds, cache, attn_impl="eager"):
     """Qwen2Model.forward for one stream: inputs_embeds [M, hidden], appends M tokens to `cache`; returns the final
-    RMSNorm output [M, hidden]."""
+    RMSNorm output [M, hidden].  attn_impl: "eager" (the oracle of record: fp32 softmax, as HF's eager attention) or
+    "sdpa" (torch SDPA as the reference's default `attn_implementation`; only bench.py's baseline timing uses it)."""
     M = inputs_embeds.shape[0]
     past = len(cache)
     pos = torch.arange(past, past + M, device=inputs_embeds.device)
@@ -174,10 +175,14 @@ def decoder_forward(w, arch, inputs_embeds, cache):
         kk, vv = cache.append(i, k, v)
         kk = kk.repeat_interleave(Hq // Hkv, dim=0)
         vv = vv.repeat_interleave(Hq // Hkv, dim=0)
-        s = (q @ kk.transpose(-1, -2)) * dh ** -0.5
-        s = s.masked_fill(~mask[None], float("-inf"))
-        a = torch.softmax(s.float(), dim=-1).to(q.dtype)
-        o = (a @ vv).transpose(0, 1).reshape(M, Hq * dh)
+        if attn_impl == "sdpa":
+            o = F.scaled_dot_product_attention(q[None], kk[None], vv[None], attn_mask=mask[None, None])[0]
+            o = o.transpose(0, 1).reshape(M, Hq * dh)
+        else:
+            s = (q @ kk.transpose(-1, -2)) * dh ** -0.5
+            s = s.masked_fill(~mask[None], float("-inf"))
+            a = torch.softmax(s.float(), dim=-1).to(q.dtype)
+            o = (a @ vv).transpose(0, 1).reshape(M, Hq * dh)
         x = x + F.linear(o, w[p + "self_attn.o_proj.weight"])
         h = rms_norm(x, w[p + "post_attention_layernorm.weight"], arch.rms_eps)
         h = F.silu(F.linear(h, w[p + "mlp.gate_proj.weight"])) * F.linear(h, w[p + "mlp.up_proj.weight"])
@@ -185,10 +190,10 @@ def decoder_forward(w, arch, inputs_embeds, cache):
     return rms_norm(x, w["model.norm.weight"], arch.rms_eps)
 
 
-def model_forward(w, arch, inputs_embeds, cache, want_lm_logits=False):
+def model_forward(w, arch, inputs_embeds, cache, want_lm_logits=False, attn_impl="eager"):
     """VideoHeadLiveLlavaQwenForCausalLM.forward (video_head_live_llava_qwen.py:121-205) on inputs_embeds [M, hidden]:
     returns dict(informative_logits [M,2] fp32, relevance_logits [M,2] fp32, logits [M,V] fp32 (optional))."""
-    h = decoder_forward(w, arch, inputs_embeds, cache)
+    h = decoder_forward(w, arch, inputs_embeds, cache, attn_impl)
     out = {
         "informative_logits": F.linear(h, w["informative_head.weight"]).float(),
         "relevance_logits": F.linear(h, w["relevance_head.weight"]).float(),

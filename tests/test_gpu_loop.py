@@ -168,3 +168,18 @@ def test_benchmark_driver_writes_reference_jsonl(setup, tmp_path):
     for d in lines[0]["debug_data"]:
         assert set(d) == {"time", "informative_score", "relevance_score"}
         assert round(d["informative_score"], 3) == d["informative_score"]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (symmetric memory over NVLink)")
+def test_peer_store_encoder_two_gpus():
+    """Frame-parallel encode where each rank's projector/pool kernel stores into the owner's HBM (no collective):
+    bit-identical to a single-rank encode; the tool asserts that itself."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MMD_EXCHANGE="peer", N_FRAMES="40")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "check_multigpu.py")], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "max diff vs single-rank encode 0.0" in r.stdout

@@ -10,7 +10,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mmduet_b200.config import ModelConfig  # noqa: E402
 from mmduet_b200.engine import DecoderEngine, VisionEngine  # noqa: E402
-from mmduet_b200.parallel import FrameParallelEncoder, frame_range  # noqa: E402
+from mmduet_b200.parallel import FrameParallelEncoder, PeerStoreEncoder, frame_range  # noqa: E402
 from mmduet_b200.random_init import random_state_dict, synthetic_frames  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -23,7 +23,12 @@ vis = VisionEngine(cfg, sd, dev)
 n = int(os.environ.get("N_FRAMES", "96"))
 frames = synthetic_frames(n, seed=5, device=dev)          # same seed on every rank: the full video, sliced below
 lo, hi = frame_range(n, world, rank)
-enc = FrameParallelEncoder(lambda fr: vis.visual_embed(fr, normalize=True), vis.tokens_per_frame, cfg.hidden, device=dev, owner=0)
+mode = os.environ.get("MMD_EXCHANGE", "peer")              # "peer": kernel stores into the owner's HBM; "nccl": send/recv
+if mode == "peer":
+    enc = PeerStoreEncoder(lambda fr, dst: vis.visual_embed(fr, normalize=True, out=dst), vis.tokens_per_frame, cfg.hidden,
+                           max_frames=n, device=dev, owner=0)
+else:
+    enc = FrameParallelEncoder(lambda fr: vis.visual_embed(fr, normalize=True), vis.tokens_per_frame, cfg.hidden, device=dev, owner=0)
 for _ in range(2):
     out, ready = enc.encode(n, frames[lo:hi])
     FrameParallelEncoder.wait_all(ready)
@@ -38,7 +43,7 @@ dt = time.perf_counter() - t0
 if rank == 0:
     ref = vis.visual_embed(frames, normalize=True)
     diff = (out.float() - ref.float()).abs().max().item()
-    print(f"world {world}: {n} frames encoded+gathered in {dt*1e3:.1f} ms ({n/dt:.0f} frames/s), max diff vs single-rank encode {diff}")
+    print(f"world {world} [{mode}]: {n} frames encoded+gathered in {dt*1e3:.1f} ms ({n/dt:.0f} frames/s), max diff vs single-rank encode {diff}")
     assert diff == 0.0
     dec = DecoderEngine(cfg, sd, dev, max_context=n * 49 + 64, max_tokens=512)
     st, L = dec.new_stream(), 0

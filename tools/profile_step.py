@@ -1,5 +1,5 @@
 """Small, fixed kernel sequence for ncu (launch list / --set full captures).  Never a source of bench numbers.
-  python tools/profile_step.py step        one 32-frame encode + two 8-frame decoder passes at ~3k context (full-size model)
+  python tools/profile_step.py step        one 32-frame encode + two 10-frame decoder passes at ~3k context (full-size model)
   python tools/profile_step.py gate_up     the dominant weight-streaming GEMM alone (M=392 and M=49), 4 launches each
   python tools/profile_step.py vit         one ViT layer's kernels at batch 32"""
 import os
@@ -54,8 +54,8 @@ torch.cuda.synchronize()
 torch.cuda.nvtx.range_push("profiled")
 emb = vis.visual_embed(fr, normalize=True)
 for p in range(2):
-    rows = [49 * (j + 1) - 1 for j in range(8)]
-    out = dec.step([dict(storage=st, past=L, ids=[], frames=emb[p * 392:(p + 1) * 392], score_rows=rows)], score="frame_ends")
+    rows = [49 * (j + 1) - 1 for j in range(10)]
+    out = dec.step([dict(storage=st, past=L, ids=[], frames=emb[p * 490:(p + 1) * 490], score_rows=rows)], score="frame_ends")
     L = out["views"][0].length
 torch.cuda.synchronize()
 torch.cuda.nvtx.range_pop()
