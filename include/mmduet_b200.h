@@ -77,6 +77,12 @@ MMD_API int mmd_gemm_splits(int64_t K, int k_splits);
 /* ---------------------------------------------------------------------------------------------------------------
  * Building-block kernels (exported so that tests can check each against the oracle).
  * ------------------------------------------------------------------------------------------------------------- */
+/* Frame ingest: decoded BGR uint8 frames [T, in_h, in_w, 3] -> RGB uint8 [T, 3, res, res], aspect-preserving
+ * 8-bit INTER_LINEAR resize (bit-exact with cv2.resize: 11-bit fixed-point separable filter) of the longer side to `res`,
+ * centred zero padding, BGR->RGB, HWC->CHW.  Replaces the cv2.resize / copyMakeBorder / cvtColor / transpose chain of
+ * test/datasets.py:50-72 and demo/liveinfer.py:32-54 (video decoding itself stays on the host).  res % 4 == 0. */
+MMD_API int mmd_frame_ingest(const void* frames_bgr_hwc, int n_frames, int in_h, int in_w, void* out_rgb_chw, int res,
+                             void* stream);
 /* Patch im2col (+ optional (x/255-0.5)/0.5): pixels [T,3,img,img] (u8/bf16/f32) -> A bf16 [T*G*G, k_pad].
  * SiglipVisionEmbeddings Conv2d (TF:models/siglip/modeling_siglip.py:124-130); models/vision_live.py:13. */
 MMD_API int mmd_im2col(const void* pixels, int px_dtype, int normalize, void* A, int T, int img, int patch, int k_pad,

@@ -82,6 +82,7 @@ SIGNATURES = {
     "mmd_profile_tag_name": (ctypes.c_char_p, [c_int]),
     "mmd_profile_start": (c_int, [c_void_p, ctypes.c_char_p]),
     "mmd_profile_stop": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "mmd_frame_ingest": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "mmd_im2col": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mmd_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int, c_float, c_void_p]),
     "mmd_vit_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

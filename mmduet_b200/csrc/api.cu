@@ -199,6 +199,19 @@ int mmd_gemm_bf16(mmd_ctx* c, int epi, int act, const void* X, const void* X2, i
 
 int mmd_gemm_splits(int64_t K, int k_splits) { return mmd::gemm_effective_splits((int)K, k_splits); }
 
+int mmd_frame_ingest(const void* frames_bgr_hwc, int n_frames, int in_h, int in_w, void* out_rgb_chw, int res, void* stream) {
+  if (frames_bgr_hwc == nullptr || out_rgb_chw == nullptr || n_frames < 0 || in_h <= 0 || in_w <= 0 || res <= 0 || res % 4 != 0)
+    return fail(MMD_ERR_ARG, "mmd_frame_ingest: bad arguments (res must be a positive multiple of 4)");
+  // the reference's int((short/long) * res) may truncate to 0 for extreme aspect ratios; cv2.resize raises there
+  const int nw = in_w > in_h ? res : (int)(((double)in_w / (double)in_h) * res);
+  const int nh = in_w > in_h ? (int)(((double)in_h / (double)in_w) * res) : res;
+  if (nw < 1 || nh < 1) return fail(MMD_ERR_ARG, "mmd_frame_ingest: aspect ratio too extreme (resized side would be 0)");
+  if (n_frames == 0) return 0;
+  RUNK(mmd::launch_frame_ingest(static_cast<const uint8_t*>(frames_bgr_hwc), n_frames, in_h, in_w, static_cast<uint8_t*>(out_rgb_chw), res,
+                                S(stream)), "mmd_frame_ingest");
+  return check_launch("mmd_frame_ingest");
+}
+
 int mmd_im2col(const void* pixels, int px_dtype, int normalize, void* A, int T, int img, int patch, int k_pad, void* stream) {
   if (pixels == nullptr || A == nullptr || T < 0 || patch <= 0 || img < patch || k_pad < 3 * patch * patch)
     return fail(MMD_ERR_ARG, "mmd_im2col: bad arguments");

@@ -73,6 +73,73 @@ __global__ void im2col_kernel(const TIn* __restrict__ px, __nv_bfloat16* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Frame ingest: aspect-preserving 8-bit bilinear resize + centred zero pad + BGR->RGB + HWC->CHW, bit-exact with the
+// cv2.resize / copyMakeBorder / cvtColor / transpose chain of the reference (test/datasets.py:50-72).  OpenCV's 8-bit
+// INTER_LINEAR is a separable fixed-point filter: weights rounded to 11 bits, horizontal pass into int32, vertical pass
+// (b * (S >> 4)) >> 16 summed, + 2, >> 2.  The coordinate arithmetic below uses the same double / float operation
+// sequence (explicit _rn intrinsics: no FMA contraction), so the weights are the same integers.
+// ---------------------------------------------------------------------------------------------------------------
+struct ResizeTap { int i0, i1, w0, w1; };
+
+__device__ __forceinline__ ResizeTap resize_tap(int d, int src, int dst, bool drop_fraction_at_edges) {
+  const double scale = __ddiv_rn(1.0, __ddiv_rn((double)dst, (double)src));
+  float f = __double2float_rn(__dsub_rn(__dmul_rn(__dadd_rn((double)d, 0.5), scale), 0.5));
+  int s = __float2int_rd(f);
+  f = __fsub_rn(f, (float)s);
+  ResizeTap t;
+  if (drop_fraction_at_edges) {            // horizontal: clamp the index and zero the fraction (resize.cpp dx loop)
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= src - 1) { s = src - 1; f = 0.f; }
+    t.i0 = s; t.i1 = min(s + 1, src - 1);
+  } else {                                 // vertical: rows are clamped, the fraction is kept
+    t.i0 = min(max(s, 0), src - 1); t.i1 = min(max(s + 1, 0), src - 1);
+  }
+  t.w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  t.w1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  return t;
+}
+
+__global__ void frame_ingest_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, int H, int W, int res, int nw, int nh,
+                                    int left, int top) {
+  const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y, t = blockIdx.z;
+  if (x4 >= res) return;
+  const uint8_t* src = frames + (size_t)t * H * W * 3;
+  uint32_t px[3] = {0u, 0u, 0u};           // four output pixels per plane, packed little-endian
+  const int yy = y - top;
+  if (yy >= 0 && yy < nh) {
+    const ResizeTap ty = resize_tap(yy, H, nh, false);
+    const uint8_t *r0 = src + (size_t)ty.i0 * W * 3, *r1 = src + (size_t)ty.i1 * W * 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int xx = x4 + k - left;
+      if (xx < 0 || xx >= nw) continue;
+      const ResizeTap tx = resize_tap(xx, W, nw, true);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {        // c indexes the SOURCE (BGR) channel; it lands in plane 2 - c
+        const int S0 = r0[tx.i0 * 3 + c] * tx.w0 + r0[tx.i1 * 3 + c] * tx.w1;
+        const int S1 = r1[tx.i0 * 3 + c] * tx.w0 + r1[tx.i1 * 3 + c] * tx.w1;
+        int v = (((ty.w0 * (S0 >> 4)) >> 16) + ((ty.w1 * (S1 >> 4)) >> 16) + 2) >> 2;
+        v = min(max(v, 0), 255);
+        px[2 - c] |= (uint32_t)v << (8 * k);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    *reinterpret_cast<uint32_t*>(out + (((size_t)t * 3 + c) * res + y) * res + x4) = px[c];
+}
+
+int launch_frame_ingest(const uint8_t* frames, int T, int H, int W, uint8_t* out, int res, cudaStream_t s) {
+  const int nw = W > H ? res : (int)(((double)W / (double)H) * res);     // test/datasets.py:51-58
+  const int nh = W > H ? (int)(((double)H / (double)W) * res) : res;
+  if (nw < 1 || nh < 1 || res % 4 != 0) return -2;
+  const int left = (res - nw) / 2, top = (res - nh) / 2;
+  dim3 block(96), grid((res / 4 + 95) / 96, res, T);
+  frame_ingest_kernel<<<grid, block, 0, s>>>(frames, out, H, W, res, nw, nh, left, top);
+  return 0;
+}
+
 int launch_im2col(const void* px, int px_dtype, int normalize, __nv_bfloat16* A, int T, int C, int img, int P, int Kpad,
                   cudaStream_t s) {
   const int G = img / P;

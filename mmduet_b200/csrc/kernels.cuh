@@ -8,6 +8,7 @@ namespace mmd {
 
 enum DType : int { DT_U8 = 0, DT_BF16 = 1, DT_F32 = 2 };
 
+int launch_frame_ingest(const uint8_t* frames, int T, int H, int W, uint8_t* out, int res, cudaStream_t s);
 int launch_im2col(const void* px, int px_dtype, int normalize, __nv_bfloat16* A, int T, int C, int img, int P, int Kpad,
                   cudaStream_t s);
 int launch_broadcast_rows(const float* src, float* dst, long long rows, int S, int D, cudaStream_t s);

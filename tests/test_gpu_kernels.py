@@ -289,3 +289,29 @@ def test_heads_and_argmax(env):
     pen = top[:2].contiguous()
     _lib.check(lib.mmd_argmax(lg.data_ptr(), V, pen.data_ptr(), 2, 100.0, out.data_ptr(), _s()))
     assert out.item() == top[2].item()
+
+
+@pytest.mark.parametrize("H,W", [(480, 640), (640, 360), (384, 384), (385, 383), (100, 37), (37, 100), (720, 1280), (2, 3)])
+def test_frame_ingest_bit_exact(env, H, W):
+    """mmd_frame_ingest == the oracle restatement of cv2.resize + copyMakeBorder + BGR2RGB + transpose (pinned to cv2 by
+    tests/test_ingest_cpu.py), bit for bit."""
+    from mmduet_b200.ingest import ingest_frames
+    from oracle import ingest as I
+    import numpy as np
+    rng = np.random.default_rng(H * 10007 + W)
+    frames = rng.integers(0, 256, (3, H, W, 3), dtype=np.uint8)
+    got = ingest_frames(torch.from_numpy(frames).cuda()).cpu().numpy()
+    for t in range(3):
+        ref = I.ingest_frame(frames[t])
+        assert np.array_equal(got[t], ref), (t, int(np.abs(got[t].astype(int) - ref.astype(int)).max()))
+
+
+def test_frame_ingest_feeds_the_encoder(env):
+    """ingest output is exactly what input_video_stream / visual_embed(normalize=True) take: [T,3,384,384] uint8."""
+    from mmduet_b200.ingest import ingest_frames
+    f = torch.randint(0, 256, (2, 270, 480, 3), dtype=torch.uint8, device="cuda")
+    out = ingest_frames(f)
+    assert out.shape == (2, 3, 384, 384) and out.dtype == torch.uint8
+    assert (out[:, :, :84] == 0).all() and (out[:, :, 300:] == 0).all()      # 480x270 -> 384x216, 84 rows of padding
+    with pytest.raises(Exception):
+        ingest_frames(torch.zeros(1, 1, 5000, 3, dtype=torch.uint8, device="cuda"))   # resized side would be 0
