@@ -179,10 +179,15 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def _encoder_batch():
+    from mmduet_b200.engine import VisionEngine
+    return VisionEngine.MAX_BATCH
+
+
 def workload_config(args, extra=None):
     c = {"workload": "BASELINE.json configs[1]: SigLIP-so400m/14@384 + Qwen2-7B LiveLlava frame step, 2 fps x 60 s = 120 synthetic "
                      "384x384 frames per stream, 32-token prefix, per-frame KV append + informative/relevance heads, random-init",
-         "frames_per_step": N_FRAMES, "encoder_batch": 32, "decoder_frames_per_pass": args.chunk,
+         "frames_per_step": N_FRAMES, "encoder_batch": _encoder_batch(), "decoder_frames_per_pass": args.chunk,
          "final_context_tokens": PREFIX_LEN + N_FRAMES * 49, "streams_per_gpu": 1,
          "l2": "weights (16 GB) and activations exceed the 126 MB L2 every step; no explicit flush"}
     if extra:
@@ -286,7 +291,7 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     stage = _lib.profile_stop(local)
     stage_ms = {k: round(v[0], 3) for k, v in sorted(stage.items(), key=lambda kv: -kv[1][0])}
-    known = {k: v for k, v in stage.items() if algorithmic_work(k, cfg, 49, 32) is not None}
+    known = {k: v for k, v in stage.items() if algorithmic_work(k, cfg, 49, _encoder_batch()) is not None}
     roof_tags = {}
     dominant = max(known.items(), key=lambda kv: kv[1][0])[0]
 
@@ -377,7 +382,7 @@ def run_gpu_arm(args):
             dist.destroy_process_group()
         return
     pk = peaks()
-    work = algorithmic_work(dominant, cfg, 49 * max(args.chunk, 1), 32)
+    work = algorithmic_work(dominant, cfg, 49 * max(args.chunk, 1), _encoder_batch())
     dom_ms, dom_n = dom
     roofline = None
     if work is not None and dom_n > 0:
@@ -400,7 +405,7 @@ def run_gpu_arm(args):
     roof_all = []
     tot_ms = sum(v[0] for v in stage.values())
     for tag, (ms_t, n_t) in sorted(stage.items(), key=lambda kv: -kv[1][0]):
-        wk = algorithmic_work(tag, cfg, 49 * max(args.chunk, 1), 32)
+        wk = algorithmic_work(tag, cfg, 49 * max(args.chunk, 1), _encoder_batch())
         if wk is None or n_t == 0:
             continue
         sec = ms_t / n_t / 1e3

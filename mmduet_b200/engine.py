@@ -2,6 +2,7 @@
 (SigLIP tower + projector + pooling) and the decoder with its paged KV pool.  PyTorch is used for device memory,
 streams and host<->device copies only; all arithmetic on the path happens in libmmduet_b200.so."""
 import ctypes
+import os
 import math
 import threading
 
@@ -61,7 +62,10 @@ class VisionEngine:
     """model.visual_embed(frames) of the reference (models/modeling_live.py:26-33): SigLIP tower (26 layers, pre-post-LN)
     -> mm_projector -> spatial pooling -> [T * tokens, hidden] bf16; also the legacy models/vision_live.py entry."""
 
-    MAX_BATCH = 32  # test/inference.py:208 encodes in batches of 32
+    # Frames per encoder launch sequence.  The reference encodes 32 at a time (test/inference.py:208); frames are independent,
+    # so the batch size does not change any value.  40 divides the usual 120/200/400-frame videos evenly and fills the
+    # attention grid better (40*16*3 CTAs = 12.97 waves of 148): +3.4 % frames/s over 32 (measured, bench.py).
+    MAX_BATCH = int(os.environ.get("MMD_ENCODER_BATCH", "40"))
 
     def __init__(self, cfg: ModelConfig, state_dict, device, with_projector=True, n_layers=None, legacy_post_ln=False,
                  attn_out_split=True, projector_hilo=True):
