@@ -416,6 +416,13 @@ def run_gpu_arm(args):
         else:
             roof_all.append({"kernel": tag, "share": round(ms_t / tot_ms, 3), "bound": "tensor", "achieved_TFLOPs": round(wk[1] / sec / 1e12, 1),
                              "frac": round(wk[1] / sec / 1e12 / pk["bf16_tflops_sustained"], 3)})
+            if tag in ("vit_attention", "kv_attention"):
+                # the attention kernels' real ceiling is MUFU.EX2 (16 lanes/clk/SM), not the tensor pipe: one exponential
+                # per score = QK^T+PV flops / (4 * head_dim); peak at the maximum SM clock (conservative)
+                dh = cfg.vit_head_dim if tag == "vit_attention" else cfg.head_dim
+                exps = wk[1] / (4.0 * dh)
+                mufu_peak = 16.0 * torch.cuda.get_device_properties(dev).multi_processor_count * (clocks.get("sm_max_mhz") or 1965.0) * 1e6
+                roof_all[-1].update(mufu_bound_frac=round(exps / sec / mufu_peak, 3), exps_per_launch=int(exps))
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": workload_config(args),
