@@ -44,7 +44,7 @@ MMD_API void mmd_destroy(mmd_ctx*);
 MMD_API int mmd_num_sms(mmd_ctx*);
 /* Attention kernels: 0 = mma.sync flash attention (csrc/vit_attention.cu, csrc/kv_attention.cu); 1 = tcgen05.mma / TMEM
  * flash attention (csrc/attn_tcgen05.cu); 2 (default) = auto: tcgen05 for the ViT and for decoder steps with >= 1024 stacked
- * query rows or >= 16k context, mma.sync for short single-frame steps.  Both are parity-tested.  Process-wide. */
+ * query rows or >= 2k context, mma.sync for short single-frame steps.  Both are parity-tested.  Process-wide. */
 MMD_API int mmd_set_attention_impl(int impl);
 /* 1 (default): large-M GEMMs (ViT, projector) run on CTA pairs (tcgen05.mma.cta_group::2, UMMA M = 256); 0: single-CTA
  * kernel everywhere.  Process-wide. */

@@ -271,11 +271,12 @@ __global__ void kv_attention_combine_kernel(const float* __restrict__ o_part, co
 }  // namespace
 
 // 0 = mma.sync kernels, 1 = tcgen05/TMEM kernels (attn_tcgen05.cu), 2 = auto: tcgen05 for the ViT and for decoder steps
-// with >= 1024 stacked query rows or >= 16k context (where it is 1.2-1.5x faster), mma.sync for short single-frame steps.
+// with >= 1024 stacked query rows or >= 2k context (measured faster from there on: tools/long_stream.py), mma.sync for
+// short single-frame steps.
 int g_attention_impl = 2;
 
 static bool kv_use_tc(int max_rows, int max_kv_len) {
-  if (g_attention_impl == 2) return max_rows >= 1024 || max_kv_len >= 16384;
+  if (g_attention_impl == 2) return max_rows >= 1024 || max_kv_len >= 2048;
   return g_attention_impl == 1;
 }
 
