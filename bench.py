@@ -474,7 +474,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chunk", type=int, default=10,
+    ap.add_argument("--chunk", type=int, default=40,
                     help="frames per decoder weight pass (1 = the reference's per-frame step; k > 1 gives identical scores and "
                          "decisions, see tests/test_gpu_loop.py::test_multi_frame_passes_equal_single_frame_steps)")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
