@@ -102,6 +102,13 @@ class PeerStoreEncoder:
         # the owner's buffer as seen from this rank (a peer mapping unless this rank is the owner)
         self.dst = self.buf if self.rank == owner else self.hdl.get_buffer(owner, tuple(self.buf.shape), torch.bfloat16)
 
+    N_CHANNELS = 15          # signal channels 1..15 (0 is the barrier's); the signal pad holds world x channels words
+
+    def _channel(self, n):
+        if n >= self.N_CHANNELS:
+            raise ValueError(f"PeerStoreEncoder: more than {self.N_CHANNELS} batches per rank; raise `batch`")
+        return 1 + n
+
     def encode(self, n_frames, local_frames):
         """Returns (tokens, ready) on the owner (tokens is a view of the symmetric buffer, valid until the next encode;
         ready[i]() makes the current stream wait until frame i has landed) and (None, None) elsewhere."""
@@ -110,26 +117,29 @@ class PeerStoreEncoder:
         assert len(local_frames) == hi - lo, (len(local_frames), lo, hi)
         # nobody may overwrite the owner's buffer while it is still decoding the previous video
         self.hdl.barrier(channel=0)
-        for b0 in range(lo, hi, self.batch):
+        for n, b0 in enumerate(range(lo, hi, self.batch)):
             b1 = min(b0 + self.batch, hi)
             self.embed_into(local_frames[b0 - lo:b1 - lo], self.dst[b0 * self.tpf:b1 * self.tpf])
             if self.rank != self.owner:
-                self.hdl.put_signal(self.owner, channel=1)     # stream-ordered after the kernel that stored the batch
+                # stream-ordered after the kernel that stored the batch.  One channel per batch: a signal is a binary
+                # semaphore, and reusing one channel would block this rank's stream until the owner had consumed the
+                # previous batch (the owner consumes in frame order, so ranks would serialise behind each other).
+                self.hdl.put_signal(self.owner, channel=self._channel(n))
         if self.rank != self.owner:
             return None, None
         pending = {}                                           # src rank -> list of its batches, in sending order
         for src in range(self.world):
             if src != self.owner:
                 s_lo, s_hi = frame_range(n_frames, self.world, src)
-                pending[src] = [(b0, min(b0 + self.batch, s_hi)) for b0 in range(s_lo, s_hi, self.batch)]
+                pending[src] = [(b0, min(b0 + self.batch, s_hi), self._channel(n)) for n, b0 in enumerate(range(s_lo, s_hi, self.batch))]
 
         def ready_fn(i):
             def wait():
                 for src, batches in pending.items():
-                    if batches and any(b0 <= i < b1 for b0, b1 in batches):
-                        while batches:                        # signals of one source arrive in order: consume up to frame i
-                            b0, b1 = batches.pop(0)
-                            self.hdl.wait_signal(src, channel=1)
+                    if batches and any(b0 <= i < b1 for b0, b1, _ in batches):
+                        while batches:                        # consume this source's signals up to the batch holding frame i
+                            b0, b1, ch = batches.pop(0)
+                            self.hdl.wait_signal(src, channel=ch)
                             if b0 <= i < b1:
                                 break
             return wait
