@@ -36,7 +36,6 @@ constexpr int TA_QT = 2;                   // query tiles per CTA
 constexpr int TA_BN = 64;                  // keys per tile
 constexpr int TA_QREGION = TA_BM * 128;    // one 64-column swizzled region of a 128-row operand (16 KB)
 constexpr int TA_KREGION = TA_BN * 128;    // same for a 64-row operand (8 KB)
-constexpr int TA_KRING = 5, TA_VRING = 5;
 constexpr int TA_SOFTMAX_WARPS = 4 * TA_QT, TA_LOADER_WARPS = 4;
 constexpr int TA_THREADS = 32 * (TA_SOFTMAX_WARPS + TA_LOADER_WARPS + 4);   // MMA warp + 3 idle warps: setmaxnreg works on whole warpgroups
 constexpr int TA_TMEM_PER_Q = 256;         // S0 [0,64) S1 [64,128) O [128, 128+DHP)
@@ -136,21 +135,35 @@ __device__ __forceinline__ void trace_ev(uint32_t* tr, int role, int j, int e) {
 #define TRACE_EV(role, j, e)
 #endif
 
-struct AttnSmem {  // byte offsets from the 1024-B aligned base
-  static constexpr int Q = 0;                                   // [qi][2 regions]
-  static constexpr int K = Q + TA_QT * 2 * TA_QREGION;          // ring of [2 regions]
-  static constexpr int V = K + TA_KRING * 2 * TA_KREGION;
-  static constexpr int BARS = V + TA_VRING * 2 * TA_KREGION;
+// Shared-memory layout and mbarrier indices for the two launch shapes:
+//   AttnCfg<2, 3>  persistent CTAs walking several work items: Q double-buffered (the loaders fetch the next item's Q while
+//                  this one finishes), K and V rings of 3:        2 x 64 KB + 2 x 3 x 16 KB = 224 KB
+//   AttnCfg<1, 5>  at most one work item per CTA (short single-frame decoder steps): one Q buffer, rings of 5, so every
+//                  tile of a short split is in flight at once:     64 KB + 2 x 5 x 16 KB = 224 KB
+template <int QBUF_, int RING_>
+struct AttnCfg {
+  static constexpr int QBUF = QBUF_, RING = RING_;
+  // byte offsets from the 1024-B aligned base
+  static constexpr int Q = 0;                                   // [buffer][qi][2 regions]
+  static constexpr int QBUF_BYTES = TA_QT * 2 * TA_QREGION;
+  static constexpr int K = Q + QBUF * QBUF_BYTES;               // ring of [2 regions]
+  static constexpr int V = K + RING * 2 * TA_KREGION;
+  static constexpr int BARS = V + RING * 2 * TA_KREGION;
   static constexpr int TOTAL = BARS + 512 + 1024;               // barriers + alignment slack
+  // barrier indices
+  static constexpr int BAR_Q_FULL = 0, BAR_Q_EMPTY = BAR_Q_FULL + QBUF;   // [buffer]
+  static constexpr int BAR_K_FULL = BAR_Q_EMPTY + QBUF, BAR_K_EMPTY = BAR_K_FULL + RING, BAR_V_FULL = BAR_K_EMPTY + RING,
+                       BAR_V_EMPTY = BAR_V_FULL + RING;
+  static constexpr int BAR_S_FULL = BAR_V_EMPTY + RING;         // [qi][2]
+  static constexpr int BAR_P_FULL = BAR_S_FULL + 2 * TA_QT;     // [qi][2]
+  static constexpr int BAR_O_FULL = BAR_P_FULL + 2 * TA_QT;     // [qi]
+  static constexpr int BAR_O_EMPTY = BAR_O_FULL + TA_QT;        // [qi]: the softmax group has read the finished O out of TMEM
+  static constexpr int BAR_COUNT = BAR_O_EMPTY + TA_QT;
+  static_assert(8 * BAR_COUNT + 8 <= 512, "barrier area");
+  static_assert(TOTAL <= 232448, "shared memory per CTA");
 };
-
-// barrier indices
-constexpr int BAR_Q_FULL = 0;
-constexpr int BAR_K_FULL = 1, BAR_K_EMPTY = BAR_K_FULL + TA_KRING, BAR_V_FULL = BAR_K_EMPTY + TA_KRING, BAR_V_EMPTY = BAR_V_FULL + TA_VRING;
-constexpr int BAR_S_FULL = BAR_V_EMPTY + TA_VRING;   // [qi][2]
-constexpr int BAR_P_FULL = BAR_S_FULL + 2 * TA_QT;  // [qi][2]
-constexpr int BAR_O_FULL = BAR_P_FULL + 2 * TA_QT;  // [qi]
-constexpr int BAR_COUNT = BAR_O_FULL + TA_QT;
+using AttnCfgPersistent = AttnCfg<2, 3>;
+using AttnCfgSingle = AttnCfg<1, 5>;
 
 struct VitAttnParams {
   const __nv_bfloat16* qkv;   // [T*S, 3*H*DH]
@@ -166,13 +179,18 @@ struct PagedAttnParams {
   const int* block_tables;
   float* o_part;                  // [n_splits, total_q*Hq, 128]
   float* ml_part;                 // [n_splits, total_q*Hq, 2]
-  int Hq, Hkv, n_splits;
+  int Hq, Hkv, n_splits, grid_x;   // grid_x = query blocks x kv heads
   long long part_stride_rows;
   float scale_log2e;
 };
 
-template <int DH, typename Front>
-__device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base, uint32_t tmem_base) {
+// The CTA is persistent: it walks the work items blockIdx.x, blockIdx.x + gridDim.x, ... (an item = 256 query rows of one
+// head x its key range).  Every role runs the same item loop with its own running counters, so the loaders are already
+// fetching the next item's Q (second Q buffer) and K/V tiles while the softmax groups finish and store the current one,
+// and the MMA threads issue the next item's first two QK^T products during that epilogue: the per-item prologue
+// (~6k clk until the first S tile) disappears from the critical path after the first item.
+template <int DH, typename Front, typename C, typename Params>
+__device__ __forceinline__ void attention_pipeline(const Params& prm, int n_items, uint32_t smem_base, uint32_t tmem_base) {
   constexpr int DHP = (DH + 15) / 16 * 16;      // head dim padded to the UMMA K/N granularity
   constexpr int CH = DH / 8;                     // 16-B chunks per row
   // When the head dim has padding columns (72 -> 80), column DH of V holds 1.0 for every key, so O[:, DH] accumulates
@@ -180,9 +198,8 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
   // together with O.
   constexpr bool ONES_COL = (DHP > DH);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bars = smem_base + AttnSmem::BARS;
+  const uint32_t bars = smem_base + C::BARS;
   auto bar = [&](int i) { return bars + 8u * i; };
-  const int n_tiles = fe.n_tiles();
   TRACE_INIT;
 
   if (warp >= TA_SOFTMAX_WARPS && warp < TA_SOFTMAX_WARPS + TA_LOADER_WARPS) {
@@ -191,42 +208,52 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
     // rounds before the matching V tile, so each stream runs as far ahead as its own ring allows); all four load Q first.
     // Work is split in 16-B units with consecutive lanes on consecutive chunks of a row, so one warp instruction reads
     // whole rows (full sectors) instead of one chunk from each of 32 rows.
+    // Completion is tracked by the mbarriers themselves (cp.async.mbarrier.arrive.noinc: the arrival fires when this
+    // thread's copies so far have landed), so a loader thread never waits for data: it only blocks on a free ring slot
+    // or Q buffer and runs ahead of the MMA threads, across item boundaries (a tile takes ~3000 clk to land, one is
+    // consumed every ~1000-1800 clk).
     reg_dec<72>();
     const int lt = threadIdx.x - 32 * TA_SOFTMAX_WARPS;      // 0..127
     const bool is_v = lt >= 64;
     const int lrow = lt & 63;
-    const int ring = is_v ? TA_VRING : TA_KRING;
-    const int bar_full = is_v ? BAR_V_FULL : BAR_K_FULL, bar_empty = is_v ? BAR_V_EMPTY : BAR_K_EMPTY;
-    const uint32_t ring_base = smem_base + (is_v ? AttnSmem::V : AttnSmem::K);
+    const int ring = is_v ? C::RING : C::RING;
+    const int bar_full = is_v ? C::BAR_V_FULL : C::BAR_K_FULL, bar_empty = is_v ? C::BAR_V_EMPTY : C::BAR_K_EMPTY;
+    const uint32_t ring_base = smem_base + (is_v ? C::V : C::K);
+    int g = 0;                                               // tiles this stream has loaded so far (all items)
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      Front fe(prm, item);
+      const int n_tiles = fe.n_tiles();
+      const int qb = it % C::QBUF;
+      // the Q buffer is free once both softmax groups have finished the item that used it (their staged stores included)
+      mbar_wait(bar(C::BAR_Q_EMPTY + qb), ((it / C::QBUF) & 1) ^ 1);
+      const uint32_t qbase = smem_base + C::Q + qb * C::QBUF_BYTES;
 #pragma unroll 4
-    for (int u = lt; u < TA_QT * TA_BM * CH; u += 32 * TA_LOADER_WARPS) {
-      const int r = u / CH, c = u % CH;                      // row within the CTA's 256 query rows, 16-B chunk
-      const __nv_bfloat16* src = fe.q_row(r);
-      const uint32_t dst = smem_base + AttnSmem::Q + (r / TA_BM) * 2 * TA_QREGION + (c >> 3) * TA_QREGION + sw128_off(r % TA_BM, c & 7);
-      cp_async16(dst, src ? src + c * 8 : fe.any_ptr(), src ? 16 : 0);
-    }
-    // Completion is tracked by the mbarriers themselves (cp.async.mbarrier.arrive.noinc: the arrival fires when this
-    // thread's copies so far have landed), so a loader thread never waits for data: it only blocks on a free ring slot
-    // and runs up to the ring depth ahead of the MMA threads (a tile takes ~3000 clk to land, one is consumed every
-    // ~1000-1800 clk).
-    cp_async_mbar_arrive(bar(BAR_Q_FULL));
-    for (int j = 0; j < n_tiles; ++j) {
-      const int st = j % ring;
-      if (lrow == 0) TRACE_EV(4 + is_v, j, 0);
-      mbar_wait(bar(bar_empty + st), ((j / ring) & 1) ^ 1);
-      if (lrow == 0) TRACE_EV(4 + is_v, j, 1);
-      const uint32_t dstb = ring_base + st * 2 * TA_KREGION;
-      int valid;                                             // rows past `valid` are zero-filled
-      const __nv_bfloat16* tile = fe.kv_tile(j, is_v, valid);
-      const long long rstride = fe.kv_row_stride();
-#pragma unroll
-      for (int i = 0; i < CH; ++i) {
-        const int u = i * 64 + lrow, r = u / CH, c = u % CH;
-        const bool ok = r < valid;
-        cp_async16(dstb + (c >> 3) * TA_KREGION + sw128_off(r, c & 7), ok ? tile + r * rstride + c * 8 : fe.any_ptr(), ok ? 16 : 0);
+      for (int u = lt; u < TA_QT * TA_BM * CH; u += 32 * TA_LOADER_WARPS) {
+        const int r = u / CH, c = u % CH;                    // row within the CTA's 256 query rows, 16-B chunk
+        const __nv_bfloat16* src = fe.q_row(r);
+        const uint32_t dst = qbase + (r / TA_BM) * 2 * TA_QREGION + (c >> 3) * TA_QREGION + sw128_off(r % TA_BM, c & 7);
+        cp_async16(dst, src ? src + c * 8 : fe.any_ptr(), src ? 16 : 0);
       }
-      cp_async_mbar_arrive(bar(bar_full + st));
-      if (lrow == 0) TRACE_EV(4 + is_v, j, 2);
+      cp_async_mbar_arrive(bar(C::BAR_Q_FULL + qb));
+      for (int j = 0; j < n_tiles; ++j, ++g) {
+        const int st = g % ring;
+        if (lrow == 0) TRACE_EV(4 + is_v, g, 0);
+        mbar_wait(bar(bar_empty + st), ((g / ring) & 1) ^ 1);
+        if (lrow == 0) TRACE_EV(4 + is_v, g, 1);
+        const uint32_t dstb = ring_base + st * 2 * TA_KREGION;
+        int valid;                                           // rows past `valid` are zero-filled
+        const __nv_bfloat16* tile = fe.kv_tile(j, is_v, valid);
+        const long long rstride = fe.kv_row_stride();
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const int u = i * 64 + lrow, r = u / CH, c = u % CH;
+          const bool ok = r < valid;
+          cp_async16(dstb + (c >> 3) * TA_KREGION + sw128_off(r, c & 7), ok ? tile + r * rstride + c * 8 : fe.any_ptr(), ok ? 16 : 0);
+        }
+        cp_async_mbar_arrive(bar(bar_full + st));
+        if (lrow == 0) TRACE_EV(4 + is_v, g, 2);
+      }
     }
     cp_async_commit();
     cp_async_wait<0>();   // nothing may still be writing this CTA's shared memory when it exits
@@ -246,51 +273,63 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
       auto desc = [](uint32_t lo) { return (static_cast<uint64_t>(HI) << 32) | lo; };
       auto lo_k = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | (1u << 16); };                       // K-major
       auto lo_mn = [](uint32_t addr) { return ((addr & 0x3FFFFu) >> 4) | ((uint32_t)(TA_KREGION >> 4) << 16); };   // MN-major
-      const uint32_t q_lo = lo_k(smem_base + AttnSmem::Q), k_lo = lo_k(smem_base + AttnSmem::K), v_lo = lo_mn(smem_base + AttnSmem::V);
-      auto issue_qk = [&](int j) {
-        const int st = j % TA_KRING, sb = j & 1;
-        TRACE_EV(2 + qi, j, 4);
-        mbar_wait(bar(BAR_K_FULL + st), (j / TA_KRING) & 1);
-        fence_proxy_async_smem();                            // cp.async (generic proxy) data -> tcgen05.mma operand reads
-        tc_fence_after();
-        TRACE_EV(2 + qi, j, 5);
-        // No "S buffer free" barrier: QK_j is issued after PV_{j-2} (which read P_{j-2} from this buffer, itself written
-        // after S_{j-2} had been read), and the tensor pipe executes this thread's MMAs in issue order.
-        const uint32_t qa = q_lo + qi * (2 * TA_QREGION >> 4), ka = k_lo + st * (2 * TA_KREGION >> 4);
-        const uint32_t d = tmem_base + qi * TA_TMEM_PER_Q + sb * TA_BN;
+      const uint32_t q_lo = lo_k(smem_base + C::Q), k_lo = lo_k(smem_base + C::K), v_lo = lo_mn(smem_base + C::V);
+      int g0 = 0;            // key tiles of all earlier items: S/P/O barrier phases and the K/V ring positions run on
+      int busy_items = 0;    // items that had at least one tile (O_EMPTY phases)
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        Front fe(prm, item);
+        const int n_tiles = fe.n_tiles();
+        const int qb = it % C::QBUF;
+        const uint32_t qa = q_lo + ((qb * C::QBUF_BYTES + qi * 2 * TA_QREGION) >> 4);
+        auto issue_qk = [&](int j) {
+          const int g = g0 + j, st = g % C::RING, sb = g & 1;
+          TRACE_EV(2 + qi, g, 4);
+          mbar_wait(bar(C::BAR_K_FULL + st), (g / C::RING) & 1);
+          fence_proxy_async_smem();                          // cp.async (generic proxy) data -> tcgen05.mma operand reads
+          tc_fence_after();
+          TRACE_EV(2 + qi, g, 5);
+          // No "S buffer free" barrier: QK_g is issued after PV_{g-2} (which read P_{g-2} from this buffer, itself written
+          // after S_{g-2} had been read), and the tensor pipe executes this thread's MMAs in issue order.
+          const uint32_t ka = k_lo + st * (2 * TA_KREGION >> 4);
+          const uint32_t d = tmem_base + qi * TA_TMEM_PER_Q + sb * TA_BN;
 #pragma unroll
-        for (int k = 0; k < DHP / 16; ++k)
-          umma_f16(d, desc(qa + (k >> 2) * (TA_QREGION >> 4) + 2 * (k & 3)), desc(ka + (k >> 2) * (TA_KREGION >> 4) + 2 * (k & 3)), idesc_qk,
-                   k > 0 ? 1u : 0u);
-        umma_commit(bar(BAR_S_FULL + qi * 2 + sb));
-        umma_commit(bar(BAR_K_EMPTY + st));                  // the slot is free once both tiles' issuers have arrived
-        TRACE_EV(2 + qi, j, 6);
-      };
-      mbar_wait(bar(BAR_Q_FULL), 0);
-      fence_proxy_async_smem();
-      tc_fence_after();
-      for (int j = 0; j < 2 && j < n_tiles; ++j) issue_qk(j);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int st = j % TA_VRING;
-        {
-          TRACE_EV(2 + qi, j, 0);
-          mbar_wait(bar(BAR_V_FULL + st), (j / TA_VRING) & 1);   // usually long complete: take its latency before P arrives
-          TRACE_EV(2 + qi, j, 1);
-          mbar_wait(bar(BAR_P_FULL + qi * 2 + (j & 1)), (j >> 1) & 1);
-          TRACE_EV(2 + qi, j, 2);
+          for (int k = 0; k < DHP / 16; ++k)
+            umma_f16(d, desc(qa + (k >> 2) * (TA_QREGION >> 4) + 2 * (k & 3)), desc(ka + (k >> 2) * (TA_KREGION >> 4) + 2 * (k & 3)), idesc_qk,
+                     k > 0 ? 1u : 0u);
+          umma_commit(bar(C::BAR_S_FULL + qi * 2 + sb));
+          umma_commit(bar(C::BAR_K_EMPTY + st));                // the slot is free once both tiles' issuers have arrived
+          TRACE_EV(2 + qi, g, 6);
+        };
+        mbar_wait(bar(C::BAR_Q_FULL + qb), (it / C::QBUF) & 1);
+        fence_proxy_async_smem();
+        tc_fence_after();
+        for (int j = 0; j < 2 && j < n_tiles; ++j) issue_qk(j);
+        for (int j = 0; j < n_tiles; ++j) {
+          const int g = g0 + j, st = g % C::RING;
+          TRACE_EV(2 + qi, g, 0);
+          mbar_wait(bar(C::BAR_V_FULL + st), (g / C::RING) & 1);   // usually long complete: take its latency before P arrives
+          TRACE_EV(2 + qi, g, 1);
+          mbar_wait(bar(C::BAR_P_FULL + qi * 2 + (g & 1)), (g >> 1) & 1);
+          if (j == 0) {     // the previous item's O must have been read out of TMEM before this PV overwrites it
+            mbar_wait(bar(C::BAR_O_EMPTY + qi), (busy_items & 1) ^ 1);
+            ++busy_items;
+          }
+          TRACE_EV(2 + qi, g, 2);
           fence_proxy_async_smem();
           tc_fence_after();
-          // P_j (bf16) sits in TMEM over the first 32 columns of the S buffer it was computed from: 8 columns per K=16 step
-          const uint32_t tP = tmem_base + qi * TA_TMEM_PER_Q + (j & 1) * TA_BN;
+          // P_g (bf16) sits in TMEM over the first 32 columns of the S buffer it was computed from: 8 columns per K=16 step
+          const uint32_t tP = tmem_base + qi * TA_TMEM_PER_Q + (g & 1) * TA_BN;
           const uint32_t va = v_lo + st * (2 * TA_KREGION >> 4);
 #pragma unroll
           for (int k = 0; k < TA_BN / 16; ++k)
             umma_f16_ts(tmem_base + qi * TA_TMEM_PER_Q + 2 * TA_BN, tP + 8 * k, desc(va + k * (2048 >> 4)), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-          umma_commit(bar(BAR_O_FULL + qi));
-          umma_commit(bar(BAR_V_EMPTY + st));
-          TRACE_EV(2 + qi, j, 3);
+          umma_commit(bar(C::BAR_O_FULL + qi));
+          umma_commit(bar(C::BAR_V_EMPTY + st));
+          TRACE_EV(2 + qi, g, 3);
           if (j + 2 < n_tiles) issue_qk(j + 2);
         }
+        g0 += n_tiles;
       }
     }
     __syncwarp();
@@ -300,147 +339,156 @@ __device__ __forceinline__ void attention_pipeline(Front& fe, uint32_t smem_base
     const int qi = warp >> 2;
     const int row = (warp & 3) * 32 + lane;                 // row within the query tile = TMEM lane
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + qi * TA_TMEM_PER_Q;
-    float m_ref = -INFINITY, l_run = 0.f;
-    const int key_lim = fe.key_limit(qi * TA_BM + row);    // tile-local key indices > key_lim are masked for this row
-    const float sl2 = fe.scale_log2e();
     // MUFU.EX2 (16 lanes/clk/SM) is the slowest pipe of this kernel: one key tile costs 2 x 128 x 64 exponentials =
     // 1024 clk of it, as much as the tile's tensor work.  A warp issues in order, so while its MUFU instructions queue
     // nothing else of that warp moves; the second group's TMEM loads / max / barrier traffic fill those slots.
     struct Tile { uint32_t a[32], b[32]; };
     auto val = [](const Tile& t, int i) { return __uint_as_float(i < 32 ? t.a[i] : t.b[i - 32]); };
-    auto fetch = [&](int j, Tile& t) {                     // wait for S_j and start reading it (finish: tmem_ld_wait)
-      mbar_wait(bar(BAR_S_FULL + qi * 2 + (j & 1)), (j >> 1) & 1);
-      tc_fence_after();
-      tmem_ld_32x32b_x32(t_row + (j & 1) * TA_BN, t.a);
-      tmem_ld_32x32b_x32(t_row + (j & 1) * TA_BN + 32, t.b);
-    };
-    auto mask_tile = [&](int j, Tile& t) {
-      // masking only in the tiles that reach beyond some row's limit (warp-uniform test; ISETP/SEL per element only there)
-      const int k0 = j * TA_BN;
-      if (__any_sync(0xffffffffu, k0 + TA_BN - 1 > key_lim)) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          t.a[i] = (k0 + i > key_lim) ? 0xff800000u : t.a[i];
-          t.b[i] = (k0 + 32 + i > key_lim) ? 0xff800000u : t.b[i];
-        }
-      }
-    };
-    auto row_max = [&](const Tile& t) {                    // four chains of 3-input FMNMX3
-      float m0 = fmaxf(val(t, 0), val(t, 1)), m1 = fmaxf(val(t, 2), val(t, 3)), m2 = fmaxf(val(t, 4), val(t, 5)), m3 = fmaxf(val(t, 6), val(t, 7));
-#pragma unroll
-      for (int i = 8; i < TA_BN; i += 8) {
-        m0 = fmaxf(m0, fmaxf(val(t, i), val(t, i + 1)));
-        m1 = fmaxf(m1, fmaxf(val(t, i + 2), val(t, i + 3)));
-        m2 = fmaxf(m2, fmaxf(val(t, i + 4), val(t, i + 5)));
-        m3 = fmaxf(m3, fmaxf(val(t, i + 6), val(t, i + 7)));
-      }
-      return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-    };
     // The two groups take turns in the exponential phase (named barriers 1 + qi: "group qi may go"): a group alone
     // streams its MUFU work almost back to back, and the other group's non-MUFU phases run underneath instead of both
-    // groups queueing on the MUFU and then both leaving it idle.
+    // groups queueing on the MUFU and then both leaving it idle.  The token keeps circulating across items.
     constexpr int NSM = 32 * TA_SOFTMAX_WARPS;
-    if (qi == 1 && n_tiles > 0) named_bar_arrive(1, NSM);
-    Tile cur;
-    for (int j = 0; j < n_tiles; ++j) {
-      const int sb = j & 1;
-      if (row == 0) TRACE_EV(qi, j, 0);
-      fetch(j, cur);
-      if (row == 0) TRACE_EV(qi, j, 1);
-      tmem_ld_wait();
-      mask_tile(j, cur);
-      if (row == 0) TRACE_EV(qi, j, 2);
-      const float mx = row_max(cur);
-      const float m_new = fmaxf(m_ref, mx);
-      const bool need = j > 0 && m_new > m_ref && (m_ref == -INFINITY || (m_new - m_ref) * sl2 > 8.0f);
-      if (j == 0) {
-        m_ref = m_new;
-      } else if (__any_sync(0xffffffffu, need)) {
-        // lazy rescaling: O (TMEM) and l move to the new exponent base.  tcgen05.ld/st are .sync.aligned, so the whole
-        // warp takes this path together; rows that do not need it rescale by 1.  PV_{j-1} must have completed first
-        // (it is the newest PV that can have been issued, so the barrier is at most one phase ahead of this parity).
-        mbar_wait(bar(BAR_O_FULL + qi), (j - 1) & 1);
+    int total_tiles = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) total_tiles += Front(prm, item).n_tiles();
+    if (qi == 1 && total_tiles > 0) named_bar_arrive(1, NSM);
+    int g0 = 0, it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      Front fe(prm, item);
+      const int n_tiles = fe.n_tiles();
+      const int key_lim = fe.key_limit(qi * TA_BM + row);  // tile-local key indices > key_lim are masked for this row
+      const float sl2 = fe.scale_log2e();
+      float m_ref = -INFINITY, l_run = 0.f;
+      Tile cur;
+      for (int j = 0; j < n_tiles; ++j) {
+        const int g = g0 + j, sb = g & 1;
+        if (row == 0) TRACE_EV(qi, g, 0);
+        mbar_wait(bar(C::BAR_S_FULL + qi * 2 + sb), (g >> 1) & 1);     // S_g: wait, then read the row into registers
         tc_fence_after();
-        const float f = !need ? 1.f : ((m_ref == -INFINITY) ? 0.f : exp2f((m_ref - m_new) * sl2));
+        tmem_ld_32x32b_x32(t_row + sb * TA_BN, cur.a);
+        tmem_ld_32x32b_x32(t_row + sb * TA_BN + 32, cur.b);
+        if (row == 0) TRACE_EV(qi, g, 1);
+        tmem_ld_wait();
+        {
+          // masking only in the tiles that reach beyond some row's limit (warp-uniform test; ISETP/SEL per element only there)
+          const int k0 = j * TA_BN;
+          if (__any_sync(0xffffffffu, k0 + TA_BN - 1 > key_lim)) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              cur.a[i] = (k0 + i > key_lim) ? 0xff800000u : cur.a[i];
+              cur.b[i] = (k0 + 32 + i > key_lim) ? 0xff800000u : cur.b[i];
+            }
+          }
+        }
+        if (row == 0) TRACE_EV(qi, g, 2);
+        float mx;
+        {                                                    // four chains of 3-input FMNMX3
+          float m0 = fmaxf(val(cur, 0), val(cur, 1)), m1 = fmaxf(val(cur, 2), val(cur, 3)), m2 = fmaxf(val(cur, 4), val(cur, 5)),
+                m3 = fmaxf(val(cur, 6), val(cur, 7));
+#pragma unroll
+          for (int i = 8; i < TA_BN; i += 8) {
+            m0 = fmaxf(m0, fmaxf(val(cur, i), val(cur, i + 1)));
+            m1 = fmaxf(m1, fmaxf(val(cur, i + 2), val(cur, i + 3)));
+            m2 = fmaxf(m2, fmaxf(val(cur, i + 4), val(cur, i + 5)));
+            m3 = fmaxf(m3, fmaxf(val(cur, i + 6), val(cur, i + 7)));
+          }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        }
+        const float m_new = fmaxf(m_ref, mx);
+        const bool need = j > 0 && m_new > m_ref && (m_ref == -INFINITY || (m_new - m_ref) * sl2 > 8.0f);
+        if (j == 0) {
+          m_ref = m_new;
+        } else if (__any_sync(0xffffffffu, need)) {
+          // lazy rescaling: O (TMEM) and l move to the new exponent base.  tcgen05.ld/st are .sync.aligned, so the whole
+          // warp takes this path together; rows that do not need it rescale by 1.  PV_{g-1} must have completed first
+          // (it is the newest PV that can have been issued, so the barrier is at most one phase ahead of this parity).
+          mbar_wait(bar(C::BAR_O_FULL + qi), (g - 1) & 1);
+          tc_fence_after();
+          const float f = !need ? 1.f : ((m_ref == -INFINITY) ? 0.f : exp2f((m_ref - m_new) * sl2));
+#pragma unroll
+          for (int c0 = 0; c0 < DHP; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_row + 2 * TA_BN + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+            tmem_st_32x32b_x16(t_row + 2 * TA_BN + c0, v);
+          }
+          tmem_st_wait();
+          if (need) {
+            l_run *= f;
+            m_ref = m_new;
+          }
+        }
+        named_bar_sync(1 + qi, NSM);
+        if (row == 0) TRACE_EV(qi, g, 3);
+        const float msc = (m_ref == -INFINITY) ? 0.f : m_ref * sl2;
+        // probabilities -> bf16 P tile, written back into TMEM over the S buffer they came from (two keys per 32-bit
+        // column).  PV_{g-2}, the last reader of these columns, completed before S_g was produced: no wait needed, and
+        // the softmax of the next tile can start while PV_g is still running.
+        float rs = 0.f;
+#pragma unroll
+        for (int c = 0; c < TA_BN / 32; ++c) {         // 16 columns = 32 keys per store
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = fmaf(val(cur, 32 * c + i), sl2, -msc);
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+#if MMD_EXP_MODE == 3   // timing experiment only: no exponential at all
+            const float p0 = x[2 * i], p1 = x[2 * i + 1];
+#else
+            const float p0 = exp_on_fma_pipe(i) ? exp2_poly(x[2 * i]) : exp2f(x[2 * i]);
+            const float p1 = exp_on_fma_pipe(i) ? exp2_poly(x[2 * i + 1]) : exp2f(x[2 * i + 1]);
+#endif
+            __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+            pk[i] = *reinterpret_cast<uint32_t*>(&h);
+            if constexpr (!ONES_COL) {
+              // row sum of the ROUNDED probabilities (numerator and denominator stay consistent under the stale base)
+              rs += __uint_as_float(pk[i] << 16) + __uint_as_float(pk[i] & 0xffff0000u);
+            }
+          }
+          tmem_st_32x32b_x16(t_row + sb * TA_BN + 16 * c, pk);
+        }
+        l_run += rs;
+        if (qi == 0 || g + 1 < total_tiles) named_bar_arrive(2 - qi, NSM);
+        if (row == 0) TRACE_EV(qi, g, 4);
+        tmem_st_wait();
+        if (row == 0) TRACE_EV(qi, g, 5);
+        tc_fence_before();
+        // one P_FULL barrier per S buffer: tile g+2's arrivals cannot start before the MMA thread has consumed tile g's
+        // (S_{g+2} is produced after PV_g), so a phase can never be skipped and no wait for PV_{g-1} is needed here
+        mbar_arrive(bar(C::BAR_P_FULL + qi * 2 + sb));
+        if (row == 0) TRACE_EV(qi, g, 6);
+      }
+      if (row == 0) TRACE_EV(6, qi + 2 * (it & 3), 2);
+      float o[DHP];
+      if (n_tiles > 0) {
+        mbar_wait(bar(C::BAR_O_FULL + qi), (g0 + n_tiles - 1) & 1);
+        tc_fence_after();
 #pragma unroll
         for (int c0 = 0; c0 < DHP; c0 += 16) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(t_row + 2 * TA_BN + c0, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
-          tmem_st_32x32b_x16(t_row + 2 * TA_BN + c0, v);
+          for (int i = 0; i < 16; ++i) o[c0 + i] = __uint_as_float(v[i]);
         }
-        tmem_st_wait();
-        if (need) {
-          l_run *= f;
-          m_ref = m_new;
-        }
+        if constexpr (ONES_COL) l_run = o[DH];
+        tc_fence_before();
+        mbar_arrive(bar(C::BAR_O_EMPTY + qi));                  // the next item's first PV may overwrite O now
+      } else {
+#pragma unroll
+        for (int i = 0; i < DHP; ++i) o[i] = 0.f;
       }
-      named_bar_sync(1 + qi, NSM);
-      if (row == 0) TRACE_EV(qi, j, 3);
-      const float msc = (m_ref == -INFINITY) ? 0.f : m_ref * sl2;
-      // probabilities -> bf16 P tile, written back into TMEM over the S buffer they came from (two keys per 32-bit
-      // column).  PV_{j-2}, the last reader of these columns, completed before S_j was produced: no wait needed, and
-      // the softmax of tile j+1 can start while PV_j is still running.
-      float rs = 0.f;
-#pragma unroll
-      for (int c = 0; c < TA_BN / 32; ++c) {         // 16 columns = 32 keys per store
-        float x[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = fmaf(val(cur, 32 * c + i), sl2, -msc);
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-#if MMD_EXP_MODE == 3   // timing experiment only: no exponential at all
-          const float p0 = x[2 * i], p1 = x[2 * i + 1];
-#else
-          const float p0 = exp_on_fma_pipe(i) ? exp2_poly(x[2 * i]) : exp2f(x[2 * i]);
-          const float p1 = exp_on_fma_pipe(i) ? exp2_poly(x[2 * i + 1]) : exp2f(x[2 * i + 1]);
-#endif
-          __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-          pk[i] = *reinterpret_cast<uint32_t*>(&h);
-          if constexpr (!ONES_COL) {
-            // row sum of the ROUNDED probabilities (numerator and denominator stay consistent under the stale base)
-            rs += __uint_as_float(pk[i] << 16) + __uint_as_float(pk[i] & 0xffff0000u);
-          }
-        }
-        tmem_st_32x32b_x16(t_row + sb * TA_BN + 16 * c, pk);
-      }
-      l_run += rs;
-      if (qi == 0 || j + 1 < n_tiles) named_bar_arrive(2 - qi, NSM);
-      if (row == 0) TRACE_EV(qi, j, 4);
-      tmem_st_wait();
-      if (row == 0) TRACE_EV(qi, j, 5);
-      tc_fence_before();
-      // one P_FULL barrier per S buffer: tile j+2's arrivals cannot start before the MMA thread has consumed tile j's
-      // (S_{j+2} is produced after PV_j), so a phase can never be skipped and no wait for PV_{j-1} is needed here
-      mbar_arrive(bar(BAR_P_FULL + qi * 2 + sb));
-      if (row == 0) TRACE_EV(qi, j, 6);
+      if (row == 0) TRACE_EV(6, qi + 2 * (it & 3), 3);
+      // Output goes through the group's own (now idle) part of this item's Q buffer so that global stores are whole rows
+      // per warp instruction instead of one 16-B piece from each of 32 rows; named barrier 3 + qi synchronises the group.
+      fe.store(qi, row, o, m_ref, l_run, smem_base + C::Q + (it % C::QBUF) * C::QBUF_BYTES + qi * 2 * TA_QREGION, 3 + qi);
+      mbar_arrive(bar(C::BAR_Q_EMPTY + it % C::QBUF));           // this thread is done with the staging area: once all 256
+                                                              // softmax threads are, the loaders may refill the Q buffer
+      if (row == 0) TRACE_EV(6, qi + 2 * (it & 3), 4);
+      g0 += n_tiles;
     }
-    if (row == 0) TRACE_EV(6, qi, 2);
-    float o[DHP];
-    if (n_tiles > 0) {
-      mbar_wait(bar(BAR_O_FULL + qi), (n_tiles - 1) & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < DHP; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(t_row + 2 * TA_BN + c0, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o[c0 + i] = __uint_as_float(v[i]);
-      }
-      if constexpr (ONES_COL) l_run = o[DH];
-    } else {
-#pragma unroll
-      for (int i = 0; i < DHP; ++i) o[i] = 0.f;
-    }
-    if (row == 0) TRACE_EV(6, qi, 3);
-    // Output goes through the group's own (now idle) Q region so that global stores are whole rows per warp
-    // instruction instead of one 16-B piece from each of 32 rows; named barrier 3 + qi synchronises the group.
-    fe.store(qi, row, o, m_ref, l_run, smem_base + AttnSmem::Q + qi * 2 * TA_QREGION, 3 + qi);
-    if (row == 0) TRACE_EV(6, qi, 4);
   }
 }
 
@@ -453,8 +501,9 @@ struct VitFront {
   int t, h, q0;
   const __nv_bfloat16 *gQ, *gK, *gV;
   int row_stride;
-  __device__ VitFront(const VitAttnParams& p_) : p(p_) {
-    q0 = blockIdx.x * TA_BM * TA_QT; h = blockIdx.y; t = blockIdx.z;
+  __device__ VitFront(const VitAttnParams& p_, int item) : p(p_) {
+    const int qblocks = (p.S + TA_BM * TA_QT - 1) / (TA_BM * TA_QT);   // item = (frame, head, query block), query block fastest
+    q0 = (item % qblocks) * TA_BM * TA_QT; h = (item / qblocks) % p.H; t = item / (qblocks * p.H);
     row_stride = 3 * p.H * DH;
     const __nv_bfloat16* base = p.qkv + (long long)t * p.S * row_stride;
     gQ = base + h * DH; gK = base + (p.H + h) * DH; gV = base + (2 * p.H + h) * DH;
@@ -510,12 +559,14 @@ struct PagedFront {
   const PagedAttnParams& p;
   int G, kvh, sp, q_start, n_q, kv_len, R, r_base, past, t_begin, t_end;
   const int* table;
-  __device__ PagedFront(const PagedAttnParams& p_) : p(p_) {
+  __device__ PagedFront(const PagedAttnParams& p_, int item) : p(p_) {
+    // item = (stream, split, query block x kv head), the last fastest
+    const int bx = item % p.grid_x;
     G = p.Hq / p.Hkv;
-    kvh = blockIdx.x % p.Hkv;
-    const int qt = blockIdx.x / p.Hkv;
-    sp = blockIdx.y;
-    const int st = blockIdx.z;
+    kvh = bx % p.Hkv;
+    const int qt = bx / p.Hkv;
+    sp = (item / p.grid_x) % p.n_splits;
+    const int st = item / (p.grid_x * p.n_splits);
     q_start = p.stream_desc[st * 4 + 0]; n_q = p.stream_desc[st * 4 + 1]; kv_len = p.stream_desc[st * 4 + 2];
     table = p.block_tables + p.stream_desc[st * 4 + 3];
     R = n_q * G;
@@ -581,32 +632,38 @@ struct PagedFront {
   }
 };
 
-template <int DH, typename Params, typename Front>
-__global__ void __launch_bounds__(TA_THREADS, 1) attn_tcgen05_kernel(const Params p) {
+template <int DH, typename Params, typename Front, typename C>
+__global__ void __launch_bounds__(TA_THREADS, 1) attn_tcgen05_kernel(const Params p, const int n_items) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bars = smem_base + AttnSmem::BARS;
-  const uint32_t tmem_slot = bars + 8u * BAR_COUNT;
+  const uint32_t bars = smem_base + C::BARS;
+  const uint32_t tmem_slot = bars + 8u * C::BAR_COUNT;
   const int warp = threadIdx.x >> 5;
   TRACE_INIT;
   griddep_launch_dependents();
   if (threadIdx.x == 0) TRACE_EV(6, 0, 0);
   if (threadIdx.x == 0) {
     constexpr uint32_t NLOAD = 32 * TA_LOADER_WARPS / 2;   // one 64-thread stream per ring
-    mbar_init(bars + 8u * BAR_Q_FULL, 32 * TA_LOADER_WARPS);
-    for (int s = 0; s < TA_KRING; ++s) {
-      mbar_init(bars + 8u * (BAR_K_FULL + s), NLOAD);
-      mbar_init(bars + 8u * (BAR_K_EMPTY + s), TA_QT);
+    for (int i = 0; i < C::QBUF; ++i) {
+      mbar_init(bars + 8u * (C::BAR_Q_FULL + i), 32 * TA_LOADER_WARPS);
+      mbar_init(bars + 8u * (C::BAR_Q_EMPTY + i), 32 * TA_SOFTMAX_WARPS);
     }
-    for (int s = 0; s < TA_VRING; ++s) {
-      mbar_init(bars + 8u * (BAR_V_FULL + s), NLOAD);
-      mbar_init(bars + 8u * (BAR_V_EMPTY + s), TA_QT);
+    for (int s = 0; s < C::RING; ++s) {
+      mbar_init(bars + 8u * (C::BAR_K_FULL + s), NLOAD);
+      mbar_init(bars + 8u * (C::BAR_K_EMPTY + s), TA_QT);
+    }
+    for (int s = 0; s < C::RING; ++s) {
+      mbar_init(bars + 8u * (C::BAR_V_FULL + s), NLOAD);
+      mbar_init(bars + 8u * (C::BAR_V_EMPTY + s), TA_QT);
     }
     for (int i = 0; i < 2 * TA_QT; ++i) {
-      mbar_init(bars + 8u * (BAR_S_FULL + i), 1);
-      mbar_init(bars + 8u * (BAR_P_FULL + i), 128);
+      mbar_init(bars + 8u * (C::BAR_S_FULL + i), 1);
+      mbar_init(bars + 8u * (C::BAR_P_FULL + i), 128);
     }
-    for (int i = 0; i < TA_QT; ++i) mbar_init(bars + 8u * (BAR_O_FULL + i), 1);
+    for (int i = 0; i < TA_QT; ++i) {
+      mbar_init(bars + 8u * (C::BAR_O_FULL + i), 1);
+      mbar_init(bars + 8u * (C::BAR_O_EMPTY + i), TA_BM);
+    }
     fence_mbar_init();
   }
   // Head-dim padding (72 -> 80): the loaders never write those chunks, so they are set once here: zero everywhere, and
@@ -615,18 +672,19 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attn_tcgen05_kernel(const Param
     static_assert(DH % 8 == 0 && ((DH + 15) / 16 * 16) - DH == 8, "one 16-B padding chunk");
     uint8_t* sm = smem_raw + (smem_base - smem_u32(smem_raw));
     constexpr int PC = DH / 8;                                           // index of the padding chunk
-    constexpr int ROWS = TA_QT * TA_BM + (TA_KRING + TA_VRING) * TA_BN;
+    constexpr int QROWS = C::QBUF * TA_QT * TA_BM;           // both Q buffers (tiles are contiguous: [buffer][qi])
+    constexpr int ROWS = QROWS + (C::RING + C::RING) * TA_BN;
     for (int i = threadIdx.x; i < ROWS; i += TA_THREADS) {
       uint32_t off;
       uint4 val = make_uint4(0, 0, 0, 0);
-      if (i < TA_QT * TA_BM) {
-        off = AttnSmem::Q + (i / TA_BM) * 2 * TA_QREGION + (PC >> 3) * TA_QREGION + sw128_off(i % TA_BM, PC & 7);
-      } else if (i < TA_QT * TA_BM + TA_KRING * TA_BN) {
-        const int k = i - TA_QT * TA_BM;
-        off = AttnSmem::K + (k / TA_BN) * 2 * TA_KREGION + (PC >> 3) * TA_KREGION + sw128_off(k % TA_BN, PC & 7);
+      if (i < QROWS) {
+        off = C::Q + (i / TA_BM) * 2 * TA_QREGION + (PC >> 3) * TA_QREGION + sw128_off(i % TA_BM, PC & 7);
+      } else if (i < QROWS + C::RING * TA_BN) {
+        const int k = i - QROWS;
+        off = C::K + (k / TA_BN) * 2 * TA_KREGION + (PC >> 3) * TA_KREGION + sw128_off(k % TA_BN, PC & 7);
       } else {
-        const int k = i - TA_QT * TA_BM - TA_KRING * TA_BN;
-        off = AttnSmem::V + (k / TA_BN) * 2 * TA_KREGION + (PC >> 3) * TA_KREGION + sw128_off(k % TA_BN, PC & 7);
+        const int k = i - QROWS - C::RING * TA_BN;
+        off = C::V + (k / TA_BN) * 2 * TA_KREGION + (PC >> 3) * TA_KREGION + sw128_off(k % TA_BN, PC & 7);
         val.x = 0x3f80u;                                                 // bf16 1.0 in element 0 of the chunk
       }
       *reinterpret_cast<uint4*>(sm + off) = val;
@@ -641,10 +699,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attn_tcgen05_kernel(const Param
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   griddep_wait();
   if (threadIdx.x == 0) TRACE_EV(6, 0, 1);
-  {
-    Front fe(p);
-    attention_pipeline<DH>(fe, smem_base, tmem_base);
-  }
+  attention_pipeline<DH, Front, C>(p, n_items, smem_base, tmem_base);
   tc_fence_before();
   __syncthreads();
   if (warp == TA_SOFTMAX_WARPS + TA_LOADER_WARPS) tmem_dealloc<512>(tmem_base);
@@ -659,40 +714,57 @@ extern "C" __attribute__((visibility("default"))) int mmd_debug_attn_trace(void*
 }
 #endif
 
+// persistent grid: one CTA per SM (the kernel needs all of an SM's TMEM and shared memory)
+static int attn_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <typename Kern, typename Params>
+static int launch_attn(Kern kern, bool* attr_done, int smem, const Params& p, int n_items, cudaStream_t s) {
+  if (!*attr_done) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -4;
+    *attr_done = true;
+  }
+  dim3 grid(min(n_items, attn_num_sms()));
+  if (launch_k(kern, grid, dim3(TA_THREADS), smem, s, p, n_items) != cudaSuccess) return -5;
+  return 0;
+}
+
+// more items than SMs -> persistent shape (double-buffered Q); otherwise every CTA has one item and deeper K/V rings pay more
+template <int DH, typename Params, typename Front>
+static int launch_attn_auto(const Params& p, int n_items, cudaStream_t s) {
+  static bool attr_p = false, attr_s = false;
+  if (n_items > attn_num_sms())
+    return launch_attn(attn_tcgen05_kernel<DH, Params, Front, AttnCfgPersistent>, &attr_p, AttnCfgPersistent::TOTAL, p, n_items, s);
+  return launch_attn(attn_tcgen05_kernel<DH, Params, Front, AttnCfgSingle>, &attr_s, AttnCfgSingle::TOTAL, p, n_items, s);
+}
+
 int launch_vit_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int T, int S, int H, int dh, int split_hi_lo, cudaStream_t s) {
   if (T <= 0) return 0;
   if (dh != 72) return -2;
-  auto kern = attn_tcgen05_kernel<72, VitAttnParams, VitFront<72>>;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL) != cudaSuccess) return -4;
-    attr = true;
-  }
   VitAttnParams p;
   p.qkv = qkv; p.out = out; p.S = S; p.H = H; p.split_hi_lo = split_hi_lo;
   p.scale_log2e = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
-  dim3 grid((S + TA_BM * TA_QT - 1) / (TA_BM * TA_QT), H, T);
-  if (launch_k(kern, grid, dim3(TA_THREADS), AttnSmem::TOTAL, s, p) != cudaSuccess) return -5;
-  return 0;
+  const int n_items = ((S + TA_BM * TA_QT - 1) / (TA_BM * TA_QT)) * H * T;
+  return launch_attn_auto<72, VitAttnParams, VitFront<72>>(p, n_items, s);
 }
 
 int launch_kv_attention_tc_main(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, const int* stream_desc, const int* block_tables,
                                 int n_streams, int max_n_q, int total_q, float* o_part, float* ml_part, int Hq, int Hkv, int n_splits,
                                 cudaStream_t s) {
-  auto kern = attn_tcgen05_kernel<128, PagedAttnParams, PagedFront>;
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL) != cudaSuccess) return -4;
-    attr = true;
-  }
   PagedAttnParams p;
   p.q = q; p.kv_layer = kv_layer; p.stream_desc = stream_desc; p.block_tables = block_tables; p.o_part = o_part; p.ml_part = ml_part;
   p.Hq = Hq; p.Hkv = Hkv; p.n_splits = n_splits; p.part_stride_rows = (long long)total_q * Hq;
   p.scale_log2e = (1.0f / sqrtf(128.f)) * 1.4426950408889634f;
   const int G = Hq / Hkv;
-  dim3 grid(((max_n_q * G + TA_BM * TA_QT - 1) / (TA_BM * TA_QT)) * Hkv, n_splits, n_streams);
-  if (launch_k(kern, grid, dim3(TA_THREADS), AttnSmem::TOTAL, s, p) != cudaSuccess) return -5;
-  return 0;
+  p.grid_x = ((max_n_q * G + TA_BM * TA_QT - 1) / (TA_BM * TA_QT)) * Hkv;
+  return launch_attn_auto<128, PagedAttnParams, PagedFront>(p, p.grid_x * n_splits * n_streams, s);
 }
 
 int kv_attention_tc_q_rows_per_cta() { return TA_BM * TA_QT; }

@@ -244,19 +244,25 @@ __global__ void kv_attention_combine_kernel(const float* __restrict__ o_part, co
                                             __nv_bfloat16* __restrict__ out, int n_splits, long long part_stride_rows) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  // one warp per (token, head) row: lane l owns dims 4l..4l+3 (one 16-B load per split, one 8-B store)
+  // one warp per (token, head) row: lane l owns dims 4l..4l+3 (one 16-B load per split, one 8-B store).  The (m, l)
+  // pairs of the <= 32 splits are read by one lane each and combined with shuffles, so the weights are known before
+  // the O loads are issued and those can all be in flight together.
   const long long grow = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (grow >= part_stride_rows) return;
   const int lane = threadIdx.x & 31;
-  float mmax = -INFINITY;
-  for (int s = 0; s < n_splits; ++s) mmax = fmaxf(mmax, __ldg(ml_part + ((long long)s * part_stride_rows + grow) * 2));
+  float2 ml = make_float2(-INFINITY, 0.f);
+  if (lane < n_splits) ml = __ldg(reinterpret_cast<const float2*>(ml_part + ((long long)lane * part_stride_rows + grow) * 2));
+  float mmax = ml.x;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mmax = fmaxf(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
+  const float w_mine = (ml.x == -INFINITY) ? 0.f : exp2f(ml.x - mmax);
+  float lsum = w_mine * ml.y;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  float lsum = 0.f;
+#pragma unroll 4
   for (int s = 0; s < n_splits; ++s) {
-    const float2 ml = __ldg(reinterpret_cast<const float2*>(ml_part + ((long long)s * part_stride_rows + grow) * 2));
-    if (ml.x == -INFINITY) continue;
-    const float w = exp2f(ml.x - mmax);
-    lsum += w * ml.y;
+    const float w = __shfl_sync(0xffffffffu, w_mine, s);
     const float4 o = __ldg(reinterpret_cast<const float4*>(o_part + ((long long)s * part_stride_rows + grow) * KA_DH) + lane);
     acc.x += w * o.x; acc.y += w * o.y; acc.z += w * o.z; acc.w += w * o.w;
   }
@@ -304,7 +310,7 @@ int kv_attention_pick_splits(int max_rows, int Hkv, int n_streams, int max_kv_le
   for (int sp = 1; sp <= max_by_work; ++sp) {
     const int waves = (base * sp + slots - 1) / slots;
     const int per = (kv_tiles + sp - 1) / sp;
-    const double cost = waves * (per + fixed) + 0.25 * sp;   // + the combine kernel reading sp partial planes
+    const double cost = waves * (per + fixed) + 0.1 * sp;    // + the combine kernel reading sp partial planes
     if (cost < best - 1e-9) { best = cost; splits = sp; }
   }
   return splits;
@@ -314,7 +320,7 @@ int launch_kv_attention(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, c
                         int n_streams, int max_n_q, int total_q, int max_kv_len, float* o_part, float* ml_part, __nv_bfloat16* out,
                         int Hq, int Hkv, int dh, int page_tokens, int n_splits, cudaStream_t s) {
   if (n_streams <= 0 || total_q <= 0) return 0;
-  if (dh != KA_DH || page_tokens != KA_BN || Hq % Hkv != 0) return -2;
+  if (dh != KA_DH || page_tokens != KA_BN || Hq % Hkv != 0 || n_splits < 1 || n_splits > 32) return -2;   // combine: one lane per split
   constexpr int SMEM = (KA_BM + 4 * KA_BN) * KA_LDS * 2;
   static bool attr = false;
   if (!attr) {
