@@ -37,7 +37,7 @@ for _ in range(2):
     lib.mmd_vit_attention(qkv.data_ptr(), out.data_ptr(), T, S, H, dh, 1, s)
 torch.cuda.synchronize(); buf.zero_()
 lib.mmd_vit_attention(qkv.data_ptr(), out.data_ptr(), T, S, H, dh, 1, s)
-res.append(dump("vit T=32", 12))
+res.append(dump("vit T=32", 28))
 
 Hq, Hkv, dh, PAGE = 28, 4, 128, 64
 n_q, L = 392, 6000
@@ -55,6 +55,6 @@ for _ in range(2):
     _lib.check(call())
 torch.cuda.synchronize(); buf.zero_()
 _lib.check(call())
-res.append(dump(f"kv n_q={n_q} L={L} splits={ns}", 24))
+res.append(dump(f"kv n_q={n_q} L={L} splits={ns}", 40))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(res, open("gpurun_out/trace_attn.json", "w"))
