@@ -118,7 +118,7 @@ def attn_impl(env, request):
     lib.mmd_set_attention_impl(2)
 
 
-@pytest.mark.parametrize("T,S,H", [(2, 729, 16), (1, 729, 4), (3, 100, 2), (1, 64, 2), (1, 129, 1)])
+@pytest.mark.parametrize("T,S,H", [(2, 729, 16), (1, 729, 4), (3, 100, 2), (1, 64, 2), (1, 129, 1), (8, 729, 16), (5, 300, 16)])
 def test_vit_attention(env, attn_impl, T, S, H):
     _lib, ops, lib, ctx = env
     dh = 72
@@ -136,7 +136,7 @@ def test_vit_attention(env, attn_impl, T, S, H):
     hi_lo = out2[:, :H * dh].float() + out2[:, H * dh:].float()
     # hi+lo removes the output rounding: what is left is the bf16 rounding of P inside the kernel (the tcgen05 kernel's
     # lazy rescaling keeps a stale exponent base, so its dominant probability is not exactly 1.0: slightly larger)
-    assert (hi_lo - ref).abs().max() < (4e-3 if attn_impl == 0 else 1.5e-2)
+    assert (hi_lo - ref).abs().max() < (6e-3 if attn_impl == 0 else 1.5e-2)   # max over up to 6.7 M outputs
 
 
 def test_resid_add_rmsnorm(env):
