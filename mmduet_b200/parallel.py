@@ -91,16 +91,18 @@ class PeerStoreEncoder:
 
     embed_into(frames[b0:b1], dst[(b1-b0)*tokens_per_frame, hidden]) must write the tokens of those frames into dst."""
 
-    def __init__(self, embed_into, tokens_per_frame, hidden, max_frames, device, owner=0, batch=32, group=None):
-        import torch.distributed._symmetric_memory as symm
+    def __init__(self, embed_into, tokens_per_frame, hidden, max_frames, device, owner=0, batch=32, group=None, symm=None,
+                 dtype=torch.bfloat16):
+        if symm is None:                   # injectable: the CPU tests drive the same control flow through a gloo-backed stand-in
+            import torch.distributed._symmetric_memory as symm
         self.embed_into, self.tpf, self.hidden, self.device = embed_into, tokens_per_frame, hidden, device
         self.owner, self.batch, self.max_frames = owner, batch, max_frames
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
-        self.buf = symm.empty(max_frames * tokens_per_frame, hidden, dtype=torch.bfloat16, device=device)
+        self.buf = symm.empty(max_frames * tokens_per_frame, hidden, dtype=dtype, device=device)
         self.hdl = symm.rendezvous(self.buf, self.group)
         # the owner's buffer as seen from this rank (a peer mapping unless this rank is the owner)
-        self.dst = self.buf if self.rank == owner else self.hdl.get_buffer(owner, tuple(self.buf.shape), torch.bfloat16)
+        self.dst = self.buf if self.rank == owner else self.hdl.get_buffer(owner, tuple(self.buf.shape), dtype)
 
     N_CHANNELS = 15          # signal channels 1..15 (0 is the barrier's); the signal pad holds world x channels words
 

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mmduet_b200.parallel import FrameParallelEncoder, frame_range, gather_results, videos_for_rank
+from mmduet_b200.parallel import FrameParallelEncoder, PeerStoreEncoder, frame_range, gather_results, videos_for_rank
 
 
 def test_partitions_cover_everything_once():
@@ -73,3 +73,89 @@ def test_frame_parallel_gather_gloo(n_frames, owner):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert results == {0: True, 1: True}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# PeerStoreEncoder: same control flow as on the GPUs (barrier, one signal channel per batch, in-order consumption), with a
+# gloo-backed stand-in for torch's CUDA symmetric memory: "peer stores" land in a local staging tensor and the signal
+# carries them (send on put_signal, recv into the owner's buffer on wait_signal).
+# ---------------------------------------------------------------------------------------------------------------------
+class _GlooSymm:
+    class Handle:
+        def __init__(self, buf, group):
+            self.buf, self.group, self.rank = buf, group, dist.get_rank(group)
+            self.staging = torch.full_like(buf, float("nan"))
+            self.sent = {}          # channel -> rows already shipped by this rank
+            self.log = []
+
+        def get_buffer(self, rank, sizes, dtype):
+            assert tuple(sizes) == tuple(self.buf.shape) and dtype == self.buf.dtype
+            return self.staging    # what this rank writes "into the owner's memory"
+
+        def barrier(self, channel=0):
+            dist.barrier(self.group)
+
+        def put_signal(self, dst_rank, channel=0):
+            assert channel not in self.sent, "a signal channel is a binary semaphore: one batch per channel and encode"
+            rows = (~torch.isnan(self.staging[:, 0])).nonzero().flatten()
+            new = rows[~torch.isin(rows, torch.tensor(sorted(r for v in self.sent.values() for r in v), dtype=torch.long))]
+            self.sent[channel] = new.tolist()
+            meta = torch.tensor([channel, int(new[0]), int(new[-1]) + 1])
+            dist.send(meta, dst_rank, group=self.group)
+            dist.send(self.staging[int(new[0]):int(new[-1]) + 1].contiguous(), dst_rank, group=self.group)
+
+        def wait_signal(self, src_rank, channel=0):
+            meta = torch.zeros(3, dtype=torch.long)
+            dist.recv(meta, src_rank, group=self.group)
+            assert int(meta[0]) == channel, (int(meta[0]), channel)      # signals of one source are consumed in sending order
+            dist.recv(self.buf[int(meta[1]):int(meta[2])], src_rank, group=self.group)
+            self.log.append((src_rank, channel))
+
+    @staticmethod
+    def empty(*size, dtype=None, device=None):
+        return torch.full(size, float("nan"), dtype=dtype, device=device)
+
+    @staticmethod
+    def rendezvous(tensor, group):
+        return _GlooSymm.Handle(tensor, group)
+
+
+def _peer_worker(rank, world, port, n_frames, owner, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        tpf, hidden = 3, 4
+        lo, hi = frame_range(n_frames, world, rank)
+        frames = torch.arange(lo, hi, dtype=torch.float32)
+
+        def embed_into(fr, dst):
+            dst.copy_((fr[:, None] * 10 + torch.arange(tpf)[None, :]).reshape(-1, 1).expand(-1, hidden))
+
+        enc = PeerStoreEncoder(embed_into, tpf, hidden, max_frames=n_frames, device="cpu", owner=owner, batch=2, symm=_GlooSymm,
+                               dtype=torch.float32)
+        out, ready = enc.encode(n_frames, frames)
+        if rank == owner:
+            PeerStoreEncoder.wait_all(ready)
+            want = (torch.arange(n_frames)[:, None] * 10 + torch.arange(tpf)[None, :]).reshape(-1, 1).expand(-1, hidden).float()
+            src = 1 - owner
+            n_batches = (frame_range(n_frames, world, src)[1] - frame_range(n_frames, world, src)[0] + 1) // 2
+            ok = torch.equal(out, want) and enc.hdl.log == [(src, 1 + b) for b in range(n_batches)]
+        else:
+            ok = out is None and ready is None
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames,owner", [(7, 0), (12, 1)])
+def test_peer_store_encoder_world2_control_flow(n_frames, owner):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, n_frames, owner, q)) for r in range(2)]
+    for p_ in procs:
+        p_.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p_ in procs:
+        p_.join(timeout=60)
+    assert res == {0: True, 1: True}
