@@ -525,16 +525,22 @@ __global__ void argmax_kernel(const float* __restrict__ partial, int n_planes, l
                               float* __restrict__ out_logit) {
   __shared__ float bv[32];
   __shared__ int bi[32];
+  extern __shared__ uint32_t penal_bits[];   // one bit per vocabulary entry (only when n_penal > 0)
+  if (n_penal > 0) {
+    for (int w = threadIdx.x; w < (V + 31) / 32; w += blockDim.x) penal_bits[w] = 0u;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n_penal; j += blockDim.x) {
+      const long long id = penal_ids[j];
+      if (id >= 0 && id < V) atomicOr(&penal_bits[id >> 5], 1u << (id & 31));
+    }
+    __syncthreads();
+  }
   float best = -INFINITY;
   int besti = 0x7fffffff;
   for (int c = threadIdx.x; c < V; c += blockDim.x) {
     float v = 0.f;
     for (int p = 0; p < n_planes; ++p) v += __ldg(partial + p * plane_stride + c);
-    if (n_penal > 0) {
-      for (int j = 0; j < n_penal; ++j) {
-        if (penal_ids[j] == c) { v = v < 0.f ? v * penalty : v / penalty; break; }
-      }
-    }
+    if (n_penal > 0 && ((penal_bits[c >> 5] >> (c & 31)) & 1u)) v = v < 0.f ? v * penalty : v / penalty;
     if (v > best || (v == best && c < besti)) { best = v; besti = c; }
   }
 #pragma unroll
@@ -563,7 +569,9 @@ __global__ void argmax_kernel(const float* __restrict__ partial, int n_planes, l
 }
 int launch_argmax(const float* partial, int n_planes, long long plane_stride, int V, const long long* penal_ids, int n_penal,
                   float penalty, long long* out_id, float* out_logit, cudaStream_t s) {
-  argmax_kernel<<<1, 1024, 0, s>>>(partial, n_planes, plane_stride, V, penal_ids, n_penal, penalty, out_id, out_logit);
+  const size_t smem = n_penal > 0 ? (size_t)((V + 31) / 32) * sizeof(uint32_t) : 0;
+  if (smem > 48 * 1024) return -2;            // vocabulary above 393k entries: not this model family
+  argmax_kernel<<<1, 1024, smem, s>>>(partial, n_planes, plane_stride, V, penal_ids, n_penal, penalty, out_id, out_logit);
   return 0;
 }
 

@@ -197,21 +197,25 @@ def fast_greedy_generate(*, model, inputs_embeds, past_key_values, eos_token_id,
     view = past_key_values
     x = inputs_embeds[0] if inputs_embeds.dim() == 3 else inputs_embeds
     new_id = torch.zeros(1, dtype=torch.long, device=model.device)
+    # penalised ids live on the device and grow by one device-to-device copy per token (no per-token H2D upload)
+    n_pen, pen_buf = 0, None
+    if repetition_penalty is not None:
+        n_pen = len(generated_token_ids)
+        pen_buf = torch.zeros(n_pen + inplace_output_ids.size(1) + 1, dtype=torch.long, device=model.device)
+        if n_pen:
+            pen_buf[:n_pen] = torch.tensor(generated_token_ids, dtype=torch.long, device=model.device)
     i = 0
     for i in range(inplace_output_ids.size(1)):
         out = dec.step([dict(storage=view.storage, past=view.length, embeds=x)], score="none", lm="last")
         view = out["views"][0]
-        pen = None
-        n_pen = 0
-        if repetition_penalty is not None and len(generated_token_ids) > 0:
-            pen = torch.tensor(generated_token_ids, dtype=torch.long, device=model.device)
-            n_pen = pen.numel()
-        rc = lib.mmd_argmax(out["lm_logits"].data_ptr(), model.vocab_size, _lib.ptr(pen), n_pen,
+        rc = lib.mmd_argmax(out["lm_logits"].data_ptr(), model.vocab_size, _lib.ptr(pen_buf) if n_pen else 0, n_pen,
                             float(repetition_penalty or 1.0), new_id.data_ptr(), _lib.stream_ptr())
         _lib.check(rc, "mmd_argmax")
         tok = int(new_id.item())
         if repetition_penalty is not None and tok != eos_token_id:
             generated_token_ids.append(tok)
+            pen_buf[n_pen:n_pen + 1].copy_(new_id)
+            n_pen += 1
         inplace_output_ids[:, i] = tok
         if tok == eos_token_id:
             break
