@@ -286,10 +286,16 @@ int mmd_argmax(const float* logits, int64_t V, const int64_t* penal_ids, int n_p
 // ---------------------------------------------------------------------------------------------------------------
 // SigLIP tower
 // ---------------------------------------------------------------------------------------------------------------
-struct VitBufs { __nv_bfloat16 *x, *qkv, *h; };
+// Below this many token rows (one frame = 729) the residual-updating GEMMs (out_proj, fc2: N = 1152, i.e. 36 output tiles
+// with a serial K loop of up to 4304) run swap-AB + split-K over all SMs instead; their fp32 partial planes, bias and
+// the residual add are folded, in a fixed order, into the LayerNorm that follows.
+constexpr int kVitSmallRows = 1024;
+constexpr int kVitMaxSplits = 8;
+struct VitBufs { __nv_bfloat16 *x, *qkv, *h; float* planes; };
 static int64_t vit_carve(const mmd_vit_weights* w, int T, Bump& b, VitBufs* o) {
   const int G = w->image_size / w->patch_size;
   const int64_t M = (int64_t)T * G * G;
+  o->planes = M < kVitSmallRows ? b.take<float>((int64_t)kVitMaxSplits * M * w->dim) : nullptr;
   int wide = w->mlp > w->k_pad ? w->mlp : w->k_pad;
   if (wide < 2 * w->dim) wide = 2 * w->dim;
   o->x = b.take<__nv_bfloat16>(M * w->dim);
@@ -325,21 +331,43 @@ int mmd_vit_forward(mmd_ctx* c, const mmd_vit_weights* w, const void* pixels, in
   PRUNK(mmd::launch_im2col(pixels, px_dtype, normalize, buf.h, T, 3, w->image_size, w->patch_size, w->k_pad, s), "im2col");
   PRUNK(mmd::launch_broadcast_rows(w->pos_emb, resid_out, M, Sg, D, s), "pos_emb");
   PRUN(gemm_normal(c, buf.h, M, w->patch_w, D, w->k_pad, w->k_pad, mmd::EPI_RESID_F32, 0, w->patch_b, resid_out, D, s), "patch_embed");
+  const bool small = M < kVitSmallRows;
+  // pending split-K result of the previous residual GEMM, consumed by the next LayerNorm (small-batch path only)
+  const float* pend_bias = nullptr;
+  int pend_planes = 0;
+  auto resid_gemm = [&](const void* act, const void* wt, const float* bias, int K, const char* tag) -> int {
+    if (!small) return gemm_normal(c, act, M, wt, D, K, K, mmd::EPI_RESID_F32, 0, bias, resid_out, D, s);
+    int splits = choose_splits(c->num_sms, D, K, M);
+    if (splits > kVitMaxSplits) splits = kVitMaxSplits;
+    int eff = 1;
+    const int rc = gemm_T_partials(c, act, M, wt, D, K, splits, buf.planes, s, &eff);
+    pend_bias = bias;
+    pend_planes = eff;
+    (void)tag;
+    return rc;
+  };
+  auto layernorm = [&](const float* g, const float* be, void* out) -> int {
+    const int rc = mmd::launch_resid_add_layernorm(resid_out, buf.planes, pend_planes, (int64_t)M * D, pend_bias, g, be, out, 0, M, D, eps, s);
+    pend_planes = 0;
+    pend_bias = nullptr;
+    return rc;
+  };
   for (int l = 0; l < w->n_layers; ++l) {
     const mmd_vit_layer& L = w->layers[l];
-    PRUNK(mmd::launch_layernorm(resid_out, L.ln1_w, L.ln1_b, buf.x, 0, M, D, eps, s), "ln1");
+    PRUNK(layernorm(L.ln1_w, L.ln1_b, buf.x), "ln1");
     PRUN(gemm_normal(c, buf.x, M, L.qkv_w, 3 * D, D, D, mmd::EPI_BF16, mmd::ACT_NONE, L.qkv_b, buf.qkv, 3 * D, s), "qkv");
     if (w->attn_out_split) {  // out_w is [dim, 2*dim] = [W | W]; the attention output is [hi | lo]
       PRUNK(mmd::launch_vit_attention(buf.qkv, buf.h, T, Sg, w->heads, D / w->heads, 1, s), "vit_attention");
-      PRUN(gemm_normal(c, buf.h, M, L.out_w, D, 2 * D, 2 * D, mmd::EPI_RESID_F32, 0, L.out_b, resid_out, D, s), "out_proj");
+      PRUN(resid_gemm(buf.h, L.out_w, L.out_b, 2 * D, "out_proj"), "out_proj");
     } else {
       PRUNK(mmd::launch_vit_attention(buf.qkv, buf.x, T, Sg, w->heads, D / w->heads, 0, s), "vit_attention");
-      PRUN(gemm_normal(c, buf.x, M, L.out_w, D, D, D, mmd::EPI_RESID_F32, 0, L.out_b, resid_out, D, s), "out_proj");
+      PRUN(resid_gemm(buf.x, L.out_w, L.out_b, D, "out_proj"), "out_proj");
     }
-    PRUNK(mmd::launch_layernorm(resid_out, L.ln2_w, L.ln2_b, buf.x, 0, M, D, eps, s), "ln2");
+    PRUNK(layernorm(L.ln2_w, L.ln2_b, buf.x), "ln2");
     PRUN(gemm_normal(c, buf.x, M, L.fc1_w, w->mlp, D, D, mmd::EPI_BF16, mmd::ACT_GELU_TANH, L.fc1_b, buf.h, w->mlp, s), "fc1");
-    PRUN(gemm_normal(c, buf.h, M, L.fc2_w, D, w->mlp, w->mlp, mmd::EPI_RESID_F32, 0, L.fc2_b, resid_out, D, s), "fc2");
+    PRUN(resid_gemm(buf.h, L.fc2_w, L.fc2_b, w->mlp, "fc2"), "fc2");
   }
+  if (pend_planes > 0) PRUNK(layernorm(nullptr, nullptr, nullptr), "ln1");   // the last fc2: residual update only
   return check_launch("mmd_vit_forward");
 }
 

@@ -181,15 +181,19 @@ int launch_broadcast_rows(const float* src, float* dst, long long rows, int S, i
 // LayerNorm: fp32 residual row -> bf16 GEMM operand (or fp32).  One warp per row, row cached in registers.
 // Restates nn.LayerNorm(eps=1e-6) of SiglipEncoderLayer (TF:models/siglip/modeling_siglip.py:333-362).
 // ------------------------------------------------------------------------------------------------------------
-template <int MAXV, bool OUT_F32>
-__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                 void* __restrict__ out, long long rows, int D, float eps) {
+template <int MAXV, bool OUT_F32, bool PLANES>
+__global__ void layernorm_kernel(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 void* __restrict__ out, long long rows, int D, float eps, const float* __restrict__ planes,
+                                 int n_planes, long long plane_stride, const float* __restrict__ add_bias) {
+  // Optional prologue (small-batch ViT): x[row] += add_bias + sum_s planes[s][row] — the deterministic reduction of the
+  // previous split-K GEMM (out_proj / fc2) and its residual add — written back before normalising.  gamma == nullptr:
+  // only that update.
   const int warps_per_block = blockDim.x >> 5;
   const long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int D4 = D >> 2;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  float4* xr = reinterpret_cast<float4*>(x + row * D);
   float4 v[MAXV];
   float sum = 0.f;
 #pragma unroll
@@ -197,9 +201,22 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
     const int c = lane + j * 32;
     if (c < D4) {
       v[j] = xr[c];
+      if constexpr (PLANES) {
+        if (add_bias != nullptr) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(add_bias) + c);
+          v[j].x += b.x; v[j].y += b.y; v[j].z += b.z; v[j].w += b.w;
+        }
+#pragma unroll 4
+        for (int p = 0; p < n_planes; ++p) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(planes + p * plane_stride + row * D) + c);
+          v[j].x += a.x; v[j].y += a.y; v[j].z += a.z; v[j].w += a.w;
+        }
+        xr[c] = v[j];
+      }
       sum += v[j].x + v[j].y + v[j].z + v[j].w;
     }
   }
+  if (gamma == nullptr) return;
   const float mean = warp_sum(sum) / D;
   float var = 0.f;
 #pragma unroll
@@ -230,13 +247,70 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
     }
   }
 }
+// Small-batch variant (a few hundred rows): one BLOCK per row, one float4 per thread, so the 1 + n_planes loads of a thread
+// are all in flight at once and a 729-row frame still spreads over every SM.
+template <int NT>
+__global__ void resid_add_layernorm_block_kernel(float* __restrict__ x, const float* __restrict__ planes, int n_planes,
+                                                 long long plane_stride, const float* __restrict__ add_bias,
+                                                 const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                 __nv_bfloat16* __restrict__ out, int D, float eps) {
+  __shared__ float red[NT / 32];
+  const long long row = blockIdx.x;
+  const int c = threadIdx.x, D4 = D >> 2;
+  const bool act = c < D4;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (act) {
+    v = reinterpret_cast<float4*>(x + row * D)[c];
+    if (add_bias != nullptr) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(add_bias) + c);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+    }
+#pragma unroll 8
+    for (int p = 0; p < n_planes; ++p) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(planes + p * plane_stride + row * D) + c);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    reinterpret_cast<float4*>(x + row * D)[c] = v;
+  }
+  if (gamma == nullptr) return;
+  const float mean = block_sum<NT>(act ? v.x + v.y + v.z + v.w : 0.f, red) / D;
+  const float a0 = v.x - mean, a1 = v.y - mean, a2 = v.z - mean, a3 = v.w - mean;
+  const float rstd = rsqrtf(block_sum<NT>(act ? a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3 : 0.f, red) / D + eps);
+  if (act) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+    uint2 o;
+    o.x = pack2(a0 * rstd * g.x + b.x, a1 * rstd * g.y + b.y);
+    o.y = pack2(a2 * rstd * g.z + b.z, a3 * rstd * g.w + b.w);
+    reinterpret_cast<uint2*>(out + row * D)[c] = o;
+  }
+}
+
 int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_f32, long long rows, int D,
                      float eps, cudaStream_t s) {
+  return launch_resid_add_layernorm(const_cast<float*>(x), nullptr, 0, 0, nullptr, gamma, beta, out, out_f32, rows, D, eps, s);
+}
+int launch_resid_add_layernorm(float* x, const float* planes, int n_planes, long long plane_stride, const float* add_bias,
+                               const float* gamma, const float* beta, void* out, int out_f32, long long rows, int D, float eps,
+                               cudaStream_t s) {
   if (D % 4 != 0 || D > 12 * 128) return -2;
+  if (rows <= 0) return 0;
   const int wpb = 8;
   const unsigned blocks = (unsigned)((rows + wpb - 1) / wpb);
-  if (out_f32) layernorm_kernel<12, true><<<blocks, wpb * 32, 0, s>>>(x, gamma, beta, out, rows, D, eps);
-  else layernorm_kernel<12, false><<<blocks, wpb * 32, 0, s>>>(x, gamma, beta, out, rows, D, eps);
+  if (n_planes > 0) {   // small-batch ViT path: bf16 output (or none) only
+    if (out_f32) return -2;
+    if (D <= 4 * 384)
+      resid_add_layernorm_block_kernel<384><<<(unsigned)rows, 384, 0, s>>>(x, planes, n_planes, plane_stride, add_bias, gamma, beta,
+                                                                           static_cast<__nv_bfloat16*>(out), D, eps);
+    else
+      layernorm_kernel<12, false, true><<<blocks, wpb * 32, 0, s>>>(x, gamma, beta, out, rows, D, eps, planes, n_planes, plane_stride, add_bias);
+  } else if (gamma == nullptr) {
+    return 0;           // nothing to add, nothing to normalise
+  } else if (out_f32) {
+    layernorm_kernel<12, true, false><<<blocks, wpb * 32, 0, s>>>(x, gamma, beta, out, rows, D, eps, nullptr, 0, 0, nullptr);
+  } else {
+    layernorm_kernel<12, false, false><<<blocks, wpb * 32, 0, s>>>(x, gamma, beta, out, rows, D, eps, nullptr, 0, 0, nullptr);
+  }
   return 0;
 }
 

@@ -14,6 +14,10 @@ int launch_im2col(const void* px, int px_dtype, int normalize, __nv_bfloat16* A,
 int launch_broadcast_rows(const float* src, float* dst, long long rows, int S, int D, cudaStream_t s);
 int launch_layernorm(const float* x, const float* gamma, const float* beta, void* out, int out_f32, long long rows, int D,
                      float eps, cudaStream_t s);
+// x[row] += add_bias + sum_s planes[s][row]  (written back), then LayerNorm -> out; gamma == nullptr: only the update
+int launch_resid_add_layernorm(float* x, const float* planes, int n_planes, long long plane_stride, const float* add_bias,
+                               const float* gamma, const float* beta, void* out, int out_f32, long long rows, int D, float eps,
+                               cudaStream_t s);
 int launch_resid_add_rmsnorm(float* resid, const float* partial, int n_planes, long long plane_stride, const float* w,
                              __nv_bfloat16* out_bf16, float* out_f32, long long rows, int H, float eps, cudaStream_t s);
 int launch_qkv_finish(const float* partial, int n_planes, long long plane_stride, const float* bias, const float* cos_tab,
