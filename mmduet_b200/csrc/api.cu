@@ -332,6 +332,10 @@ int mmd_vit_forward(mmd_ctx* c, const mmd_vit_weights* w, const void* pixels, in
   PRUNK(mmd::launch_broadcast_rows(w->pos_emb, resid_out, M, Sg, D, s), "pos_emb");
   PRUN(gemm_normal(c, buf.h, M, w->patch_w, D, w->k_pad, w->k_pad, mmd::EPI_RESID_F32, 0, w->patch_b, resid_out, D, s), "patch_embed");
   const bool small = M < kVitSmallRows;
+  // Live mode is a chain of ~190 kernels of 5-20 us: programmatic dependent launch overlaps each kernel's set-up with its
+  // predecessor's tail.  Every kernel of the small-batch chain waits (griddepcontrol.wait) before touching global memory;
+  // the CTA-pair GEMM of the batched path has no such prologue, so PDL stays off there.
+  struct VitPdlGuard { VitPdlGuard(bool on) { mmd::g_use_pdl = on; } ~VitPdlGuard() { mmd::g_use_pdl = false; } } pdl_guard(c->use_pdl && small);
   // pending split-K result of the previous residual GEMM, consumed by the next LayerNorm (small-batch path only)
   const float* pend_bias = nullptr;
   int pend_planes = 0;

@@ -188,6 +188,7 @@ __global__ void layernorm_kernel(float* __restrict__ x, const float* __restrict_
   // Optional prologue (small-batch ViT): x[row] += add_bias + sum_s planes[s][row] — the deterministic reduction of the
   // previous split-K GEMM (out_proj / fc2) and its residual add — written back before normalising.  gamma == nullptr:
   // only that update.
+  pdl_prologue();
   const int warps_per_block = blockDim.x >> 5;
   const long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -255,6 +256,7 @@ __global__ void resid_add_layernorm_block_kernel(float* __restrict__ x, const fl
                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
                                                  __nv_bfloat16* __restrict__ out, int D, float eps) {
   __shared__ float red[NT / 32];
+  pdl_prologue();
   const long long row = blockIdx.x;
   const int c = threadIdx.x, D4 = D >> 2;
   const bool act = c < D4;
@@ -300,16 +302,19 @@ int launch_resid_add_layernorm(float* x, const float* planes, int n_planes, long
   if (n_planes > 0) {   // small-batch ViT path: bf16 output (or none) only
     if (out_f32) return -2;
     if (D <= 4 * 384)
-      resid_add_layernorm_block_kernel<384><<<(unsigned)rows, 384, 0, s>>>(x, planes, n_planes, plane_stride, add_bias, gamma, beta,
-                                                                           static_cast<__nv_bfloat16*>(out), D, eps);
+      launch_k(resid_add_layernorm_block_kernel<384>, dim3((unsigned)rows), dim3(384), 0, s, x, planes, n_planes, plane_stride, add_bias,
+               gamma, beta, static_cast<__nv_bfloat16*>(out), D, eps);
     else
-      layernorm_kernel<12, false, true><<<blocks, wpb * 32, 0, s>>>(x, gamma, beta, out, rows, D, eps, planes, n_planes, plane_stride, add_bias);
+      launch_k(layernorm_kernel<12, false, true>, dim3(blocks), dim3(wpb * 32), 0, s, x, gamma, beta, out, rows, D, eps, planes, n_planes,
+               plane_stride, add_bias);
   } else if (gamma == nullptr) {
     return 0;           // nothing to add, nothing to normalise
   } else if (out_f32) {
-    layernorm_kernel<12, true, false><<<blocks, wpb * 32, 0, s>>>(x, gamma, beta, out, rows, D, eps, nullptr, 0, 0, nullptr);
+    launch_k(layernorm_kernel<12, true, false>, dim3(blocks), dim3(wpb * 32), 0, s, x, gamma, beta, out, rows, D, eps,
+             (const float*)nullptr, 0, 0ll, (const float*)nullptr);
   } else {
-    layernorm_kernel<12, false, false><<<blocks, wpb * 32, 0, s>>>(x, gamma, beta, out, rows, D, eps, nullptr, 0, 0, nullptr);
+    launch_k(layernorm_kernel<12, false, false>, dim3(blocks), dim3(wpb * 32), 0, s, x, gamma, beta, out, rows, D, eps,
+             (const float*)nullptr, 0, 0ll, (const float*)nullptr);
   }
   return 0;
 }
