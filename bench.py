@@ -389,7 +389,7 @@ def run_gpu_arm(args):
         per_launch_s = dom_ms / dom_n / 1e3
         nbytes, nflops = work
         t_hbm, t_tc = nbytes / (pk["hbm_gbs"] * 1e9), nflops / (pk["bf16_tflops_sustained"] * 1e12)
-        common = {"kernel": dominant, "traffic": ncu_traffic(dominant), "launches_timed": dom_n, "avg_launch_us": per_launch_s * 1e6,
+        common = {"kernel": dominant, "traffic": ncu_traffic(dominant, max(args.chunk, 1)), "launches_timed": dom_n, "avg_launch_us": per_launch_s * 1e6,
                   "algorithmic_bytes_per_launch": nbytes, "algorithmic_flops_per_launch": nflops,
                   "share_of_stream": round(stage[dominant][0] / sum(v[0] for v in stage.values()), 3)}
         if t_hbm >= t_tc:
@@ -460,11 +460,12 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
-def ncu_traffic(tag):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json), else null."""
+def ncu_traffic(tag, chunk):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/ncu_traffic.json): captured at
+    40 frames per pass (M=1960, the default) and at one frame per pass (M=49); null for any other pass size."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get(tag)
+    if os.path.exists(p) and chunk in (1, 40):
+        return json.load(open(p)).get(tag if chunk == 40 else tag + "_M49")
     return None
 
 

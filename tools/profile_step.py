@@ -1,6 +1,6 @@
 """Small, fixed kernel sequence for ncu (launch list / --set full captures).  Never a source of bench numbers.
   python tools/profile_step.py step        one 32-frame encode + two 10-frame decoder passes at ~3k context (full-size model)
-  python tools/profile_step.py gate_up     the dominant weight-streaming GEMM alone (M=392 and M=49), 4 launches each
+  python tools/profile_step.py gate_up     the dominant weight-streaming GEMM alone (M=1960 = 40 frames per pass, and M=49), 4 launches each
   python tools/profile_step.py vit         one ViT layer's kernels at batch 32"""
 import os
 import sys
@@ -20,7 +20,7 @@ if mode == "gate_up":
     H, I = 3584, 18944
     wg = [(torch.randn(I, H, device=dev) * 0.02).bfloat16() for _ in range(3)]
     wu = [(torch.randn(I, H, device=dev) * 0.02).bfloat16() for _ in range(3)]
-    for M in (392, 49):
+    for M in (1960, 49):
         x = (torch.randn(M, H, device=dev) * 0.5).bfloat16()
         out = torch.empty(M, I, device=dev, dtype=torch.bfloat16)
         for i in range(4):
