@@ -65,6 +65,8 @@ MMD_API int mmd_set_gemm_2cta(int on);
 #define MMD_EPI_T_SWIGLU 3  /* out_bf16[m][n] = silu(acc_gate) * acc_up            */
 #define MMD_EPI_F32 4       /* out_f32 = acc + bias[n]                             */
 #define MMD_EPI_SWIGLU_PAIR 6 /* interleaved gate/up weight rows: out_bf16[m,j] = silu(acc[2j]) * acc[2j+1] (CTA-pair kernel) */
+#define MMD_EPI_T_SWIGLU_IL 7 /* swap-AB, X rows interleaved (2j = gate_j, 2j+1 = up_j): out_bf16[m][j] = silu(acc[2j]) * acc[2j+1];
+                                out is [M, x_rows / 2]; one accumulator, 256-token tiles (decoder gate/up above 128 tokens) */
 #define MMD_EPI_BF16_HILO 5 /* v = act(acc + bias[n]); out[m,n] = bf16(v), out[m,N+n] = bf16(v - bf16(v)) */
 #define MMD_ACT_NONE 0
 #define MMD_ACT_GELU_TANH 1

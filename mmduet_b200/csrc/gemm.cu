@@ -326,6 +326,35 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             }
           }
         }
+      } else if constexpr (EPI == EPI_T_SWIGLU_IL) {
+        // lane = interleaved weight row: even lanes hold gate_j, odd lanes up_j (j = xi / 2).  Each pair exchanges its
+        // values by shuffle, computes silu(gate) * up, then pairs of pairs pack two outputs: lanes with (lane & 3) == 0
+        // store 4 bytes, i.e. a warp writes 32 contiguous bytes (16 output features) per token.
+        const bool n_ok = xi < p.x_rows;            // x_rows is even, so a pair is in or out together
+        const bool odd = (lane_row & 1) != 0;
+        const bool writer = (lane_row & 3) == 0;
+        __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll 1
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+          if (y0 + c0 >= p.y_rows) break;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_row + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float mine = __uint_as_float(v[j]);
+            const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+            const float gv = odd ? other : mine, uv = odd ? mine : other;
+            const float r = gv / (1.0f + __expf(-gv)) * uv;
+            const float r2 = __shfl_xor_sync(0xffffffffu, r, 2);        // the next pair's result
+            const int tok = y0 + c0 + j;
+            if (writer && n_ok && tok < p.y_rows) {
+              __nv_bfloat162 o = __floats2bfloat162_rn(r, r2);
+              if (xi + 2 < p.x_rows) *reinterpret_cast<__nv_bfloat162*>(outp + (long long)tok * p.ldo + (xi >> 1)) = o;
+              else outp[(long long)tok * p.ldo + (xi >> 1)] = o.x;   // last pair of an odd pair count
+            }
+          }
+        }
       } else if constexpr (EPI == EPI_T_SWIGLU) {
         const bool n_ok = xi < p.x_rows;
         __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
@@ -835,7 +864,7 @@ static int launch_cfg(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
   const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
   if (grid <= 0) return 0;
   p.x_blocked = a.x_blocked;
-  p.pdl_prefetch_x = (g_use_pdl && (EPI == EPI_T_F32 || EPI == EPI_T_SWIGLU)) ? 1 : 0;
+  p.pdl_prefetch_x = (g_use_pdl && (EPI == EPI_T_F32 || EPI == EPI_T_SWIGLU || EPI == EPI_T_SWIGLU_IL)) ? 1 : 0;
   cudaError_t e = launch_k(kern, dim3(grid), dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, tmX, tmX2, tmY, p);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { g_gemm_err = std::string("gemm launch: ") + cudaGetErrorString(e); return -5; }
@@ -936,6 +965,9 @@ int gemm_launch(GemmContext* c, const GemmArgs& a, cudaStream_t s) {
       if (a.y_rows <= 64) return launch_cfg<64, false, EPI_T_F32, ACT_NONE>(c, a, s);
       if (a.y_rows <= 128) return launch_cfg<128, false, EPI_T_F32, ACT_NONE>(c, a, s);
       return launch_cfg<256, false, EPI_T_F32, ACT_NONE>(c, a, s);
+    case EPI_T_SWIGLU_IL:
+      if (a.x_rows % 4 != 0 || a.ldo % 2 != 0) { g_gemm_err = "interleaved swiglu gemm needs x_rows % 4 == 0 and an even ldo"; return -2; }
+      return launch_cfg<256, false, EPI_T_SWIGLU_IL, ACT_NONE>(c, a, s);
     case EPI_T_SWIGLU:
       if (a.X2 == nullptr) { g_gemm_err = "swiglu gemm needs X2"; return -2; }
       if (a.y_rows <= 64) return launch_cfg<64, true, EPI_T_SWIGLU, ACT_NONE>(c, a, s);

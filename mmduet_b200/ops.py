@@ -2,7 +2,8 @@
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_T_F32, EPI_T_SWIGLU)
+from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_T_F32, EPI_T_SWIGLU,
+                   EPI_T_SWIGLU_IL)
 
 
 def _chk2d(t, dtype):
@@ -53,6 +54,21 @@ def gemm_t_partials(x, w, k_splits, out=None, blocked_shape=None):
                            x.data_ptr(), M, x.stride(0), K, 0, out.data_ptr(), out.stride(1), k_splits, out.stride(0),
                            _lib.stream_ptr())
     _lib.check(rc, "mmd_gemm_bf16(T_F32)")
+    return out
+
+
+def gemm_t_swiglu_interleaved(x, w_il, out=None):
+    """Swap-AB fused SwiGLU on ONE interleaved weight matrix (row 2j = gate_j, row 2j+1 = up_j): out[M, N] with N = rows/2."""
+    _chk2d(x, torch.bfloat16)
+    _chk2d(w_il, torch.bfloat16)
+    M, K = x.shape
+    N = w_il.shape[0] // 2
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=torch.bfloat16)
+    lib = _lib.load()
+    rc = lib.mmd_gemm_bf16(_lib.context(x.device.index), EPI_T_SWIGLU_IL, ACT_NONE, w_il.data_ptr(), 0, 2 * N, w_il.stride(0),
+                           x.data_ptr(), M, x.stride(0), K, 0, out.data_ptr(), out.stride(0), 1, 0, _lib.stream_ptr())
+    _lib.check(rc, "mmd_gemm_bf16(T_SWIGLU_IL)")
     return out
 
 

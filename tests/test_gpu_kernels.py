@@ -75,6 +75,21 @@ def test_gemm_swiglu(env, M, N, K):
     assert ((out.float() - ref).abs() / (1 + ref.abs())).max() < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K", [(490, 18944, 3584), (200, 1216, 896), (1960, 2432, 512), (130, 6, 256)])
+def test_gemm_swiglu_interleaved(env, M, N, K):
+    """One interleaved operand (row 2j = gate_j, 2j+1 = up_j), single accumulator, 256-token tiles."""
+    _lib, ops, lib, ctx = env
+    torch.manual_seed(3)
+    x = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+    wg, wu = (torch.randn(N, K, device="cuda") * 0.05).bfloat16(), (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    w_il = torch.stack([wg, wu], 1).reshape(2 * N, K).contiguous()
+    out = ops.gemm_t_swiglu_interleaved(x, w_il)
+    g, u = x.float() @ wg.float().T, x.float() @ wu.float().T
+    ref = torch.nn.functional.silu(g) * u
+    assert (out.float() - ref).abs().max() <= 2e-2 * max(1.0, ref.abs().max().item())
+    assert torch.equal(out, ops.gemm_t_swiglu(x, wg, wu)) or (out.float() - ops.gemm_t_swiglu(x, wg, wu).float()).abs().max() < 1e-2
+
+
 @pytest.mark.parametrize("dtype,normalize", [(torch.uint8, True), (torch.float32, False), (torch.bfloat16, False), (torch.float32, True)])
 def test_im2col(env, dtype, normalize):
     _lib, ops, lib, ctx = env
