@@ -465,13 +465,15 @@ __device__ __forceinline__ void attention_pipeline(const Params& prm, int n_item
       if (n_tiles > 0) {
         mbar_wait(bar(C::BAR_O_FULL + qi), (g0 + n_tiles - 1) & 1);
         tc_fence_after();
+        {   // all loads in flight, one wait
+          uint32_t v[DHP / 16][16];
 #pragma unroll
-        for (int c0 = 0; c0 < DHP; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(t_row + 2 * TA_BN + c0, v);
+          for (int c = 0; c < DHP / 16; ++c) tmem_ld_32x32b_x16(t_row + 2 * TA_BN + 16 * c, v[c]);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[c0 + i] = __uint_as_float(v[i]);
+          for (int c = 0; c < DHP / 16; ++c)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[16 * c + i] = __uint_as_float(v[c][i]);
         }
         if constexpr (ONES_COL) l_run = o[DH];
         tc_fence_before();
