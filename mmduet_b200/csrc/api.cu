@@ -516,10 +516,10 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
       if (big) {   // interleaved (gate, up) columns, SwiGLU on adjacent accumulator columns
         a.X = buf.x; a.x_rows = M; a.ldx = H; a.Y = gu; a.y_rows = 2 * I; a.ldy = H; a.K = H;
         a.epi = mmd::EPI_SWIGLU_PAIR; a.out = buf.h; a.ldo = I; a.force_2cta = 1;
-      } else if (M > 128 && I % 2 == 0) {
+      } else if (M > 1024 && I % 2 == 0) {   // (at 490 tokens the two-accumulator form is still 7 % faster: 4 re-reads only)
         // swap-AB on the interleaved matrix as ONE operand: a single accumulator per 128 weight rows (64 gate/up pairs on
-        // adjacent TMEM lanes) leaves room for 256-token tiles, so each weight tile is re-read from L2 half as often as
-        // with two accumulators (ncu: that form moved 6.5 GB L2->SM per launch at 1960 tokens, 17 TB/s)
+        // adjacent TMEM lanes) leaves room for 256-token tiles, i.e. UMMA N = 256 instead of 2 x 128 (ncu at 1960 tokens:
+        // tensor pipe 87.8 % active vs 80.6 % with two accumulators; L2->SM traffic is the same 6.5 GB either way)
         a.X = gu; a.x_rows = 2 * I; a.ldx = H; a.Y = buf.x; a.y_rows = M; a.ldy = H; a.K = H;
         a.epi = mmd::EPI_T_SWIGLU_IL; a.out = buf.h; a.ldo = I;
       } else {     // swap-AB: gate rows and up rows of the interleaved matrix as two strided operands

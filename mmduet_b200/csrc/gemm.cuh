@@ -19,7 +19,7 @@ enum GemmEpi : int {
   EPI_F32 = 4,       // out_f32[m, n] = acc + bias[n]
   EPI_SWIGLU_PAIR = 6, // normal orientation, weights interleaved (row 2j = gate_j, row 2j+1 = up_j): out_bf16[m, j] = silu(acc[2j]) * acc[2j+1]
   EPI_T_SWIGLU_IL = 7, // swap-AB, ONE operand with interleaved rows (2j = gate_j, 2j+1 = up_j): out_bf16[m, j] = silu(acc[2j]) * acc[2j+1];
-                       // single accumulator, 256-token tiles (half the L2 re-reads of the dual-accumulator form); out is [M, x_rows/2]
+                       // single accumulator, 256-token tiles (UMMA N = 256 instead of 2 x 128); out is [M, x_rows/2]
   EPI_BF16_HILO = 5, // v = act(acc + bias[n]); out_bf16[m, n] = hi = bf16(v); out_bf16[m, N + n] = bf16(v - hi)  (ldo >= 2N)
 };
 enum GemmAct : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2 };

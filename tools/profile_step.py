@@ -20,11 +20,15 @@ if mode == "gate_up":
     H, I = 3584, 18944
     wg = [(torch.randn(I, H, device=dev) * 0.02).bfloat16() for _ in range(3)]
     wu = [(torch.randn(I, H, device=dev) * 0.02).bfloat16() for _ in range(3)]
+    wil = [torch.stack([g, u], 1).reshape(2 * I, H).contiguous() for g, u in zip(wg, wu)]   # row 2j = gate_j, 2j+1 = up_j
     for M in (1960, 49):
         x = (torch.randn(M, H, device=dev) * 0.5).bfloat16()
         out = torch.empty(M, I, device=dev, dtype=torch.bfloat16)
         for i in range(4):
-            ops.gemm_t_swiglu(x, wg[i % 3], wu[i % 3], out=out)
+            if M > 128:   # what the decoder step launches above 128 tokens: one interleaved operand, 256-token tiles
+                ops.gemm_t_swiglu_interleaved(x, wil[i % 3], out=out)
+            else:
+                ops.gemm_t_swiglu(x, wg[i % 3], wu[i % 3], out=out)
     torch.cuda.synchronize()
     sys.exit(0)
 
