@@ -488,6 +488,10 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
   // (measured: 8/10/24-frame passes, profiles/r01_decoder_paths.md); the normal-orientation CTA-pair path (UMMA M = 256,
   // TMA-store epilogue, interleaved gate/up + pairwise SwiGLU) only pays off for much larger multi-stream batches.
   const bool big = M >= 2048;
+  // q/k/v, o and down (plain fp32 outputs) already win in the normal-orientation CTA-pair kernel from 1024 tokens
+  // (measured at 1960 tokens: -5 %, -5 %, -10 %: no split-K planes, whole waves of 256x256 tiles); gate/up keeps the
+  // swap-AB SwiGLU epilogue up to 2048.
+  const bool pair_qkv = M >= 1024, pair_o = M >= 1024, pair_down = M >= 1024;
   auto gemm_big_f32 = [&](const void* act, const void* wt, int N, int K, int splits, int* eff) -> int {
     mmd::GemmArgs a;
     a.X = static_cast<const __nv_bfloat16*>(act); a.x_rows = M; a.ldx = K;
@@ -499,14 +503,14 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
   for (int l = 0; l < w->n_layers; ++l) {
     const mmd_dec_layer& L = w->layers[l];
     int eff = 1;
-    if (big) PRUN(gemm_big_f32(buf.x, L.qkv_w, NQKV, H, 1, &eff), "qkv_proj");
+    if (pair_qkv) PRUN(gemm_big_f32(buf.x, L.qkv_w, NQKV, H, 1, &eff), "qkv_proj");
     else PRUN(gemm_T_partials(c, buf.x, M, L.qkv_w, NQKV, H, s_qkv, buf.planes, s, &eff), "qkv_proj");
     __nv_bfloat16* kv_layer = static_cast<__nv_bfloat16*>(pool->pool) + (int64_t)l * pool->layer_stride;
     PRUNK(mmd::launch_qkv_finish(buf.planes, eff, (int64_t)M * NQKV, L.qkv_b, w->rope_cos, w->rope_sin, st->tok_pos, st->tok_slot,
                                 buf.q, kv_layer, M, Hq, Hkv, dh, MMD_PAGE_TOKENS, s), "qkv_finish");
     PRUNK2(mmd::launch_kv_attention(buf.q, kv_layer, st->stream_desc, st->block_tables, st->n_streams, st->max_n_q, M, st->max_kv_len, buf.o_part,
                                   buf.ml_part, buf.attn, Hq, Hkv, dh, MMD_PAGE_TOKENS, attn_splits, s), "kv_attention");
-    if (big) PRUN(gemm_big_f32(buf.attn, L.o_w, H, QD, 1, &eff), "o_proj");
+    if (pair_o) PRUN(gemm_big_f32(buf.attn, L.o_w, H, QD, 1, &eff), "o_proj");
     else PRUN(gemm_T_partials(c, buf.attn, M, L.o_w, H, QD, s_o, buf.planes, s, &eff), "o_proj");
     PRUNK(mmd::launch_resid_add_rmsnorm(buf.resid, buf.planes, eff, (int64_t)M * H, L.ln2_w, buf.x, nullptr, M, H, w->rms_eps, s),
          "post_attention_layernorm");
@@ -528,7 +532,7 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
       }
       PRUN(mmd::gemm_launch(c->gemm, a, s), "gate_up_swiglu");
     }
-    if (big) PRUN(gemm_big_f32(buf.h, L.down_w, H, I, 3, &eff), "down_proj");
+    if (pair_down) PRUN(gemm_big_f32(buf.h, L.down_w, H, I, 3, &eff), "down_proj");
     else PRUN(gemm_T_partials(c, buf.h, M, L.down_w, H, I, s_down, buf.planes, s, &eff), "down_proj");
     const bool last = (l + 1 == w->n_layers);
     const float* next_w = last ? w->final_norm_w : w->layers[l + 1].ln1_w;
