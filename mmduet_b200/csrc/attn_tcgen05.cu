@@ -100,8 +100,13 @@ __device__ __forceinline__ constexpr bool exp_on_fma_pipe(int i) {
 
 // warpgroup register reallocation: the kernel starts with 128 registers per thread (512 threads); the loader warpgroup
 // and the MMA warpgroup hand most of theirs to the two softmax warpgroups (64 scores + 64..128 outputs per thread).
+#ifdef MMD_NO_SETMAXNREG   // diagnostic builds only (the softmax warps then spill)
+template <int N> __device__ __forceinline__ void reg_dec() {}
+template <int N> __device__ __forceinline__ void reg_inc() {}
+#else
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+#endif
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
