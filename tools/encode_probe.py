@@ -10,6 +10,11 @@ arch = A.SMALL
 w = R.make_weights(arch, seed=91)
 cfg = ModelConfig.from_any(arch)
 vis = VisionEngine(cfg, w, torch.device("cuda:0"))
+from mmduet_b200 import _lib
+if os.environ.get("ATTN_IMPL"):
+    _lib.load().mmd_set_attention_impl(int(os.environ["ATTN_IMPL"]))
+if os.environ.get("GEMM_2CTA"):
+    _lib.load().mmd_set_gemm_2cta(int(os.environ["GEMM_2CTA"]))
 frames = R.synthetic_frames(14, seed=5).cuda()
 print("vit heads", cfg.vit_heads, "dim", cfg.vit_dim, "layers", cfg.vit_layers_total)
 r1 = vis.tower(frames, True).clone(); e1 = vis.visual_embed(frames, normalize=True).clone()
