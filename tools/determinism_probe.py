@@ -44,3 +44,17 @@ def ln():
     _lib.check(lib.mmd_layernorm(xf.data_ptr(), g.data_ptr(), b.data_ptr(), o2.data_ptr(), 0, M, 288, 1e-6, s()))
     return o2
 check("layernorm", ln)
+
+# the chain that showed the memcheck-only mismatch: CTA-pair GEMM (TMA store) -> tcgen05 attention -> CTA-pair GEMM (reduce-add)
+D = 288
+xin = (torch.randn(M, D, device="cuda") * 0.5).bfloat16()
+wqkv = (torch.randn(3 * D, D, device="cuda") * 0.06).bfloat16(); wo = (torch.randn(D, 2 * D, device="cuda") * 0.05).bfloat16()
+qkv2 = torch.empty(M, 3 * D, device="cuda", dtype=torch.bfloat16)
+att2 = torch.empty(M, 2 * D, device="cuda", dtype=torch.bfloat16)
+def chain():
+    ops.gemm(xin, wqkv, out=qkv2)
+    _lib.check(lib.mmd_vit_attention(qkv2.data_ptr(), att2.data_ptr(), T, S, H, dh, 1, s()))
+    r = res0.clone()
+    ops.gemm(att2, wo, out=r, epi=EPI_RESID_F32)
+    return r
+check("chain qkv-gemm -> attention -> out_proj", chain)
