@@ -105,6 +105,19 @@ __device__ __forceinline__ constexpr bool exp_on_fma_pipe(int i) {
   return MMD_EXP_MODE == 2 ? true : (MMD_EXP_MODE == 0 ? false : ((i & 7) == 1 || (i & 7) == 4 || (i & 7) == 6));
 }
 
+// Diagnostic builds (-DMMD_ATTN_JITTER): pseudo-random sleeps in every role, to shake the hand-over protocol's timing.
+#ifdef MMD_ATTN_JITTER
+__device__ __forceinline__ void jitter(uint32_t salt) {
+  uint32_t c;
+  asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
+  c = (c ^ salt ^ (blockIdx.x * 2654435761u)) * 2246822519u;
+  if ((c >> 28) < 5) __nanosleep(200 + ((c >> 8) & 4095));
+}
+#define JITTER(salt) do { if ((MMD_ATTN_JITTER) & ((salt) >> 12)) jitter(salt); } while (0)   // 1 loaders, 2 MMA issuers, 4 softmax (salt's top nibble)
+#else
+#define JITTER(salt)
+#endif
+
 // warpgroup register reallocation: the kernel starts with 128 registers per thread (512 threads); the loader warpgroup
 // and the MMA warpgroup hand most of theirs to the two softmax warpgroups (64 scores + 64..128 outputs per thread).
 #ifdef MMD_NO_SETMAXNREG   // diagnostic builds only (the softmax warps then spill)
@@ -168,8 +181,13 @@ struct AttnCfg {
                        BAR_V_EMPTY = BAR_V_FULL + RING;
   static constexpr int BAR_S_FULL = BAR_V_EMPTY + RING;         // [qi][2]
   static constexpr int BAR_P_FULL = BAR_S_FULL + 2 * TA_QT;     // [qi][2]
-  static constexpr int BAR_O_FULL = BAR_P_FULL + 2 * TA_QT;     // [qi]
-  static constexpr int BAR_O_EMPTY = BAR_O_FULL + TA_QT;        // [qi]: the softmax group has read the finished O out of TMEM
+  // [qi][2], PV_g commits to [g & 1].  The softmax waits on O_FULL only when it rescales and at the end of an item, i.e. NOT
+  // for every phase, and a parity wait is only meaningful if the waiter knows the barrier's phase to within one.  With one
+  // barrier per parity of g that holds: when PV_k is awaited, PV_{k-2} (the previous phase of the same barrier) is known to
+  // be complete (S_{k+1} or S_k has been seen, and it is produced after PV_{k-2}) and PV_{k+2} cannot have been issued.
+  // (A single barrier was a latent race: a slow MMA thread could be two phases behind and the wait passed at once.)
+  static constexpr int BAR_O_FULL = BAR_P_FULL + 2 * TA_QT;
+  static constexpr int BAR_O_EMPTY = BAR_O_FULL + 2 * TA_QT;    // [qi]: the softmax group has read the finished O out of TMEM
   static constexpr int BAR_COUNT = BAR_O_EMPTY + TA_QT;
   static_assert(8 * BAR_COUNT + 8 <= 512, "barrier area");
   static_assert(TOTAL <= 232448, "shared memory per CTA");
@@ -251,6 +269,7 @@ __device__ __forceinline__ void attention_pipeline(const Params& prm, int n_item
       for (int j = 0; j < n_tiles; ++j, ++g) {
         const int st = g % ring;
         if (lrow == 0) TRACE_EV(4 + is_v, g, 0);
+        JITTER(0x1000u | (g & 0xfff));
         mbar_wait(bar(bar_empty + st), ((g / ring) & 1) ^ 1);
         if (lrow == 0) TRACE_EV(4 + is_v, g, 1);
         const uint32_t dstb = ring_base + st * 2 * TA_KREGION;
@@ -319,6 +338,7 @@ __device__ __forceinline__ void attention_pipeline(const Params& prm, int n_item
         for (int j = 0; j < 2 && j < n_tiles; ++j) issue_qk(j);
         for (int j = 0; j < n_tiles; ++j) {
           const int g = g0 + j, st = g % C::RING;
+          JITTER(0x2000u | (g & 0xfff));
           TRACE_EV(2 + qi, g, 0);
           mbar_wait(bar(C::BAR_V_FULL + st), (g / C::RING) & 1);   // usually long complete: take its latency before P arrives
           TRACE_EV(2 + qi, g, 1);
@@ -336,7 +356,7 @@ __device__ __forceinline__ void attention_pipeline(const Params& prm, int n_item
 #pragma unroll
           for (int k = 0; k < TA_BN / 16; ++k)
             umma_f16_ts(tmem_base + qi * TA_TMEM_PER_Q + 2 * TA_BN, tP + 8 * k, desc(va + k * (2048 >> 4)), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-          umma_commit(bar(C::BAR_O_FULL + qi));
+          umma_commit(bar(C::BAR_O_FULL + qi * 2 + (g & 1)));
           umma_commit(bar(C::BAR_V_EMPTY + st));
           TRACE_EV(2 + qi, g, 3);
           if (j + 2 < n_tiles) issue_qk(j + 2);
@@ -374,6 +394,7 @@ __device__ __forceinline__ void attention_pipeline(const Params& prm, int n_item
       for (int j = 0; j < n_tiles; ++j) {
         const int g = g0 + j, sb = g & 1;
         if (row == 0) TRACE_EV(qi, g, 0);
+        JITTER(0x4000u | ((g + (warp << 6)) & 0xfff));
         mbar_wait(bar(C::BAR_S_FULL + qi * 2 + sb), (g >> 1) & 1);     // S_g: wait, then read the row into registers
         tc_fence_after();
         tmem_ld_32x32b_x32(t_row + sb * TA_BN, cur.a);
@@ -411,9 +432,8 @@ __device__ __forceinline__ void attention_pipeline(const Params& prm, int n_item
           m_ref = m_new;
         } else if (__any_sync(0xffffffffu, need)) {
           // lazy rescaling: O (TMEM) and l move to the new exponent base.  tcgen05.ld/st are .sync.aligned, so the whole
-          // warp takes this path together; rows that do not need it rescale by 1.  PV_{g-1} must have completed first
-          // (it is the newest PV that can have been issued, so the barrier is at most one phase ahead of this parity).
-          mbar_wait(bar(C::BAR_O_FULL + qi), (g - 1) & 1);
+          // warp takes this path together; rows that do not need it rescale by 1.  PV_{g-1} must have completed first.
+          mbar_wait(bar(C::BAR_O_FULL + qi * 2 + ((g - 1) & 1)), ((g - 1) >> 1) & 1);
           tc_fence_after();
           const float f = !need ? 1.f : ((m_ref == -INFINITY) ? 0.f : exp2f((m_ref - m_new) * sl2));
 #pragma unroll
@@ -475,7 +495,7 @@ __device__ __forceinline__ void attention_pipeline(const Params& prm, int n_item
       if (row == 0) TRACE_EV(6, qi + 2 * (it & 3), 2);
       float o[DHP];
       if (n_tiles > 0) {
-        mbar_wait(bar(C::BAR_O_FULL + qi), (g0 + n_tiles - 1) & 1);
+        mbar_wait(bar(C::BAR_O_FULL + qi * 2 + ((g0 + n_tiles - 1) & 1)), ((g0 + n_tiles - 1) >> 1) & 1);
         tc_fence_after();
         {   // all loads in flight, one wait
           uint32_t v[DHP / 16][16];
@@ -674,10 +694,8 @@ __global__ void __launch_bounds__(TA_THREADS, 1) attn_tcgen05_kernel(const Param
       mbar_init(bars + 8u * (C::BAR_S_FULL + i), 1);
       mbar_init(bars + 8u * (C::BAR_P_FULL + i), 128);
     }
-    for (int i = 0; i < TA_QT; ++i) {
-      mbar_init(bars + 8u * (C::BAR_O_FULL + i), 1);
-      mbar_init(bars + 8u * (C::BAR_O_EMPTY + i), TA_BM);
-    }
+    for (int i = 0; i < 2 * TA_QT; ++i) mbar_init(bars + 8u * (C::BAR_O_FULL + i), 1);
+    for (int i = 0; i < TA_QT; ++i) mbar_init(bars + 8u * (C::BAR_O_EMPTY + i), TA_BM);
     fence_mbar_init();
   }
   // Head-dim padding (72 -> 80): the loaders never write those chunks, so they are set once here: zero everywhere, and
