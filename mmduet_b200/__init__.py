@@ -7,7 +7,7 @@ from .config import ModelConfig  # noqa: F401
 
 
 def build_model_and_tokenizer(is_training=False, *, state_dict=None, model_config=None, device="cuda", tokenizer=None,
-                              max_context=None, **kwargs):
+                              max_context=None, kv_pages=None, **kwargs):
     """models/__init__.py:8-13.  Checkpoints cannot be downloaded offline, so the weights come from `state_dict` (keys as
     in the reference's checkpoint: model.vision_tower..., model.mm_projector..., model.layers..., lm_head,
     informative_head, relevance_head; LoRA deltas must be merged by the caller: W + alpha/r * B @ A)."""
@@ -21,6 +21,6 @@ def build_model_and_tokenizer(is_training=False, *, state_dict=None, model_confi
     cfg = model_config or ModelConfig()
     if tokenizer is None:
         tokenizer = SyntheticTokenizer(cfg.vocab)
-    model = VideoHeadLiveLlavaQwenForCausalLM(cfg, state_dict, device=device, max_context=max_context,
+    model = VideoHeadLiveLlavaQwenForCausalLM(cfg, state_dict, device=device, max_context=max_context, kv_pages=kv_pages,
                                               eos_token_id=getattr(tokenizer, "eos_token_id", None))
     return model, tokenizer

@@ -316,6 +316,11 @@ class DecoderEngine:
     # ---- pages ----
     def _alloc_page(self):
         if not self._free:
+            # streams are released by KVStorage.__del__; objects caught in reference cycles only die at the next
+            # collection, so run one before giving up
+            import gc
+            gc.collect()
+        if not self._free:
             raise _lib.MmdError(f"KV pool exhausted ({self.n_pages} pages of {PAGE} tokens)")
         return self._free.pop()
 

@@ -20,7 +20,9 @@ def setup():
     from mmduet_b200.config import ModelConfig
     arch = A.SMALL
     w = R.make_weights(arch, seed=91)
-    model, tok = build_model_and_tokenizer(state_dict=w, model_config=ModelConfig.from_any(arch), device="cuda:0", max_context=4096)
+    # a roomy KV pool: the LiveInfer objects of earlier tests give their pages back only when they are collected
+    model, tok = build_model_and_tokenizer(state_dict=w, model_config=ModelConfig.from_any(arch), device="cuda:0", max_context=4096,
+                                           kv_pages=1024)
     frames = R.synthetic_frames(14, seed=5)
     return arch, w, model, tok, frames
 
