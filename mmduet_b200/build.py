@@ -50,5 +50,24 @@ def build(force=False, verbose=False):
     return LIB
 
 
+JITTER_LIB = os.path.join(HERE, "libmmduet_b200_jitter.so")
+
+
+def build_jitter(force=False):
+    """Diagnostic twin of the library: the attention kernel compiled with -DMMD_ATTN_JITTER=7 (pseudo-random sleeps in the
+    loader, MMA-issuer and softmax roles), every other object shared with the product build.  Only the GPU test
+    tests/test_gpu_kernels.py::test_attention_under_timing_jitter loads it (through MMD_LIB_PATH, in a subprocess)."""
+    build(force=False)
+    src = os.path.join(CSRC, "attn_tcgen05.cu")
+    if not force and os.path.exists(JITTER_LIB) and os.path.getmtime(JITTER_LIB) >= max(os.path.getmtime(LIB), os.path.getmtime(src)):
+        return JITTER_LIB
+    objdir = os.path.join(HERE, "build")
+    jobj = os.path.join(objdir, "attn_tcgen05_jitter.o")
+    subprocess.check_call([NVCC] + FLAGS + ["-DMMD_ATTN_JITTER=7", "-c", src, "-o", jobj])
+    objs = [os.path.join(objdir, os.path.basename(x)[:-3] + ".o") for x in sources() if not x.endswith("attn_tcgen05.cu")] + [jobj]
+    subprocess.check_call([NVCC, "-shared", "-o", JITTER_LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return JITTER_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

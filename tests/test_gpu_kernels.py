@@ -330,3 +330,21 @@ def test_frame_ingest_feeds_the_encoder(env):
     assert (out[:, :, :84] == 0).all() and (out[:, :, 300:] == 0).all()      # 480x270 -> 384x216, 84 rows of padding
     with pytest.raises(Exception):
         ingest_frames(torch.zeros(1, 1, 5000, 3, dtype=torch.uint8, device="cuda"))   # resized side would be 0
+
+
+def test_attention_under_timing_jitter(env):
+    """The tcgen05 attention kernel's hand-over protocol must not depend on timing: the diagnostic twin of the library
+    (attention compiled with -DMMD_ATTN_JITTER=7: pseudo-random sleeps in the loader, MMA-issuer and softmax roles; built by
+    __graft_entry__.build()) has to pass the same attention tests.  This build found the one real race of round 1."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    jlib = os.path.join(root, "mmduet_b200", "libmmduet_b200_jitter.so")
+    if not os.path.exists(jlib):
+        pytest.skip("jitter twin not built (python -c 'from mmduet_b200 import build; build.build_jitter()')")
+    if os.environ.get("MMD_LIB_PATH"):
+        pytest.skip("already running on an alternative library")
+    envv = dict(os.environ, MMD_LIB_PATH=jlib)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_kernels.py"), "-q", "-m", "gpu", "-x",
+                        "-k", "(test_vit_attention or test_qkv_finish_and_kv_attention) and tcgen05"], env=envv, cwd=root,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
