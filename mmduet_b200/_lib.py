@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("MMD_LIB_PATH") or os.path.join(_HERE, "libmmduet_b200
 c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 
 EPI_BF16, EPI_RESID_F32, EPI_T_F32, EPI_T_SWIGLU, EPI_F32, EPI_BF16_HILO = 0, 1, 2, 3, 4, 5
-EPI_T_SWIGLU_IL = 7
+EPI_SWIGLU_PAIR, EPI_T_SWIGLU_IL = 6, 7
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
 
 

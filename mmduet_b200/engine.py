@@ -312,14 +312,10 @@ class DecoderEngine:
         self.max_tokens, self.max_lm_rows = max_tokens, max_lm_rows
         self._ws = None
         self._ensure_ws(max_tokens, max_lm_rows)
+        self._meta_ring, self._meta_next = [None] * 8, 0
 
     # ---- pages ----
     def _alloc_page(self):
-        if not self._free:
-            # streams are released by KVStorage.__del__; objects caught in reference cycles only die at the next
-            # collection, so run one before giving up
-            import gc
-            gc.collect()
         if not self._free:
             raise _lib.MmdError(f"KV pool exhausted ({self.n_pages} pages of {PAGE} tokens)")
         return self._free.pop()
@@ -348,94 +344,149 @@ class DecoderEngine:
         with self._lock:
             return self._step_locked(items, score, lm)
 
-    def _step_locked(self, items, score, lm):
-        H, dev = self.cfg.hidden, self.device
-        src_row, tok_pos, tok_slot, desc, tables, score_rows, lm_rows = [], [], [], [], [], [], []
-        emb_chunks, emb_rows = [], 0
-        q_start, max_n_q, max_kv = 0, 0, 0
-        views = []
+    def _plan(self, items, score, lm):
+        """Phase 1 of a step: validates every item and works out rows, positions and page needs WITHOUT touching any stream
+        state.  Everything that can be refused (stale view, bad ids, bad shapes, context limit, KV pool exhausted) is refused
+        here, before a rollback or a page allocation has happened."""
+        H = self.cfg.hidden
+        plan, emb_rows, seen = [], 0, set()
+        pages_needed = 0
         for it in items:
             st, past = it["storage"], int(it["past"])
-            if past > st.length:
+            if id(st) in seen:
+                raise _lib.MmdError("the same stream appears twice in one step")
+            seen.add(id(st))
+            if past < 0 or past > st.length:
                 raise _lib.MmdError("cache view is longer than the stream (stale view after a rollback)")
-            if past < st.length:
-                st.truncate(past)  # an older view was passed back: rollback
-            ids = it.get("ids")
-            rows = []
+            chunk = None
             if it.get("embeds") is not None:
-                e = it["embeds"]
-                assert e.dim() == 2 and e.shape[1] == H, e.shape
-                emb_chunks.append(e if e.dtype == torch.bfloat16 else e.to(torch.bfloat16))
-                rows = [-(emb_rows + j) - 1 for j in range(e.shape[0])]
-                emb_rows += e.shape[0]
+                chunk = it["embeds"]
+                rows = []
             else:
+                ids = it.get("ids")
                 rows = [int(i) for i in (ids if ids is not None else [])]
                 if any(r < 0 or r >= self.cfg.vocab for r in rows):
                     raise _lib.MmdError("token id out of range")
                 fr = it.get("frames")
                 if fr is not None and fr.shape[0] > 0:
-                    assert fr.dim() == 2 and fr.shape[1] == H, fr.shape
-                    emb_chunks.append(fr if fr.dtype == torch.bfloat16 else fr.to(torch.bfloat16))
-                    rows += [-(emb_rows + j) - 1 for j in range(fr.shape[0])]
-                    emb_rows += fr.shape[0]
+                    chunk = fr
+            if chunk is not None:
+                if chunk.dim() != 2 or chunk.shape[1] != H:
+                    raise _lib.MmdError(f"embeddings must be [n, {H}], got {tuple(chunk.shape)}")
+                rows = rows + [-(emb_rows + j) - 1 for j in range(chunk.shape[0])]
+                emb_rows += chunk.shape[0]
             n_q = len(rows)
             if n_q == 0:
                 raise _lib.MmdError("empty step item")
             new_len = past + n_q
             if new_len > self.max_context:
                 raise _lib.MmdError(f"context {new_len} exceeds max_context {self.max_context}")
-            st.ensure(new_len)
-            src_row += rows
-            for j in range(n_q):
-                pos = past + j
-                tok_pos.append(pos)
-                tok_slot.append(st.pages[pos // PAGE] * PAGE + pos % PAGE)
-            desc += [q_start, n_q, new_len, len(tables)]
-            tables += st.pages[:(new_len + PAGE - 1) // PAGE]
-            if score == "last":
-                score_rows.append(q_start + n_q - 1)
-            elif score == "all":
-                score_rows += list(range(q_start, q_start + n_q))
-            elif score == "frame_ends":
-                score_rows += [q_start + r for r in it["score_rows"]]
-            if lm == "last":
-                lm_rows.append(q_start + n_q - 1)
-            elif lm == "all":
-                lm_rows += list(range(q_start, q_start + n_q))
+            if score == "frame_ends" and any(r < 0 or r >= n_q for r in it["score_rows"]):
+                raise _lib.MmdError("score_rows outside the item")
+            kept = min(len(st.pages), (past + PAGE - 1) // PAGE)          # pages that survive the rollback to `past`
+            pages_needed += (new_len + PAGE - 1) // PAGE - kept - (len(st.pages) - kept)   # new pages minus recycled ones
+            plan.append((it, st, past, rows, chunk, n_q, new_len))
+        if pages_needed > len(self._free):
+            import gc
+            gc.collect()       # streams are released by KVStorage.__del__; cycles only die at a collection
+            if pages_needed > len(self._free):
+                raise _lib.MmdError(f"KV pool exhausted ({self.n_pages} pages of {PAGE} tokens, {len(self._free)} free, "
+                                    f"{pages_needed} needed)")
+        return plan
+
+    def _meta_upload(self, meta):
+        """One pinned staging buffer per in-flight step (ring of 8, grown on demand) instead of a cudaHostAlloc per step."""
+        n = int(meta.size)
+        i = self._meta_next
+        self._meta_next = (i + 1) % len(self._meta_ring)
+        slot = self._meta_ring[i]
+        if slot is None or slot[0].numel() < n:
+            cap = max(4096, 1 << (n - 1).bit_length())
+            slot = [torch.empty(cap, dtype=torch.int32).pin_memory(), torch.empty(cap, dtype=torch.int32, device=self.device),
+                    torch.cuda.Event()]
+            self._meta_ring[i] = slot
+        else:
+            slot[2].synchronize()     # the copy issued 8 steps ago has long finished; this does not block in practice
+        host, devbuf, ev = slot
+        host.numpy()[:n] = meta
+        devbuf[:n].copy_(host[:n], non_blocking=True)
+        ev.record()
+        return devbuf
+
+    def _step_locked(self, items, score, lm):
+        H, dev = self.cfg.hidden, self.device
+        plan = self._plan(items, score, lm)
+        src_row, tok_pos, tok_slot, desc, tables, score_rows, lm_rows = [], [], [], [], [], [], []
+        emb_chunks = []
+        q_start, max_n_q, max_kv = 0, 0, 0
+        # phase 2: nothing below can be refused for a reason phase 1 could have seen.  Stream lengths are committed only
+        # after the launch sequence was accepted; if it is not, every touched stream is left at its rollback target
+        # (`past`): the append did not happen, and rows beyond `past` may have been overwritten, so they are not exposed.
+        try:
+            for it, st, past, rows, chunk, n_q, new_len in plan:
+                if past < st.length:
+                    st.truncate(past)  # an older view was passed back: rollback (all rollbacks first: they free pages)
+            for it, st, past, rows, chunk, n_q, new_len in plan:
+                st.ensure(new_len)
+                if chunk is not None:
+                    emb_chunks.append(chunk if chunk.dtype == torch.bfloat16 else chunk.to(torch.bfloat16))
+                src_row += rows
+                pg = st.pages
+                for pos in range(past, new_len):
+                    tok_pos.append(pos)
+                    tok_slot.append(pg[pos // PAGE] * PAGE + pos % PAGE)
+                desc += [q_start, n_q, new_len, len(tables)]
+                tables += pg[:(new_len + PAGE - 1) // PAGE]
+                if score == "last":
+                    score_rows.append(q_start + n_q - 1)
+                elif score == "all":
+                    score_rows += list(range(q_start, q_start + n_q))
+                elif score == "frame_ends":
+                    score_rows += [q_start + r for r in it["score_rows"]]
+                if lm == "last":
+                    lm_rows.append(q_start + n_q - 1)
+                elif lm == "all":
+                    lm_rows += list(range(q_start, q_start + n_q))
+                q_start += n_q
+                max_n_q, max_kv = max(max_n_q, n_q), max(max_kv, new_len)
+            M = q_start
+            self._ensure_ws(M, len(lm_rows))
+            meta = np.asarray(src_row + tok_pos + tok_slot + desc + tables + score_rows + lm_rows, dtype=np.int32)
+            meta_d = self._meta_upload(meta)
+            base = meta_d.data_ptr()
+            o = 0
+
+            def seg(n):
+                nonlocal o
+                p = base + 4 * o
+                o += n
+                return p
+            p_src, p_pos, p_slot = seg(M), seg(M), seg(M)
+            p_desc, p_tab = seg(len(desc)), seg(len(tables))
+            p_score, p_lm = seg(len(score_rows)), seg(len(lm_rows))
+            if emb_chunks:
+                frame_tokens = emb_chunks[0] if len(emb_chunks) == 1 else torch.cat(emb_chunks, 0)
+                frame_tokens = frame_tokens.contiguous()
+            else:
+                frame_tokens = None
+            n_s, n_l = len(score_rows), len(lm_rows)
+            head_logits = torch.empty(max(n_s, 1), 4, dtype=torch.float32, device=dev)
+            scores = torch.empty(max(n_s, 1), 2, dtype=torch.float32, device=dev)
+            lm_logits = torch.empty(n_l, self.cfg.vocab, dtype=torch.float32, device=dev) if n_l else None
+            step = _lib.Step(n_tokens=M, src_row=p_src, frame_tokens=_lib.ptr(frame_tokens), tok_pos=p_pos, tok_slot=p_slot,
+                             n_streams=len(items), stream_desc=p_desc, block_tables=p_tab, max_n_q=max_n_q, max_kv_len=max_kv,
+                             n_score_rows=n_s, score_rows=p_score, head_logits_out=head_logits.data_ptr(), scores_out=scores.data_ptr(),
+                             n_lm_rows=n_l, lm_rows=p_lm, lm_logits_out=_lib.ptr(lm_logits))
+            rc = self.lib.mmd_decoder_step(self.ctx, ctypes.byref(self.w), ctypes.byref(self.kv), ctypes.byref(step), self._ws.data_ptr(),
+                                           self._ws.numel(), _lib.stream_ptr())
+            _lib.check(rc, "mmd_decoder_step")
+        except BaseException:
+            for it, st, past, rows, chunk, n_q, new_len in plan:
+                st.truncate(min(st.length, past))
+            raise
+        views = []
+        for it, st, past, rows, chunk, n_q, new_len in plan:
             st.length = new_len
             views.append(CacheView(st, new_len))
-            q_start += n_q
-            max_n_q, max_kv = max(max_n_q, n_q), max(max_kv, new_len)
-        M = q_start
-        self._ensure_ws(M, len(lm_rows))
-        meta = np.asarray(src_row + tok_pos + tok_slot + desc + tables + score_rows + lm_rows, dtype=np.int32)
-        meta_d = torch.from_numpy(meta).pin_memory().to(dev, non_blocking=True)
-        base = meta_d.data_ptr()
-        o = 0
-
-        def seg(n):
-            nonlocal o
-            p = base + 4 * o
-            o += n
-            return p
-        p_src, p_pos, p_slot = seg(M), seg(M), seg(M)
-        p_desc, p_tab = seg(len(desc)), seg(len(tables))
-        p_score, p_lm = seg(len(score_rows)), seg(len(lm_rows))
-        if emb_chunks:
-            frame_tokens = emb_chunks[0] if len(emb_chunks) == 1 else torch.cat(emb_chunks, 0)
-            frame_tokens = frame_tokens.contiguous()
-        else:
-            frame_tokens = None
-        n_s, n_l = len(score_rows), len(lm_rows)
-        head_logits = torch.empty(max(n_s, 1), 4, dtype=torch.float32, device=dev)
-        scores = torch.empty(max(n_s, 1), 2, dtype=torch.float32, device=dev)
-        lm_logits = torch.empty(n_l, self.cfg.vocab, dtype=torch.float32, device=dev) if n_l else None
-        step = _lib.Step(n_tokens=M, src_row=p_src, frame_tokens=_lib.ptr(frame_tokens), tok_pos=p_pos, tok_slot=p_slot,
-                         n_streams=len(items), stream_desc=p_desc, block_tables=p_tab, max_n_q=max_n_q, max_kv_len=max_kv,
-                         n_score_rows=n_s, score_rows=p_score, head_logits_out=head_logits.data_ptr(), scores_out=scores.data_ptr(),
-                         n_lm_rows=n_l, lm_rows=p_lm, lm_logits_out=_lib.ptr(lm_logits))
-        rc = self.lib.mmd_decoder_step(self.ctx, ctypes.byref(self.w), ctypes.byref(self.kv), ctypes.byref(step), self._ws.data_ptr(),
-                                       self._ws.numel(), _lib.stream_ptr())
-        _lib.check(rc, "mmd_decoder_step")
         self._last_meta = (meta_d, frame_tokens)  # keep alive until the kernels have consumed them
         return {"head_logits": head_logits[:n_s], "scores": scores[:n_s], "lm_logits": lm_logits, "views": views}

@@ -2,8 +2,8 @@
 import torch
 
 from . import _lib
-from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_T_F32, EPI_T_SWIGLU,
-                   EPI_T_SWIGLU_IL)
+from ._lib import (ACT_GELU_ERF, ACT_GELU_TANH, ACT_NONE, EPI_BF16, EPI_F32, EPI_RESID_F32, EPI_SWIGLU_PAIR, EPI_T_F32,
+                   EPI_T_SWIGLU, EPI_T_SWIGLU_IL)
 
 
 def _chk2d(t, dtype):
@@ -89,4 +89,38 @@ def gemm_t_swiglu(x, w_gate, w_up, out=None, blocked_shape=None):
                            ldw, x.data_ptr(), M, x.stride(0), K, 0, out.data_ptr(), out.stride(0), 1, 0,
                            _lib.stream_ptr())
     _lib.check(rc, "mmd_gemm_bf16(T_SWIGLU)")
+    return out
+
+
+def gemm_f32_planes(x, w, k_splits=1, out=None):
+    """Normal orientation, fp32 split-K partial planes [splits, M, N] of x[M,K] @ w[N,K]^T.  With M >= 1024 this is the
+    CTA-pair kernel writing plane `ks` through a 3-D TMA store: the decoder's q/k/v, o (1 plane) and down (3 planes)
+    projections of passes with >= 1024 tokens (csrc/api.cu, mmd_decoder_step)."""
+    _chk2d(x, torch.bfloat16)
+    _chk2d(w, torch.bfloat16)
+    M, K = x.shape
+    N = w.shape[0]
+    lib = _lib.load()
+    splits = lib.mmd_gemm_splits(K, k_splits)
+    if out is None:
+        out = torch.empty(splits, M, N, device=x.device, dtype=torch.float32)
+    rc = lib.mmd_gemm_bf16(_lib.context(x.device.index), EPI_F32, ACT_NONE, x.data_ptr(), 0, M, x.stride(0), w.data_ptr(), N,
+                           w.stride(0), K, 0, out.data_ptr(), out.stride(1), k_splits, out.stride(0), _lib.stream_ptr())
+    _lib.check(rc, "mmd_gemm_bf16(F32 planes)")
+    return out
+
+
+def gemm_swiglu_pair(x, w_il, out=None):
+    """Normal orientation (CTA-pair kernel) on the interleaved gate/up matrix (row 2j = gate_j, 2j+1 = up_j):
+    out[M, N] = silu(x @ gate^T) * (x @ up^T) with N = rows/2 — the decoder's gate/up of passes with >= 2048 tokens."""
+    _chk2d(x, torch.bfloat16)
+    _chk2d(w_il, torch.bfloat16)
+    M, K = x.shape
+    N = w_il.shape[0] // 2
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=torch.bfloat16)
+    lib = _lib.load()
+    rc = lib.mmd_gemm_bf16(_lib.context(x.device.index), EPI_SWIGLU_PAIR, ACT_NONE, x.data_ptr(), 0, M, x.stride(0), w_il.data_ptr(),
+                           2 * N, w_il.stride(0), K, 0, out.data_ptr(), out.stride(0), 1, 0, _lib.stream_ptr())
+    _lib.check(rc, "mmd_gemm_bf16(SWIGLU_PAIR)")
     return out
