@@ -68,6 +68,13 @@ MMD_API int mmd_set_gemm_2cta(int on);
 #define MMD_EPI_T_SWIGLU_IL 7 /* swap-AB, X rows interleaved (2j = gate_j, 2j+1 = up_j): out_bf16[m][j] = silu(acc[2j]) * acc[2j+1];
                                 out is [M, x_rows / 2]; one accumulator, 256-token tiles (decoder gate/up above 128 tokens) */
 #define MMD_EPI_BF16_HILO 5 /* v = act(acc + bias[n]); out[m,n] = bf16(v), out[m,N+n] = bf16(v - bf16(v)) */
+/* OR-ed into `epi` (swap-AB epilogues MMD_EPI_T_F32 / MMD_EPI_T_SWIGLU, y_rows <= 128, K % 64 == 0):
+ * Y_HILO: Y is a bf16 hi+lo pair [hi | lo] of width 2K (ldy >= 2K); both halves are multiplied with every weight tile into
+ * the same fp32 accumulator, so the weights are streamed once and the activation rounding error drops from 2^-9 to 2^-17.
+ * OUT_HILO (MMD_EPI_T_SWIGLU): the output row is [bf16(v) | bf16(v - bf16(v))], lo at column x_rows (ldo >= 2 * x_rows).
+ * Used for the decoder rows whose scores are read ("precise rows"). */
+#define MMD_GEMM_Y_HILO 0x100
+#define MMD_GEMM_OUT_HILO 0x200
 #define MMD_ACT_NONE 0
 #define MMD_ACT_GELU_TANH 1
 #define MMD_ACT_GELU_ERF 2
@@ -99,6 +106,22 @@ MMD_API int mmd_vit_attention(const void* qkv, void* out, int T, int S, int H, i
  * Qwen2RMSNorm (TF:models/qwen2/modeling_qwen2.py:249-310).  w == NULL: reduction only. */
 MMD_API int mmd_resid_add_rmsnorm(float* resid, const float* partial, int n_planes, int64_t plane_stride, const float* w,
                                   void* out_bf16, float* out_f32, int64_t rows, int H, float eps, void* stream);
+/* The same with "precise rows": rows with j = prec_of_row[row] >= 0 take their residual update from prec_partial
+ * ([n_prec_planes] planes of [P, H], prec_plane_stride elements apart) instead of `partial`, and also get the normalised
+ * row as a bf16 hi+lo pair out_hilo[j] = [hi | lo] (2H wide).  prec_of_row == NULL with out_hilo != NULL: every row (j = row).
+ * out_bf16 / out_f32 / prec_partial / out_hilo may be NULL. */
+MMD_API int mmd_resid_add_rmsnorm_precise(float* resid, const float* partial, int n_planes, int64_t plane_stride,
+                                          const float* w, void* out_bf16, float* out_f32, int64_t rows, int H, float eps,
+                                          const int* prec_of_row, const float* prec_partial, int n_prec_planes,
+                                          int64_t prec_plane_stride, void* out_hilo, void* stream);
+/* Final RMSNorm (model.norm) fused with the informative/relevance heads, evaluated ONLY on the rows that are read:
+ * for score row i: r = resid[score_rows[i]] + sum planes; n = w * r * rsqrt(mean r^2 + eps); logits_out[i] = n . head_w[0..3];
+ * scores_out[i] = {softmax(inf)[1], softmax(rel)[1]}; for lm row i the bf16 normalised row goes to lm_x[i] (lm_head operand).
+ * (video_head_live_llava_qwen.py:152-161; test/inference.py:243-244).  prec_* as above (may be NULL / 0). */
+MMD_API int mmd_final_norm_heads(const float* resid, const float* partial, int n_planes, int64_t plane_stride, const float* w,
+                                 const int* score_rows, int n_score, const int* lm_rows, int n_lm, const float* head_w,
+                                 float* logits_out, float* scores_out, void* lm_x, int H, float eps, const int* prec_of_row,
+                                 const float* prec_partial, int n_prec_planes, int64_t prec_plane_stride, void* stream);
 /* q/k/v bias + RoPE + KV append into the paged pool (TF:models/qwen2/modeling_qwen2.py:127-146,215-233;
  * TF:cache_utils.py:119-120). */
 MMD_API int mmd_qkv_finish(const float* partial, int n_planes, int64_t plane_stride, const float* bias,
@@ -218,6 +241,11 @@ typedef struct {
   float* scores_out;                 /* fp32 [n_score_rows,2] {informative_score, relevance_score} */
   int n_lm_rows; const int* lm_rows; /* rows that need lm_head (query / generation steps), 0 on frame steps */
   float* lm_logits_out;              /* fp32 [n_lm_rows, vocab] */
+  /* "precise rows" of passes with more than 128 tokens: the (<= 128) rows whose outputs are read (score / lm rows) get a
+   * second gate/up + down pass per layer on bf16 hi+lo operands.  0 rows = off.  Passes of <= 128 tokens carry EVERY row as
+   * hi+lo inside the main kernels and ignore these fields. */
+  int n_prec_rows; const int* prec_rows;     /* int32 [n_prec_rows] row indices, ascending */
+  const int* prec_of_row;            /* int32 [n_tokens]: index into prec_rows, or -1 */
 } mmd_step;
 
 MMD_API int64_t mmd_decoder_workspace_bytes(mmd_ctx*, const mmd_dec_weights*, int max_tokens, int max_lm_rows);

@@ -11,6 +11,7 @@ c_void_p, c_int, c_int64, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int6
 
 EPI_BF16, EPI_RESID_F32, EPI_T_F32, EPI_T_SWIGLU, EPI_F32, EPI_BF16_HILO = 0, 1, 2, 3, 4, 5
 EPI_SWIGLU_PAIR, EPI_T_SWIGLU_IL = 6, 7
+GEMM_Y_HILO, GEMM_OUT_HILO = 0x100, 0x200
 ACT_NONE, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
 
 
@@ -61,7 +62,7 @@ class Step(ctypes.Structure):
                 ("tok_slot", c_void_p), ("n_streams", c_int), ("stream_desc", c_void_p), ("block_tables", c_void_p),
                 ("max_n_q", c_int), ("max_kv_len", c_int), ("n_score_rows", c_int), ("score_rows", c_void_p),
                 ("head_logits_out", c_void_p), ("scores_out", c_void_p), ("n_lm_rows", c_int), ("lm_rows", c_void_p),
-                ("lm_logits_out", c_void_p)]
+                ("lm_logits_out", c_void_p), ("n_prec_rows", c_int), ("prec_rows", c_void_p), ("prec_of_row", c_void_p)]
 
 
 P = ctypes.POINTER
@@ -89,6 +90,10 @@ SIGNATURES = {
     "mmd_vit_attention": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "mmd_resid_add_rmsnorm": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                       c_float, c_void_p]),
+    "mmd_resid_add_rmsnorm_precise": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                              c_float, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "mmd_final_norm_heads": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     "mmd_qkv_finish": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mmd_kv_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,

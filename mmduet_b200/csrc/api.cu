@@ -36,7 +36,7 @@ static const char* const kTags[] = {
     "im2col", "pos_emb", "patch_embed", "ln1", "qkv", "vit_attention", "out_proj", "ln2", "fc1", "fc2",
     "gather", "proj.0+gelu", "proj.2", "tap_pool",
     "embed/concat", "input_layernorm", "qkv_proj", "qkv_finish", "kv_attention", "o_proj", "post_attention_layernorm",
-    "gate_up_swiglu", "down_proj", "next_layernorm", "heads", "lm_head"};
+    "gate_up_swiglu", "down_proj", "next_layernorm", "heads", "lm_head", "gate_up_precise", "down_precise", "final_norm_heads"};
 constexpr int kNumTags = sizeof(kTags) / sizeof(kTags[0]);
 static int tag_of(const char* name) {
   for (int i = 0; i < kNumTags; ++i) if (strcmp(kTags[i], name) == 0) return i;
@@ -50,6 +50,7 @@ struct mmd_ctx {
   mmd::GemmContext* gemm;
   unsigned long long launches = 0;
   bool use_pdl = true;   // programmatic dependent launch across the decoder step's kernels (MMD_NO_PDL=1 disables)
+  bool precise = true;   // bf16 hi+lo operands on the rows whose outputs are read (MMD_NO_PRECISE=1 disables; diagnostics)
   bool prof_on = false;
   unsigned long long prof_mask = 0;
   std::vector<cudaEvent_t> ev_pool;
@@ -110,11 +111,12 @@ static int choose_splits(int num_sms, int N, int K, int M) {
   return best;
 }
 
+// `hilo`: act is a [hi | lo] pair of width 2K (row stride 2K)
 static int gemm_T_partials(mmd_ctx* c, const void* act, int M, const void* w, int N, int K, int splits, float* planes,
-                           cudaStream_t s, int* eff_out) {
+                           cudaStream_t s, int* eff_out, bool hilo = false) {
   mmd::GemmArgs a;
   a.X = static_cast<const __nv_bfloat16*>(w); a.x_rows = N; a.ldx = K;
-  a.Y = static_cast<const __nv_bfloat16*>(act); a.y_rows = M; a.ldy = K;
+  a.Y = static_cast<const __nv_bfloat16*>(act); a.y_rows = M; a.ldy = hilo ? 2 * (int64_t)K : K; a.y_hilo = hilo ? 1 : 0;
   a.K = K; a.epi = mmd::EPI_T_F32; a.out = planes; a.ldo = N; a.k_splits = splits; a.split_stride = (int64_t)M * N;
   *eff_out = mmd::gemm_effective_splits(K, splits);
   return mmd::gemm_launch(c->gemm, a, s);
@@ -127,15 +129,6 @@ static int gemm_normal(mmd_ctx* c, const void* act, int M, const void* w, int N,
   a.Y = static_cast<const __nv_bfloat16*>(w); a.y_rows = N; a.ldy = K;
   a.K = K; a.epi = epi; a.act = actfn; a.bias = bias; a.out = out; a.ldo = ldo;
   return mmd::gemm_launch(c->gemm, a, s);
-}
-
-__global__ void gather_rows_bf16_kernel(const __nv_bfloat16* __restrict__ src, const int* __restrict__ rows,
-                                        __nv_bfloat16* __restrict__ dst, int H8) {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  const uint4* s = reinterpret_cast<const uint4*>(src + (long long)rows[blockIdx.x] * H8 * 8);
-  uint4* d = reinterpret_cast<uint4*>(dst + (long long)blockIdx.x * H8 * 8);
-  for (int c = threadIdx.x; c < H8; c += blockDim.x) d[c] = s[c];
 }
 
 extern "C" {
@@ -159,6 +152,8 @@ mmd_ctx* mmd_create(int device) {
   c->gemm = g;
   const char* no_pdl = getenv("MMD_NO_PDL");
   c->use_pdl = !(no_pdl && no_pdl[0] == '1');
+  const char* no_prec = getenv("MMD_NO_PRECISE");
+  c->precise = !(no_prec && no_prec[0] == '1');
   return c;
 }
 
@@ -191,7 +186,8 @@ int mmd_gemm_bf16(mmd_ctx* c, int epi, int act, const void* X, const void* X2, i
   a.X2 = static_cast<const __nv_bfloat16*>(X2);
   a.Y = static_cast<const __nv_bfloat16*>(Y);
   a.x_rows = (int)x_rows; a.y_rows = (int)y_rows; a.K = (int)K;
-  a.ldx = ldx; a.ldy = ldy; a.epi = epi; a.act = act; a.bias = bias; a.out = out; a.ldo = ldo;
+  a.ldx = ldx; a.ldy = ldy; a.epi = epi & 0xff; a.act = act; a.bias = bias; a.out = out; a.ldo = ldo;
+  a.y_hilo = (epi & MMD_GEMM_Y_HILO) ? 1 : 0; a.out_hilo = (epi & MMD_GEMM_OUT_HILO) ? 1 : 0;
   a.k_splits = k_splits; a.split_stride = split_stride;
   RUN(mmd::gemm_launch(c->gemm, a, S(stream)), "mmd_gemm_bf16");
   return 0;
@@ -238,6 +234,25 @@ int mmd_resid_add_rmsnorm(float* resid, const float* partial, int n_planes, int6
   RUNK(mmd::launch_resid_add_rmsnorm(resid, partial, n_planes, plane_stride, w, static_cast<__nv_bfloat16*>(out_bf16), out_f32,
                                      rows, H, eps, S(stream)), "mmd_resid_add_rmsnorm");
   return check_launch("mmd_resid_add_rmsnorm");
+}
+
+int mmd_resid_add_rmsnorm_precise(float* resid, const float* partial, int n_planes, int64_t plane_stride, const float* w, void* out_bf16,
+                                  float* out_f32, int64_t rows, int H, float eps, const int* prec_of_row, const float* prec_partial,
+                                  int n_prec_planes, int64_t prec_plane_stride, void* out_hilo, void* stream) {
+  RUNK(mmd::launch_resid_add_rmsnorm_precise(resid, partial, n_planes, plane_stride, w, static_cast<__nv_bfloat16*>(out_bf16), out_f32, rows, H,
+                                             eps, prec_of_row, prec_partial, n_prec_planes, prec_plane_stride,
+                                             static_cast<__nv_bfloat16*>(out_hilo), S(stream)), "mmd_resid_add_rmsnorm_precise");
+  return check_launch("mmd_resid_add_rmsnorm_precise");
+}
+
+int mmd_final_norm_heads(const float* resid, const float* partial, int n_planes, int64_t plane_stride, const float* w,
+                         const int* score_rows, int n_score, const int* lm_rows, int n_lm, const float* head_w, float* logits_out,
+                         float* scores_out, void* lm_x, int H, float eps, const int* prec_of_row, const float* prec_partial,
+                         int n_prec_planes, int64_t prec_plane_stride, void* stream) {
+  RUNK(mmd::launch_final_norm_heads(resid, partial, n_planes, plane_stride, w, score_rows, n_score, lm_rows, n_lm, head_w, logits_out,
+                                    scores_out, static_cast<__nv_bfloat16*>(lm_x), H, eps, prec_of_row, prec_partial, n_prec_planes,
+                                    prec_plane_stride, S(stream)), "mmd_final_norm_heads");
+  return check_launch("mmd_final_norm_heads");
 }
 
 int mmd_qkv_finish(const float* partial, int n_planes, int64_t plane_stride, const float* bias, const float* rope_cos,
@@ -423,9 +438,10 @@ int mmd_projector_pool(mmd_ctx* c, const mmd_projector_weights* w, const float* 
 // decoder step
 // ---------------------------------------------------------------------------------------------------------------
 struct DecBufs {
-  float *resid, *planes, *hidden_f32, *o_part, *ml_part;
-  __nv_bfloat16 *x, *q, *attn, *h, *lm_x;
+  float *resid, *planes, *planes_p, *o_part, *ml_part;
+  __nv_bfloat16 *x, *q, *attn, *h, *lm_x, *xp2, *hp2;
 };
+constexpr int kMaxPrecRows = 128;   // rows carried as bf16 hi+lo pairs (one <= 128-token tile of the swap-AB GEMM)
 constexpr int kMaxSplits = 8;
 constexpr int kMaxAttnSplits = 32;
 static int64_t dec_carve(const mmd_dec_weights* w, int max_tokens, int max_lm_rows, Bump& b, DecBufs* o) {
@@ -433,8 +449,10 @@ static int64_t dec_carve(const mmd_dec_weights* w, int max_tokens, int max_lm_ro
   const int H = w->hidden, QD = w->q_heads * w->head_dim, NQKV = (w->q_heads + 2 * w->kv_heads) * w->head_dim;
   const int nmax = NQKV > H ? NQKV : H;
   o->resid = b.take<float>(M * H);
-  o->hidden_f32 = b.take<float>(M * H);
   o->planes = b.take<float>((int64_t)kMaxSplits * M * nmax);
+  o->planes_p = b.take<float>((int64_t)kMaxSplits * kMaxPrecRows * H);
+  o->xp2 = b.take<__nv_bfloat16>((int64_t)kMaxPrecRows * 2 * H);
+  o->hp2 = b.take<__nv_bfloat16>((int64_t)kMaxPrecRows * 2 * w->mlp);
   o->x = b.take<__nv_bfloat16>(M * H);
   o->q = b.take<__nv_bfloat16>(M * QD);
   o->attn = b.take<__nv_bfloat16>(M * QD);
@@ -475,13 +493,29 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
   const int QD = Hq * dh, NQKV = (Hq + 2 * Hkv) * dh, I = w->mlp;
 
   struct PdlGuard { PdlGuard(bool on) { mmd::g_use_pdl = on; } ~PdlGuard() { mmd::g_use_pdl = false; } } pdl_guard(c->use_pdl);
+  // "Precise rows": the scores are read at a handful of rows (one per frame) and their error is dominated by the bf16 rounding
+  // of the MLP operands ON THOSE ROWS (tools/noise_floor_decoder.py: x_mlp 0.012, h 0.007 of a 0.018 total; other rows' noise
+  // averages out through attention).  Those rows therefore carry their GEMM operands as bf16 hi+lo pairs:
+  //   all_prec  (M <= 128, single-frame / query / generation steps): every row, inside the main swap-AB kernels (the step is
+  //             HBM-bound, the second MMA per weight tile is free); q/k/v, gate/up and down operands are hi+lo.
+  //   side_prec (M > 128): the <= 128 listed rows get a second, skinny gate/up + down pass per layer whose result replaces the
+  //             main pass's residual update for those rows (weights re-streamed: +1.75 ms per pass at the 7B size).
+  const bool prec_ok = c->precise && H % 64 == 0 && I % 64 == 0;
+  const bool all_prec = prec_ok && M <= kMaxPrecRows;
+  const int P = st->n_prec_rows;
+  const bool side_prec = prec_ok && !all_prec && P > 0 && P <= kMaxPrecRows && st->prec_rows != nullptr && st->prec_of_row != nullptr;
+  __nv_bfloat16* xmain = all_prec ? nullptr : buf.x;         // plain bf16 normalised rows (unused when every row is hi+lo)
+  __nv_bfloat16* x_hilo = (all_prec || side_prec) ? buf.xp2 : nullptr;
+  const int* prec_of_row = side_prec ? st->prec_of_row : nullptr;
   // inputs_embeds = cat(embed_tokens(prefix ids), frame tokens) -> fp32 residual stream   (test/inference.py:235-238)
   PRUNK(mmd::launch_gather_rows_bf16_to_f32(static_cast<const __nv_bfloat16*>(w->embed), static_cast<const __nv_bfloat16*>(st->frame_tokens),
                                            st->src_row, buf.resid, M, H, s), "embed/concat");
-  PRUNK(mmd::launch_resid_add_rmsnorm(buf.resid, nullptr, 0, 0, w->layers[0].ln1_w, buf.x, nullptr, M, H, w->rms_eps, s), "input_layernorm");
+  PRUNK(mmd::launch_resid_add_rmsnorm_precise(buf.resid, nullptr, 0, 0, w->layers[0].ln1_w, xmain, nullptr, M, H, w->rms_eps, nullptr,
+                                             nullptr, 0, 0, all_prec ? buf.xp2 : nullptr, s), "input_layernorm");
   const int s_qkv = choose_splits(c->num_sms, NQKV, H, M);
   const int s_o = choose_splits(c->num_sms, H, QD, M);
   const int s_down = choose_splits(c->num_sms, H, I, M);
+  const int s_down_p = side_prec ? choose_splits(c->num_sms, H, I, P) : 1;
   int attn_splits = mmd::kv_attention_pick_splits(st->max_n_q * (Hq / Hkv), Hkv, st->n_streams, st->max_kv_len, c->num_sms);
   if (attn_splits > kMaxAttnSplits) attn_splits = kMaxAttnSplits;
   // Swap-AB + split-K (weights on the 128 UMMA rows, all SMs busy) wins up to ~1200 tokens per pass on this model
@@ -500,10 +534,18 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
     *eff = mmd::gemm_effective_splits(K, splits);
     return mmd::gemm_launch(c->gemm, a, s);
   };
+  // swap-AB SwiGLU on hi+lo activations [rows, 2H] -> hi+lo outputs [rows, 2I] (gate rows / up rows of the interleaved matrix)
+  auto gate_up_hilo = [&](const __nv_bfloat16* gu, const __nv_bfloat16* act2, int rows, __nv_bfloat16* out2) -> int {
+    mmd::GemmArgs a;
+    a.X = gu; a.X2 = gu + H; a.x_rows = I; a.ldx = 2 * (int64_t)H; a.Y = act2; a.y_rows = rows; a.ldy = 2 * (int64_t)H; a.K = H;
+    a.epi = mmd::EPI_T_SWIGLU; a.out = out2; a.ldo = 2 * (int64_t)I; a.y_hilo = 1; a.out_hilo = 1;
+    return mmd::gemm_launch(c->gemm, a, s);
+  };
+  int eff = 1, eff_p = 0;   // split-K planes of the pending residual update (main / precise side pass)
   for (int l = 0; l < w->n_layers; ++l) {
     const mmd_dec_layer& L = w->layers[l];
-    int eff = 1;
-    if (pair_qkv) PRUN(gemm_big_f32(buf.x, L.qkv_w, NQKV, H, 1, &eff), "qkv_proj");
+    if (all_prec) PRUN(gemm_T_partials(c, buf.xp2, M, L.qkv_w, NQKV, H, s_qkv, buf.planes, s, &eff, true), "qkv_proj");
+    else if (pair_qkv) PRUN(gemm_big_f32(buf.x, L.qkv_w, NQKV, H, 1, &eff), "qkv_proj");
     else PRUN(gemm_T_partials(c, buf.x, M, L.qkv_w, NQKV, H, s_qkv, buf.planes, s, &eff), "qkv_proj");
     __nv_bfloat16* kv_layer = static_cast<__nv_bfloat16*>(pool->pool) + (int64_t)l * pool->layer_stride;
     PRUNK(mmd::launch_qkv_finish(buf.planes, eff, (int64_t)M * NQKV, L.qkv_b, w->rope_cos, w->rope_sin, st->tok_pos, st->tok_slot,
@@ -512,11 +554,15 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
                                   buf.ml_part, buf.attn, Hq, Hkv, dh, MMD_PAGE_TOKENS, attn_splits, s), "kv_attention");
     if (pair_o) PRUN(gemm_big_f32(buf.attn, L.o_w, H, QD, 1, &eff), "o_proj");
     else PRUN(gemm_T_partials(c, buf.attn, M, L.o_w, H, QD, s_o, buf.planes, s, &eff), "o_proj");
-    PRUNK(mmd::launch_resid_add_rmsnorm(buf.resid, buf.planes, eff, (int64_t)M * H, L.ln2_w, buf.x, nullptr, M, H, w->rms_eps, s),
-         "post_attention_layernorm");
-    {
+    // resid += o_proj; x = RMSNorm(resid) (bf16 for the main pass, [hi | lo] for the precise rows)
+    PRUNK(mmd::launch_resid_add_rmsnorm_precise(buf.resid, buf.planes, eff, (int64_t)M * H, L.ln2_w, xmain, nullptr, M, H, w->rms_eps,
+                                               prec_of_row, nullptr, 0, 0, x_hilo, s), "post_attention_layernorm");
+    const __nv_bfloat16* gu = static_cast<const __nv_bfloat16*>(L.gate_up_w);
+    if (all_prec) {
+      PRUN(gate_up_hilo(gu, buf.xp2, M, buf.hp2), "gate_up_swiglu");
+      PRUN(gemm_T_partials(c, buf.hp2, M, L.down_w, H, I, s_down, buf.planes, s, &eff, true), "down_proj");
+    } else {
       mmd::GemmArgs a;
-      const __nv_bfloat16* gu = static_cast<const __nv_bfloat16*>(L.gate_up_w);
       if (big) {   // interleaved (gate, up) columns, SwiGLU on adjacent accumulator columns
         a.X = buf.x; a.x_rows = M; a.ldx = H; a.Y = gu; a.y_rows = 2 * I; a.ldy = H; a.K = H;
         a.epi = mmd::EPI_SWIGLU_PAIR; a.out = buf.h; a.ldo = I; a.force_2cta = 1;
@@ -531,24 +577,26 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
         a.epi = mmd::EPI_T_SWIGLU; a.out = buf.h; a.ldo = I;
       }
       PRUN(mmd::gemm_launch(c->gemm, a, s), "gate_up_swiglu");
+      if (side_prec) PRUN(gate_up_hilo(gu, buf.xp2, P, buf.hp2), "gate_up_precise");
+      if (pair_down) PRUN(gemm_big_f32(buf.h, L.down_w, H, I, 3, &eff), "down_proj");
+      else PRUN(gemm_T_partials(c, buf.h, M, L.down_w, H, I, s_down, buf.planes, s, &eff), "down_proj");
+      if (side_prec) PRUN(gemm_T_partials(c, buf.hp2, P, L.down_w, H, I, s_down_p, buf.planes_p, s, &eff_p, true), "down_precise");
     }
-    if (pair_down) PRUN(gemm_big_f32(buf.h, L.down_w, H, I, 3, &eff), "down_proj");
-    else PRUN(gemm_T_partials(c, buf.h, M, L.down_w, H, I, s_down, buf.planes, s, &eff), "down_proj");
-    const bool last = (l + 1 == w->n_layers);
-    const float* next_w = last ? w->final_norm_w : w->layers[l + 1].ln1_w;
-    PRUNK(mmd::launch_resid_add_rmsnorm(buf.resid, buf.planes, eff, (int64_t)M * H, next_w, buf.x, last ? buf.hidden_f32 : nullptr, M,
-                                       H, w->rms_eps, s), "next_layernorm");
+    if (l + 1 < w->n_layers)   // resid += down_proj (precise rows: from the side pass); x = RMSNorm(resid) for the next layer
+      PRUNK(mmd::launch_resid_add_rmsnorm_precise(buf.resid, buf.planes, eff, (int64_t)M * H, w->layers[l + 1].ln1_w, xmain, nullptr, M, H,
+                                                 w->rms_eps, prec_of_row, side_prec ? buf.planes_p : nullptr, eff_p, (int64_t)P * H,
+                                                 all_prec ? buf.xp2 : nullptr, s), "next_layernorm");
   }
-  if (st->n_score_rows > 0) {
-    if (st->score_rows == nullptr || st->head_logits_out == nullptr || st->scores_out == nullptr || w->heads_w == nullptr)
-      return fail(MMD_ERR_ARG, "mmd_decoder_step: score rows requested without buffers");
-    PRUNK(mmd::launch_heads(buf.hidden_f32, st->score_rows, w->heads_w, st->head_logits_out, st->scores_out, st->n_score_rows, H, s), "heads");
-  }
+  // final norm on the rows that are read only, with the informative/relevance heads as its epilogue (+ bf16 rows for lm_head)
+  if (st->n_score_rows > 0 && (st->score_rows == nullptr || st->head_logits_out == nullptr || st->scores_out == nullptr || w->heads_w == nullptr))
+    return fail(MMD_ERR_ARG, "mmd_decoder_step: score rows requested without buffers");
+  if (st->n_score_rows > 0 || st->n_lm_rows > 0)
+    PRUNK(mmd::launch_final_norm_heads(buf.resid, buf.planes, eff, (int64_t)M * H, w->final_norm_w, st->score_rows, st->n_score_rows,
+                                      st->lm_rows, st->n_lm_rows, w->heads_w, st->head_logits_out, st->scores_out, buf.lm_x, H, w->rms_eps,
+                                      prec_of_row, side_prec ? buf.planes_p : nullptr, eff_p, (int64_t)P * H, s), "final_norm_heads");
   if (st->n_lm_rows > 0) {
-    mmd::launch_k(gather_rows_bf16_kernel, dim3(st->n_lm_rows), dim3(128), 0, s, (const __nv_bfloat16*)buf.x, st->lm_rows, buf.lm_x, H / 8);
-    c->launches += 1;
-    int eff = 1;
-    PRUN(gemm_T_partials(c, buf.lm_x, st->n_lm_rows, w->lm_head, w->vocab, H, 1, st->lm_logits_out, s, &eff), "lm_head");
+    int e2 = 1;
+    PRUN(gemm_T_partials(c, buf.lm_x, st->n_lm_rows, w->lm_head, w->vocab, H, 1, st->lm_logits_out, s, &e2), "lm_head");
   }
   return check_launch("mmd_decoder_step");
 }

@@ -771,10 +771,10 @@ static int launch_attn(Kern kern, bool* attr_done, int smem, const Params& p, in
 // more items than SMs -> persistent shape (double-buffered Q); otherwise every CTA has one item and deeper K/V rings pay more
 template <int DH, typename Params, typename Front>
 static int launch_attn_auto(const Params& p, int n_items, cudaStream_t s) {
-  static bool attr_p = false, attr_s = false;
+  static PerDeviceFlag attr_p, attr_s;
   if (n_items > attn_num_sms())
-    return launch_attn(attn_tcgen05_kernel<DH, Params, Front, AttnCfgPersistent>, &attr_p, AttnCfgPersistent::TOTAL, p, n_items, s);
-  return launch_attn(attn_tcgen05_kernel<DH, Params, Front, AttnCfgSingle>, &attr_s, AttnCfgSingle::TOTAL, p, n_items, s);
+    return launch_attn(attn_tcgen05_kernel<DH, Params, Front, AttnCfgPersistent>, &attr_p.cur(), AttnCfgPersistent::TOTAL, p, n_items, s);
+  return launch_attn(attn_tcgen05_kernel<DH, Params, Front, AttnCfgSingle>, &attr_s.cur(), AttnCfgSingle::TOTAL, p, n_items, s);
 }
 
 int launch_vit_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int T, int S, int H, int dh, int split_hi_lo, cudaStream_t s) {

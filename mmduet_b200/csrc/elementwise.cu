@@ -324,23 +324,42 @@ int launch_resid_add_layernorm(float* x, const float* planes, int n_planes, long
 // next GEMM (and optionally the fp32 normalised row).  Qwen2RMSNorm: w * (x * rsqrt(mean(x^2) + eps))
 // (TF:models/qwen2/modeling_qwen2.py:249-263); residual adds of Qwen2DecoderLayer (:280-310).
 // ------------------------------------------------------------------------------------------------------------
+// "Precise rows" (DESIGN.md §2): rows listed in `prec_of_row` (row -> index j into the precise buffers, or -1) take their
+// residual update from `prec_partial` (the hi/lo side GEMM's planes [n_prec_planes][P][H]) instead of `partial`, and get a
+// second, [hi | lo] (2H wide) copy of the normalised row in `out_hilo[j]`.  prec_of_row == nullptr with out_hilo != nullptr
+// means every row is precise (j = row) and `partial` already is the precise result (single-frame steps).
+struct PreciseRows {
+  const int* prec_of_row = nullptr;
+  const float* prec_partial = nullptr;
+  int n_prec_planes = 0;
+  long long prec_plane_stride = 0;
+  __nv_bfloat16* out_hilo = nullptr;
+};
+
 template <int NT>
 __global__ void resid_add_rmsnorm_kernel(float* __restrict__ resid, const float* __restrict__ partial, int n_planes,
                                          long long plane_stride, const float* __restrict__ w, __nv_bfloat16* __restrict__ out_bf16,
-                                         float* __restrict__ out_f32, int H, float eps) {
+                                         float* __restrict__ out_f32, int H, float eps, PreciseRows pr) {
   extern __shared__ float row_sh[];  // H floats
   __shared__ float red[NT / 32];
   pdl_prologue();
   const long long row = blockIdx.x;
   const int H4 = H >> 2;
+  long long j = -1;
+  if (pr.prec_of_row != nullptr) j = pr.prec_of_row[row];
+  else if (pr.out_hilo != nullptr) j = row;
+  const float* src = partial + row * H;
+  int np = n_planes;
+  long long ps = plane_stride;
+  if (j >= 0 && pr.prec_partial != nullptr) { src = pr.prec_partial + j * H; np = pr.n_prec_planes; ps = pr.prec_plane_stride; }
   float ss = 0.f;
   for (int c = threadIdx.x; c < H4; c += NT) {
     float4 v = reinterpret_cast<float4*>(resid + row * H)[c];
-    for (int p = 0; p < n_planes; ++p) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(partial + p * plane_stride + row * H) + c);
+    for (int p = 0; p < np; ++p) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src + p * ps) + c);
       v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
     }
-    if (n_planes > 0) reinterpret_cast<float4*>(resid + row * H)[c] = v;
+    if (np > 0) reinterpret_cast<float4*>(resid + row * H)[c] = v;
     reinterpret_cast<float4*>(row_sh)[c] = v;
     ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
@@ -351,21 +370,131 @@ __global__ void resid_add_rmsnorm_kernel(float* __restrict__ resid, const float*
     const float4 v = reinterpret_cast<float4*>(row_sh)[c];
     const float4 g = __ldg(reinterpret_cast<const float4*>(w) + c);
     const float o0 = v.x * rstd * g.x, o1 = v.y * rstd * g.y, o2 = v.z * rstd * g.z, o3 = v.w * rstd * g.w;
-    if (out_bf16 != nullptr) {
-      uint2 o;
-      o.x = pack2(o0, o1);
-      o.y = pack2(o2, o3);
-      reinterpret_cast<uint2*>(out_bf16 + row * H)[c] = o;
-    }
+    uint2 o;
+    o.x = pack2(o0, o1);
+    o.y = pack2(o2, o3);
+    if (out_bf16 != nullptr) reinterpret_cast<uint2*>(out_bf16 + row * H)[c] = o;
     if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + row * H)[c] = make_float4(o0, o1, o2, o3);
+    if (j >= 0 && pr.out_hilo != nullptr) {
+      const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.x));
+      const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.y));
+      uint2 l;
+      l.x = pack2(o0 - h0.x, o1 - h0.y);
+      l.y = pack2(o2 - h1.x, o3 - h1.y);
+      uint2* d = reinterpret_cast<uint2*>(pr.out_hilo + j * 2 * H);
+      d[c] = o;
+      d[H4 + c] = l;
+    }
   }
 }
 int launch_resid_add_rmsnorm(float* resid, const float* partial, int n_planes, long long plane_stride, const float* w,
                              __nv_bfloat16* out_bf16, float* out_f32, long long rows, int H, float eps, cudaStream_t s) {
+  return launch_resid_add_rmsnorm_precise(resid, partial, n_planes, plane_stride, w, out_bf16, out_f32, rows, H, eps, nullptr, nullptr, 0,
+                                          0, nullptr, s);
+}
+int launch_resid_add_rmsnorm_precise(float* resid, const float* partial, int n_planes, long long plane_stride, const float* w,
+                                     __nv_bfloat16* out_bf16, float* out_f32, long long rows, int H, float eps, const int* prec_of_row,
+                                     const float* prec_partial, int n_prec_planes, long long prec_plane_stride, __nv_bfloat16* out_hilo,
+                                     cudaStream_t s) {
   if (H % 4 != 0 || rows <= 0) return rows == 0 ? 0 : -2;
   constexpr int NT = 256;
+  PreciseRows pr;
+  pr.prec_of_row = prec_of_row; pr.prec_partial = prec_partial; pr.n_prec_planes = n_prec_planes;
+  pr.prec_plane_stride = prec_plane_stride; pr.out_hilo = out_hilo;
   launch_k(resid_add_rmsnorm_kernel<NT>, dim3((unsigned)rows), dim3(NT), H * sizeof(float), s, resid, partial, n_planes,
-           plane_stride, w, out_bf16, out_f32, H, eps);
+           plane_stride, w, out_bf16, out_f32, H, eps, pr);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Final RMSNorm with the score heads as its epilogue, on the rows that are read only: for each of the `n_score` score rows
+//   r = resid[row] + sum planes (the last down_proj),  n = w * r * rsqrt(mean r^2 + eps)   (model.norm)
+//   logits = n . {informative_head[0], [1], relevance_head[0], [1]}  (fp32),  score = softmax(.)[1] = sigmoid(l1 - l0)
+// (video_head_live_llava_qwen.py:152-161; test/inference.py:243-244), and for each of the `n_lm` lm rows the normalised row as
+// the bf16 operand of lm_head.  No [M, H] hidden-state buffer is written and the other M - n rows are not normalised at all.
+// ------------------------------------------------------------------------------------------------------------
+template <int NT>
+__global__ void final_norm_heads_kernel(const float* __restrict__ resid, const float* __restrict__ partial, int n_planes,
+                                        long long plane_stride, const float* __restrict__ w, const int* __restrict__ score_rows,
+                                        int n_score, const int* __restrict__ lm_rows, const float* __restrict__ head_w,
+                                        float* __restrict__ logits_out, float* __restrict__ scores_out,
+                                        __nv_bfloat16* __restrict__ lm_x, int H, float eps, PreciseRows pr) {
+  extern __shared__ float row_sh[];  // H floats
+  __shared__ float red[NT / 32];
+  __shared__ float hred[4][NT / 32];
+  pdl_prologue();
+  const int b = blockIdx.x;
+  const bool is_score = b < n_score;
+  const long long row = is_score ? score_rows[b] : lm_rows[b - n_score];
+  const int H4 = H >> 2;
+  long long j = pr.prec_of_row != nullptr ? pr.prec_of_row[row] : -1;
+  const float* src = partial + row * H;
+  int np = n_planes;
+  long long ps = plane_stride;
+  if (j >= 0 && pr.prec_partial != nullptr) { src = pr.prec_partial + j * H; np = pr.n_prec_planes; ps = pr.prec_plane_stride; }
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < H4; c += NT) {
+    float4 v = reinterpret_cast<const float4*>(resid + row * H)[c];
+    for (int p = 0; p < np; ++p) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src + p * ps) + c);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
+    reinterpret_cast<float4*>(row_sh)[c] = v;
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  const float rstd = rsqrtf(block_sum<NT>(ss, red) / H + eps);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = threadIdx.x; c < H4; c += NT) {
+    const float4 v = reinterpret_cast<float4*>(row_sh)[c];
+    const float4 g = __ldg(reinterpret_cast<const float4*>(w) + c);
+    const float o0 = v.x * rstd * g.x, o1 = v.y * rstd * g.y, o2 = v.z * rstd * g.z, o3 = v.w * rstd * g.w;
+    if (is_score) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 hw = __ldg(reinterpret_cast<const float4*>(head_w + (long long)k * H) + c);
+        acc[k] = fmaf(o0, hw.x, fmaf(o1, hw.y, fmaf(o2, hw.z, fmaf(o3, hw.w, acc[k]))));
+      }
+    } else {
+      uint2 o;
+      o.x = pack2(o0, o1);
+      o.y = pack2(o2, o3);
+      reinterpret_cast<uint2*>(lm_x + (long long)(b - n_score) * H)[c] = o;
+    }
+  }
+  if (!is_score) return;
+  const int wi = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    acc[k] = warp_sum(acc[k]);
+    if (l == 0) hred[k][wi] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float lg[4];
+    for (int k = 0; k < 4; ++k) {
+      float sacc = 0.f;
+      for (int i = 0; i < NT / 32; ++i) sacc += hred[k][i];
+      lg[k] = sacc;
+      logits_out[b * 4 + k] = sacc;
+    }
+    scores_out[b * 2 + 0] = 1.f / (1.f + expf(lg[0] - lg[1]));
+    scores_out[b * 2 + 1] = 1.f / (1.f + expf(lg[2] - lg[3]));
+  }
+}
+int launch_final_norm_heads(const float* resid, const float* partial, int n_planes, long long plane_stride, const float* w,
+                            const int* score_rows, int n_score, const int* lm_rows, int n_lm, const float* head_w, float* logits_out,
+                            float* scores_out, __nv_bfloat16* lm_x, int H, float eps, const int* prec_of_row, const float* prec_partial,
+                            int n_prec_planes, long long prec_plane_stride, cudaStream_t s) {
+  if (H % 4 != 0 || n_score < 0 || n_lm < 0) return -2;
+  if (n_score + n_lm == 0) return 0;
+  if ((n_score > 0 && (score_rows == nullptr || head_w == nullptr || logits_out == nullptr || scores_out == nullptr)) ||
+      (n_lm > 0 && (lm_rows == nullptr || lm_x == nullptr)))
+    return -2;
+  constexpr int NT = 256;
+  PreciseRows pr;
+  pr.prec_of_row = prec_of_row; pr.prec_partial = prec_partial; pr.n_prec_planes = n_prec_planes; pr.prec_plane_stride = prec_plane_stride;
+  launch_k(final_norm_heads_kernel<NT>, dim3((unsigned)(n_score + n_lm)), dim3(NT), H * sizeof(float), s, resid, partial, n_planes,
+           plane_stride, w, score_rows, n_score, lm_rows, head_w, logits_out, scores_out, lm_x, H, eps, pr);
   return 0;
 }
 

@@ -30,6 +30,7 @@ constexpr int UMMA_K = 16;
 constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quarter, each draining half of the accumulator columns
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2..9 epilogue
 constexpr int SMEM_BUDGET = 227 * 1024;
+constexpr int kMaxDevices = 16;     // per-device "attribute set" flags (power of two)
 
 struct GemmKernelParams {
   int x_rows, y_rows;
@@ -41,12 +42,18 @@ struct GemmKernelParams {
   long long split_stride;
   int pdl_prefetch_x;   // X operand (weights, swap-AB) may be loaded before griddepcontrol.wait
   int x_blocked;        // X/X2 tensor maps are 4-D over the tile-blocked weight layout
+  int y_lo_off;         // HILO kernels: column offset (elements) of the lo half of the [hi | lo] Y operand (= K)
+  int out_hilo;         // EPI_T_SWIGLU: write bf16 hi at [tok, n] and the rounding remainder lo at [tok, x_rows + n]
 };
 
-template <int BN, bool DUAL>
+// HILO: the Y operand (activations, swap-AB) is a bf16 hi+lo pair [hi | lo] (2K wide): every stage carries the hi and the lo
+// k-block of Y next to ONE weight tile and the MMA thread issues both products into the same accumulator, so the weights
+// are streamed (HBM, L2 and shared memory) exactly once while the activation rounding error drops from 2^-9 to 2^-17.
+template <int BN, bool DUAL, bool HILO = false>
 struct GemmCfg {
   static constexpr int X_BYTES = BM * BK * 2;                      // 16 KB
-  static constexpr int Y_BYTES = BN * BK * 2;
+  static constexpr int Y_HALF = BN * BK * 2;
+  static constexpr int Y_BYTES = Y_HALF * (HILO ? 2 : 1);
   static constexpr int STAGE_BYTES = X_BYTES * (DUAL ? 2 : 1) + Y_BYTES;
   static constexpr int ACC_COLS = BN * (DUAL ? 2 : 1);
   static constexpr int TMEM_USED = 2 * ACC_COLS;                   // double-buffered accumulator
@@ -146,11 +153,11 @@ __device__ __forceinline__ void epilogue_normal(const GemmKernelParams& p, uint3
     }
 }
 
-template <int BN, bool DUAL, int EPI, int ACT>
+template <int BN, bool DUAL, int EPI, int ACT, bool HILO = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
                     const __grid_constant__ CUtensorMap tmY, const GemmKernelParams p) {
-  using Cfg = GemmCfg<BN, DUAL>;
+  using Cfg = GemmCfg<BN, DUAL, HILO>;
   constexpr int STAGES = Cfg::STAGES;
   // Tile order: the Y tile index varies fastest.  Swap-AB (weights on X): the CTAs that share a weight tile run at the
   // same time, so the second reader hits L2 instead of streaming the weights twice from HBM.  Normal orientation
@@ -233,6 +240,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         for (int i = 0; i < n_pre; ++i) {
           const uint32_t sY = smem_base + i * Cfg::STAGE_BYTES + Cfg::X_BYTES * (DUAL ? 2 : 1);
           tma_load_2d(sY, &tmY, full_bar(i), pre_kb[i] * BK, pre_yt[i] * BN);
+          if constexpr (HILO) tma_load_2d(sY + Cfg::Y_HALF, &tmY, full_bar(i), p.y_lo_off + pre_kb[i] * BK, pre_yt[i] * BN);
         }
         if (n_pre == STAGES) { stage = 0; phase = 1; } else { stage = n_pre; phase = 0; }
       } else {
@@ -246,6 +254,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         load_x(&tmX, sX, full_bar(stage));
         if constexpr (DUAL) load_x(&tmX2, sX + Cfg::X_BYTES, full_bar(stage));
         tma_load_2d(sY, &tmY, full_bar(stage), kb * BK, yt * BN);
+        if constexpr (HILO) tma_load_2d(sY + Cfg::Y_HALF, &tmY, full_bar(stage), p.y_lo_off + kb * BK, yt * BN);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         advance();
       }
@@ -275,9 +284,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             const uint32_t accum = (kb > kb0 || k > 0) ? 1u : 0u;
             // advancing K inside the 128-B swizzle atom = +32 B on the start address (encoded >> 4)
             umma_f16(d_tmem, dX + 2u * k, dY + 2u * k, idesc, accum);
+            if constexpr (HILO) umma_f16(d_tmem, dX + 2u * k, umma_desc_k_sw128(sY + Cfg::Y_HALF) + 2u * k, idesc, 1u);
             if constexpr (DUAL) {
               const uint64_t dX2 = umma_desc_k_sw128(sX + Cfg::X_BYTES);
               umma_f16(d_tmem + BN, dX2 + 2u * k, dY + 2u * k, idesc, accum);
+              if constexpr (HILO) umma_f16(d_tmem + BN, dX2 + 2u * k, umma_desc_k_sw128(sY + Cfg::Y_HALF) + 2u * k, idesc, 1u);
             }
           }
           umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
@@ -373,7 +384,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
                 const float gv = __uint_as_float(g[j]);
                 const float uv = __uint_as_float(u[j]);
                 const float s = gv / (1.0f + __expf(-gv));
-                outp[(long long)tok * p.ldo + xi] = __float2bfloat16_rn(s * uv);
+                const __nv_bfloat16 hi = __float2bfloat16_rn(s * uv);
+                outp[(long long)tok * p.ldo + xi] = hi;
+                if (p.out_hilo) outp[(long long)tok * p.ldo + p.x_rows + xi] = __float2bfloat16_rn(s * uv - __bfloat162float(hi));
               }
             }
           }
@@ -827,15 +840,16 @@ int gemm_effective_splits(int K, int k_splits) {
   return (kb_total + per - 1) / per;
 }
 
-template <int BN, bool DUAL, int EPI, int ACT>
+template <int BN, bool DUAL, int EPI, int ACT, bool HILO = false>
 static int launch_cfg(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, DUAL>;
-  auto kern = gemm_tcgen05_kernel<BN, DUAL, EPI, ACT>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  using Cfg = GemmCfg<BN, DUAL, HILO>;
+  auto kern = gemm_tcgen05_kernel<BN, DUAL, EPI, ACT, HILO>;
+  if (HILO && (a.K % BK != 0 || a.ldy < 2 * (int64_t)a.K)) { g_gemm_err = "hi/lo Y operand needs K % 64 == 0 and ldy >= 2K"; return -2; }
+  static bool attr_set[kMaxDevices] = {};  // per instantiation and per device (the attribute is per device)
+  if (!attr_set[c->device & (kMaxDevices - 1)]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { g_gemm_err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return -4; }
-    attr_set = true;
+    attr_set[c->device & (kMaxDevices - 1)] = true;
   }
   CUtensorMap tmX, tmX2, tmY;
   int rc;
@@ -848,9 +862,10 @@ static int launch_cfg(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
     if (DUAL) { if ((rc = get_map(c, a.X2, a.x_rows, a.K, a.ldx, BM, &tmX2)) != 0) return rc; }
     else tmX2 = tmX;
   }
-  if ((rc = get_map(c, a.Y, a.y_rows, a.K, a.ldy, BN, &tmY)) != 0) return rc;
+  if ((rc = get_map(c, a.Y, a.y_rows, HILO ? 2 * a.K : a.K, a.ldy, BN, &tmY)) != 0) return rc;
 
   GemmKernelParams p;
+  p.y_lo_off = a.K; p.out_hilo = a.out_hilo;
   p.x_rows = a.x_rows; p.y_rows = a.y_rows;
   p.x_tiles = (a.x_rows + BM - 1) / BM;
   p.y_tiles = (a.y_rows + BN - 1) / BN;
@@ -877,11 +892,11 @@ template <int BN2, int EPI, int ACT>
 static int launch_2cta(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN2>;
   auto kern = gemm_tcgen05_2cta_kernel<BN2, EPI, ACT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[kMaxDevices] = {};
+  if (!attr_set[c->device & (kMaxDevices - 1)]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { g_gemm_err = std::string("cudaFuncSetAttribute(2cta): ") + cudaGetErrorString(e); return -4; }
-    attr_set = true;
+    attr_set[c->device & (kMaxDevices - 1)] = true;
   }
   CUtensorMap tmA, tmB, tmOut;
   int rc;
@@ -962,6 +977,12 @@ int gemm_launch(GemmContext* c, const GemmArgs& a, cudaStream_t s) {
     case EPI_RESID_F32: return launch_normal<EPI_RESID_F32, ACT_NONE>(c, a, s);
     case EPI_F32: return launch_normal<EPI_F32, ACT_NONE>(c, a, s);
     case EPI_T_F32:
+      if (a.y_hilo) {
+        if (a.y_rows <= 64) return launch_cfg<64, false, EPI_T_F32, ACT_NONE, true>(c, a, s);
+        if (a.y_rows <= 128) return launch_cfg<128, false, EPI_T_F32, ACT_NONE, true>(c, a, s);
+        g_gemm_err = "hi/lo activations: at most 128 rows per launch";
+        return -2;
+      }
       if (a.y_rows <= 64) return launch_cfg<64, false, EPI_T_F32, ACT_NONE>(c, a, s);
       if (a.y_rows <= 128) return launch_cfg<128, false, EPI_T_F32, ACT_NONE>(c, a, s);
       return launch_cfg<256, false, EPI_T_F32, ACT_NONE>(c, a, s);
@@ -970,6 +991,12 @@ int gemm_launch(GemmContext* c, const GemmArgs& a, cudaStream_t s) {
       return launch_cfg<256, false, EPI_T_SWIGLU_IL, ACT_NONE>(c, a, s);
     case EPI_T_SWIGLU:
       if (a.X2 == nullptr) { g_gemm_err = "swiglu gemm needs X2"; return -2; }
+      if (a.y_hilo) {
+        if (a.y_rows <= 64) return launch_cfg<64, true, EPI_T_SWIGLU, ACT_NONE, true>(c, a, s);
+        if (a.y_rows <= 128) return launch_cfg<128, true, EPI_T_SWIGLU, ACT_NONE, true>(c, a, s);
+        g_gemm_err = "hi/lo activations: at most 128 rows per launch";
+        return -2;
+      }
       if (a.y_rows <= 64) return launch_cfg<64, true, EPI_T_SWIGLU, ACT_NONE>(c, a, s);
       return launch_cfg<128, true, EPI_T_SWIGLU, ACT_NONE>(c, a, s);
     default: break;

@@ -41,6 +41,10 @@ struct GemmArgs {
   int64_t split_stride = 0;           // elements between partial planes
   int max_ctas = 0;                   // 0 = number of SMs
   int force_2cta = 0;                 // use the CTA-pair kernel even for M < 1024 (decoder passes with >= ~200 tokens)
+  // swap-AB kernels (EPI_T_F32 / EPI_T_SWIGLU), at most 128 Y rows: Y is a bf16 hi+lo pair [hi | lo] of width 2K (ldy >= 2K);
+  // each weight tile is multiplied with both halves into the same accumulator ("precise rows")
+  int y_hilo = 0;
+  int out_hilo = 0;                   // EPI_T_SWIGLU: out row = [hi | lo], lo at column x_rows (ldo >= 2 * x_rows)
 };
 
 struct GemmContext;  // tensor-map cache + device properties

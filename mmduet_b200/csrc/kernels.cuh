@@ -20,6 +20,16 @@ int launch_resid_add_layernorm(float* x, const float* planes, int n_planes, long
                                cudaStream_t s);
 int launch_resid_add_rmsnorm(float* resid, const float* partial, int n_planes, long long plane_stride, const float* w,
                              __nv_bfloat16* out_bf16, float* out_f32, long long rows, int H, float eps, cudaStream_t s);
+// the same with "precise rows": see elementwise.cu (PreciseRows)
+int launch_resid_add_rmsnorm_precise(float* resid, const float* partial, int n_planes, long long plane_stride, const float* w,
+                                     __nv_bfloat16* out_bf16, float* out_f32, long long rows, int H, float eps, const int* prec_of_row,
+                                     const float* prec_partial, int n_prec_planes, long long prec_plane_stride, __nv_bfloat16* out_hilo,
+                                     cudaStream_t s);
+// final RMSNorm fused with the informative/relevance heads on the score rows (+ bf16 normalised rows for lm_head)
+int launch_final_norm_heads(const float* resid, const float* partial, int n_planes, long long plane_stride, const float* w,
+                            const int* score_rows, int n_score, const int* lm_rows, int n_lm, const float* head_w, float* logits_out,
+                            float* scores_out, __nv_bfloat16* lm_x, int H, float eps, const int* prec_of_row, const float* prec_partial,
+                            int n_prec_planes, long long prec_plane_stride, cudaStream_t s);
 int launch_qkv_finish(const float* partial, int n_planes, long long plane_stride, const float* bias, const float* cos_tab,
                       const float* sin_tab, const int* tok_pos, const int* tok_slot, __nv_bfloat16* q_out,
                       __nv_bfloat16* kv_layer, int M, int Hq, int Hkv, int dh, int page_tokens, cudaStream_t s);

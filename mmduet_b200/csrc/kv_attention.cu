@@ -322,10 +322,10 @@ int launch_kv_attention(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, c
   if (n_streams <= 0 || total_q <= 0) return 0;
   if (dh != KA_DH || page_tokens != KA_BN || Hq % Hkv != 0 || n_splits < 1 || n_splits > 32) return -2;   // combine: one lane per split
   constexpr int SMEM = (KA_BM + 4 * KA_BN) * KA_LDS * 2;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceFlag attr;
+  if (!attr.cur()) {
     if (cudaFuncSetAttribute(kv_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return -4;
-    attr = true;
+    attr.cur() = true;
   }
   const int G = Hq / Hkv;
   const int q_tiles = (max_n_q * G + KA_BM - 1) / KA_BM;

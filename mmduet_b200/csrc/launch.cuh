@@ -7,6 +7,17 @@ namespace mmd {
 
 extern thread_local bool g_use_pdl;
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: "already done" flags are kept per device of the
+// calling thread (one mmd_ctx per device may live in one process).
+struct PerDeviceFlag {
+  bool set[16] = {};
+  bool& cur() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return set[d & 15];
+  }
+};
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg = {};

@@ -5,6 +5,7 @@
 // registers with warp-shuffle row reductions.  head_dim 72 is padded to 80 in shared memory (zero columns).
 // TODO(perf): tcgen05/TMEM variant; this kernel is ~10% of the ViT FLOPs.
 #include "kernels.cuh"
+#include "launch.cuh"
 
 #include <cuda_bf16.h>
 #include <math.h>
@@ -236,11 +237,11 @@ int launch_vit_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int T, in
   if (dh != 72) return -2;  // SigLIP-so400m head_dim; other sizes need another instantiation
   constexpr int DH = 72, DPAD = 80, LDS = 88;
   constexpr int SMEM = (VA_BM + 4 * VA_BN) * LDS * 2;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceFlag attr;
+  if (!attr.cur()) {
     if (cudaFuncSetAttribute(vit_attention_kernel<DH, DPAD, LDS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return -4;
     if (cudaFuncSetAttribute(vit_attention_kernel<DH, DPAD, LDS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return -4;
-    attr = true;
+    attr.cur() = true;
   }
   dim3 grid((S + VA_BM - 1) / VA_BM, H, T);
   const float scale_log2e = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;

@@ -451,7 +451,17 @@ class DecoderEngine:
                 max_n_q, max_kv = max(max_n_q, n_q), max(max_kv, new_len)
             M = q_start
             self._ensure_ws(M, len(lm_rows))
-            meta = np.asarray(src_row + tok_pos + tok_slot + desc + tables + score_rows + lm_rows, dtype=np.int32)
+            # "precise rows" (csrc/api.cu): passes above 128 tokens re-run gate/up + down on bf16 hi+lo operands for the rows
+            # whose outputs are read; shorter passes carry every row as hi+lo inside the main kernels
+            prec = sorted(set(score_rows) | set(lm_rows)) if M > 128 else []
+            if not (1 <= len(prec) <= 128):
+                prec = []
+            prec_of_row = []
+            if prec:
+                prec_of_row = [-1] * M
+                for j, r in enumerate(prec):
+                    prec_of_row[r] = j
+            meta = np.asarray(src_row + tok_pos + tok_slot + desc + tables + score_rows + lm_rows + prec + prec_of_row, dtype=np.int32)
             meta_d = self._meta_upload(meta)
             base = meta_d.data_ptr()
             o = 0
@@ -464,6 +474,7 @@ class DecoderEngine:
             p_src, p_pos, p_slot = seg(M), seg(M), seg(M)
             p_desc, p_tab = seg(len(desc)), seg(len(tables))
             p_score, p_lm = seg(len(score_rows)), seg(len(lm_rows))
+            p_prec, p_prec_of = seg(len(prec)), seg(len(prec_of_row))
             if emb_chunks:
                 frame_tokens = emb_chunks[0] if len(emb_chunks) == 1 else torch.cat(emb_chunks, 0)
                 frame_tokens = frame_tokens.contiguous()
@@ -476,7 +487,8 @@ class DecoderEngine:
             step = _lib.Step(n_tokens=M, src_row=p_src, frame_tokens=_lib.ptr(frame_tokens), tok_pos=p_pos, tok_slot=p_slot,
                              n_streams=len(items), stream_desc=p_desc, block_tables=p_tab, max_n_q=max_n_q, max_kv_len=max_kv,
                              n_score_rows=n_s, score_rows=p_score, head_logits_out=head_logits.data_ptr(), scores_out=scores.data_ptr(),
-                             n_lm_rows=n_l, lm_rows=p_lm, lm_logits_out=_lib.ptr(lm_logits))
+                             n_lm_rows=n_l, lm_rows=p_lm, lm_logits_out=_lib.ptr(lm_logits),
+                             n_prec_rows=len(prec), prec_rows=p_prec if prec else 0, prec_of_row=p_prec_of if prec else 0)
             rc = self.lib.mmd_decoder_step(self.ctx, ctypes.byref(self.w), ctypes.byref(self.kv), ctypes.byref(step), self._ws.data_ptr(),
                                            self._ws.numel(), _lib.stream_ptr())
             _lib.check(rc, "mmd_decoder_step")

@@ -124,3 +124,47 @@ def gemm_swiglu_pair(x, w_il, out=None):
                            2 * N, w_il.stride(0), K, 0, out.data_ptr(), out.stride(0), 1, 0, _lib.stream_ptr())
     _lib.check(rc, "mmd_gemm_bf16(SWIGLU_PAIR)")
     return out
+
+
+def split_hilo(x):
+    """fp32 [M, K] -> bf16 [M, 2K] = [hi | lo] with hi = bf16(x), lo = bf16(x - hi) (plumbing for the tests; on the path the
+    RMSNorm / SwiGLU epilogues write this layout themselves)."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo], 1).contiguous()
+
+
+def gemm_t_partials_hilo(x2, w, k_splits, out=None):
+    """Swap-AB split-K on a hi+lo activation pair x2 [M <= 128, 2K]: fp32 planes [splits, M, N] of (hi + lo) @ w[N,K]^T."""
+    _chk2d(x2, torch.bfloat16)
+    _chk2d(w, torch.bfloat16)
+    M, K = x2.shape[0], w.shape[1]
+    assert x2.shape[1] == 2 * K
+    N = w.shape[0]
+    lib = _lib.load()
+    splits = lib.mmd_gemm_splits(K, k_splits)
+    if out is None:
+        out = torch.empty(splits, M, N, device=x2.device, dtype=torch.float32)
+    rc = lib.mmd_gemm_bf16(_lib.context(x2.device.index), EPI_T_F32 | _lib.GEMM_Y_HILO, ACT_NONE, w.data_ptr(), 0, N, w.stride(0),
+                           x2.data_ptr(), M, x2.stride(0), K, 0, out.data_ptr(), out.stride(1), k_splits, out.stride(0), _lib.stream_ptr())
+    _lib.check(rc, "mmd_gemm_bf16(T_F32 | Y_HILO)")
+    return out
+
+
+def gemm_t_swiglu_hilo(x2, w_il, out=None):
+    """Swap-AB fused SwiGLU on a hi+lo activation pair x2 [M <= 128, 2K] against the interleaved gate/up matrix w_il [2N, K]
+    (row 2j = gate_j, 2j+1 = up_j); the output is a hi+lo pair too: [M, 2N] = [bf16(v) | bf16(v - bf16(v))]."""
+    _chk2d(x2, torch.bfloat16)
+    _chk2d(w_il, torch.bfloat16)
+    M, K = x2.shape[0], w_il.shape[1]
+    assert x2.shape[1] == 2 * K
+    N = w_il.shape[0] // 2
+    if out is None:
+        out = torch.empty(M, 2 * N, device=x2.device, dtype=torch.bfloat16)
+    lib = _lib.load()
+    up = w_il[1:]     # up rows start one row further; both operands use row stride 2K
+    rc = lib.mmd_gemm_bf16(_lib.context(x2.device.index), EPI_T_SWIGLU | _lib.GEMM_Y_HILO | _lib.GEMM_OUT_HILO, ACT_NONE, w_il.data_ptr(),
+                           up.data_ptr(), N, 2 * w_il.stride(0), x2.data_ptr(), M, x2.stride(0), K, 0, out.data_ptr(), out.stride(0), 1, 0,
+                           _lib.stream_ptr())
+    _lib.check(rc, "mmd_gemm_bf16(T_SWIGLU | Y_HILO | OUT_HILO)")
+    return out

@@ -165,3 +165,170 @@ def build_reference_model(arch, state_dict=None, dtype=torch.float32, seed=1234)
     model = model.to(dtype).eval()
     model.requires_grad_(False)
     return model
+
+
+# ------------------------------------------------------------------------------------------------------------
+# The reference's OWN frame-loop classes (test/inference.py:20-313 LiveInferForBenchmark, demo/liveinfer.py:60-105
+# LiveInferForDemo) on CPU.  Extra shims, none of which touches the loop's logic:
+#   4. `llava.mm_utils / llava.model.builder / llava.constants / llava.conversation` (test/inference.py:11-14): imported at
+#      module level, never used by the live loop -> empty name stubs.
+#   5. `models.build_model_and_tokenizer` (test/inference.py:16,24) returns the model from build_reference_model() and the
+#      tokenizer handed to build_reference_loop(), instead of downloading lmms-lab/llava-onevision-qwen2-7b-ov.
+#   6. device: the loop hard-codes 'cuda' (torch.zeros(..., device='cuda'), .to('cuda')).  The module's `torch` global is
+#      replaced by a forwarding proxy that maps device='cuda' to 'cpu' for torch.zeros / torch.tensor, and tensors that
+#      the loop moves with .to('cuda') (tokenizer output, pixel values) are a Tensor subclass whose .to() does the same.
+#   7. cache semantics of the PINNED transformers==4.44.2 (requirements.txt:41): with past_key_values=None on the first
+#      call, Qwen2Model returns LEGACY TUPLE caches (immutable: every forward builds a new tuple), which is what makes
+#      `remove_assistant_turns` a rollback when the cache returned by fast_greedy_generate is dropped
+#      (test/inference.py:265-269).  The installed transformers 5.5 mutates a DynamicCache in place, so
+#      the model handed to the loop copies the cache it is given before each forward (LegacyCacheModel).
+#   8. LLaVA's SigLipImageProcessor (get_vision_tower().image_processor, test/inference.py:27,203) restated for frames
+#      that are already 384x384: rescale 1/255, normalise mean = std = 0.5 [recalled from
+#      llava/model/multimodal_encoder/siglip_encoder.py, unpinned].
+# ------------------------------------------------------------------------------------------------------------
+class CpuTensor(torch.Tensor):
+    """A tensor whose .to('cuda') / .cuda() stay on the CPU (shim 6)."""
+
+    def to(self, *args, **kwargs):
+        args = tuple("cpu" if (isinstance(a, str) and a.startswith("cuda")) else a for a in args)
+        if isinstance(kwargs.get("device"), str) and kwargs["device"].startswith("cuda"):
+            kwargs["device"] = "cpu"
+        return super().to(*args, **kwargs)
+
+    def cuda(self, *a, **k):
+        return self
+
+
+def as_cpu_tensor(t):
+    return t.as_subclass(CpuTensor)
+
+
+class _TorchProxy:
+    """Forwards everything to torch; zeros / tensor with device='cuda' are created on the CPU (shim 6)."""
+
+    def __init__(self):
+        self.__dict__["_t"] = torch
+
+    def __getattr__(self, name):
+        return getattr(self._t, name)
+
+    @staticmethod
+    def _dev(kwargs):
+        if isinstance(kwargs.get("device"), str) and kwargs["device"].startswith("cuda"):
+            kwargs["device"] = "cpu"
+        return kwargs
+
+    def zeros(self, *a, **k):
+        return torch.zeros(*a, **self._dev(k))
+
+    def tensor(self, *a, **k):
+        return torch.tensor(*a, **self._dev(k))
+
+
+class SigLipImageProcessorStub:
+    """Shim 8."""
+    image_mean, image_std, rescale_factor, size = (0.5, 0.5, 0.5), (0.5, 0.5, 0.5), 0.00392156862745098, (384, 384)
+
+    def preprocess(self, images, return_tensors="pt"):
+        x = torch.as_tensor(images)
+        assert tuple(x.shape[-2:]) == self.size, "the stub only handles frames already padded to 384x384 (test/datasets.py)"
+        x = (x.float() * self.rescale_factor - 0.5) / 0.5
+        return {"pixel_values": as_cpu_tensor(x)}
+
+
+class TokenizerOnCpu:
+    """Wraps any tokenizer: apply_chat_template(..., return_tensors='pt') returns the ids as a [1, n] CpuTensor, the
+    transformers==4.44.2 return type (5.x returns a BatchEncoding unless return_dict=False)."""
+
+    def __init__(self, tok):
+        self._tok = tok
+
+    def __getattr__(self, name):
+        return getattr(self._tok, name)
+
+    def apply_chat_template(self, conversation, **kw):
+        try:
+            out = self._tok.apply_chat_template(conversation, return_dict=False, **kw)
+        except TypeError:
+            out = self._tok.apply_chat_template(conversation, **kw)
+        if not torch.is_tensor(out):
+            out = torch.as_tensor(out["input_ids"] if hasattr(out, "keys") else out, dtype=torch.long)
+        return as_cpu_tensor(out.view(1, -1))
+
+
+class LegacyCacheModel:
+    """Shim 7: hands the reference loop a model whose returned caches are never mutated by later calls."""
+
+    def __init__(self, model):
+        self.__dict__["_m"] = model
+
+    def __getattr__(self, name):
+        return getattr(self._m, name)
+
+    def eval(self):
+        self._m.eval()
+        return self
+
+    def __call__(self, *args, past_key_values=None, **kwargs):
+        import copy
+        if past_key_values is not None:
+            past_key_values = copy.deepcopy(past_key_values)
+        return self._m(*args, past_key_values=past_key_values, **kwargs)
+
+
+def import_reference_loop():
+    """Returns (test.inference, demo.liveinfer) of the reference, importable on CPU."""
+    _, ml, vh = import_reference()
+    for name in ("llava.mm_utils", "llava.model.builder", "llava.constants", "llava.conversation"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["llava.mm_utils"].tokenizer_image_token = None
+    sys.modules["llava.model.builder"].load_pretrained_model = None
+    sys.modules["llava.constants"].IMAGE_TOKEN_INDEX, sys.modules["llava.constants"].DEFAULT_IMAGE_TOKEN = -200, "<image>"
+    sys.modules["llava.conversation"].conv_templates = {}
+    sys.modules["peft"].PeftModel = getattr(sys.modules["peft"], "PeftModel")
+    models = sys.modules["models"]
+    models.fast_greedy_generate = ml.fast_greedy_generate
+    models.parse_args = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("CLI parsing is not part of the loop"))
+    if not hasattr(models, "build_model_and_tokenizer"):
+        models.build_model_and_tokenizer = lambda **k: (_ for _ in ()).throw(RuntimeError("use build_reference_loop()"))
+    for pkg in ("test", "demo"):
+        if pkg not in sys.modules or not getattr(sys.modules[pkg], "__oracle_shim__", False):
+            m = types.ModuleType(pkg)
+            m.__path__ = [os.path.join(REFERENCE_ROOT, pkg)]
+            m.__oracle_shim__ = True
+            sys.modules[pkg] = m
+    import importlib
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ti = importlib.import_module("test.inference")
+        dl = importlib.import_module("demo.liveinfer")
+    proxy = _TorchProxy()
+    ti.torch = proxy
+    dl.torch = proxy
+    return ti, dl
+
+
+def build_reference_loop(arch, state_dict, tokenizer, args, demo=False, dtype=torch.float32):
+    """The reference's LiveInferForBenchmark / LiveInferForDemo (unmodified class bodies) over the reference's own model class
+    with `state_dict`, on CPU.  `args`: any dataclass with the reference's flag names (mmduet_b200.arguments_live.
+    LiveTestArguments has the same names and defaults); bf16/fp16 are forced off so the loop runs in `dtype`."""
+    import contextlib
+    import dataclasses
+    import io
+    ti, dl = import_reference_loop()
+    model = build_reference_model(arch, state_dict, dtype=dtype)
+    model.get_vision_tower().image_processor = SigLipImageProcessorStub()
+    model.config.eos_token_id = getattr(tokenizer, "eos_token_id", None)
+    wrapped = LegacyCacheModel(model)
+    tok = TokenizerOnCpu(tokenizer)
+    sys.modules["models"].build_model_and_tokenizer = lambda **k: (wrapped, tok)
+    ti.build_model_and_tokenizer = sys.modules["models"].build_model_and_tokenizer
+    args = dataclasses.replace(args, bf16=False, fp16=False)
+    cls = dl.LiveInferForDemo if demo else ti.LiveInferForBenchmark
+    with contextlib.redirect_stdout(io.StringIO()):
+        loop = cls(args)
+    assert loop.torch_dtype == torch.float32
+    loop.torch_dtype = dtype
+    return loop

@@ -128,6 +128,89 @@ def test_gemm_swiglu_pair(env, M, N, K):
     assert ((out.float() - alt.float()).abs() / (1 + ref.abs())).max() < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K,splits", [(49, 4608, 3584, 4), (81, 3584, 18944, 5), (1, 3584, 18944, 6), (128, 896, 2432, 2),
+                                           (40, 3584, 18944, 8), (7, 512, 256, 1)])
+def test_gemm_hilo_activations(env, M, N, K, splits):
+    """Swap-AB split-K with the activations as a bf16 hi+lo pair (the 'precise rows' operand form): the result must be the
+    product with the UNROUNDED fp32 activations to ~2^-17, i.e. far closer than the plain bf16-operand product."""
+    _lib, ops, lib, ctx = env
+    torch.manual_seed(M + N + K)
+    x = torch.randn(M, K, device="cuda") * 0.5
+    w = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
+    ref = x.double() @ w.double().t()
+    parts = ops.gemm_t_partials_hilo(ops.split_hilo(x), w, splits)
+    err = (parts.sum(0).double() - ref).abs().max().item()
+    plain = (ops.gemm_t_partials(x.bfloat16(), w, splits).sum(0).double() - ref).abs().max().item()
+    assert err < 2e-4, err
+    assert err < plain / 20, (err, plain)
+
+
+@pytest.mark.parametrize("M,N,K", [(49, 18944, 3584), (40, 18944, 3584), (128, 2432, 896), (1, 512, 256), (100, 1216, 896)])
+def test_gemm_swiglu_hilo(env, M, N, K):
+    """Fused SwiGLU on hi+lo activations with a hi+lo output pair (gate/up of the precise rows)."""
+    _lib, ops, lib, ctx = env
+    torch.manual_seed(M + N)
+    x = torch.randn(M, K, device="cuda") * 0.5
+    wg, wu = (torch.randn(N, K, device="cuda") * 0.05).bfloat16(), (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
+    w_il = torch.stack([wg, wu], 1).reshape(2 * N, K).contiguous()
+    out = torch.full((M, 2 * N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.gemm_t_swiglu_hilo(ops.split_hilo(x), w_il, out=out)
+    g, u = x.double() @ wg.double().T, x.double() @ wu.double().T
+    ref = torch.nn.functional.silu(g) * u
+    got = out[:, :N].double() + out[:, N:].double()
+    assert torch.isfinite(got).all()
+    assert ((got - ref).abs() / (1 + ref.abs())).max() < 3e-4            # __expf + hi/lo remainder, no operand rounding
+    assert torch.equal(out[:, :N], got.float().bfloat16()) or ((out[:, :N].double() - ref).abs() / (1 + ref.abs())).max() < 1e-2
+
+
+def test_rmsnorm_precise_rows_and_final_norm_heads(env):
+    _lib, ops, lib, ctx = env
+    rows, H, planes, P = 150, 3584, 3, 5
+    torch.manual_seed(1)
+    resid = torch.randn(rows, H, device="cuda")
+    parts = torch.randn(planes, rows, H, device="cuda")
+    pparts = torch.randn(2, P, H, device="cuda")
+    w = torch.randn(H, device="cuda")
+    prec_rows = torch.tensor([3, 48, 97, 98, 149], device="cuda", dtype=torch.int32)
+    prec_of = torch.full((rows,), -1, device="cuda", dtype=torch.int32)
+    prec_of[prec_rows.long()] = torch.arange(P, device="cuda", dtype=torch.int32)
+    want_res = resid + parts.sum(0)
+    want_res[prec_rows.long()] = resid[prec_rows.long()] + pparts.sum(0)
+    want = want_res * torch.rsqrt(want_res.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+    r = resid.clone()
+    ob = torch.empty(rows, H, device="cuda", dtype=torch.bfloat16)
+    o2 = torch.full((P, 2 * H), float("nan"), device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.mmd_resid_add_rmsnorm_precise(r.data_ptr(), parts.data_ptr(), planes, parts.stride(0), w.data_ptr(), ob.data_ptr(), 0, rows,
+                                                 H, 1e-6, prec_of.data_ptr(), pparts.data_ptr(), 2, pparts.stride(0), o2.data_ptr(), _s()))
+    assert (r - want_res).abs().max() < 1e-5
+    assert (ob.float() - want).abs().max() < 5e-2
+    hl = o2[:, :H].float() + o2[:, H:].float()
+    assert (hl - want[prec_rows.long()]).abs().max() < 2e-4
+    assert torch.equal(o2[:, :H], ob[prec_rows.long()])
+    # every row precise (single-frame steps): prec_of_row NULL, out_hilo set, no separate precise planes
+    r2 = resid.clone()
+    o3 = torch.empty(rows, 2 * H, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.mmd_resid_add_rmsnorm_precise(r2.data_ptr(), parts.data_ptr(), planes, parts.stride(0), w.data_ptr(), 0, 0, rows, H, 1e-6,
+                                                 0, 0, 0, 0, o3.data_ptr(), _s()))
+    full_res = resid + parts.sum(0)
+    full = full_res * torch.rsqrt(full_res.pow(2).mean(-1, keepdim=True) + 1e-6) * w
+    assert (o3[:, :H].float() + o3[:, H:].float() - full).abs().max() < 2e-4
+    # final norm + heads on three score rows (one precise, two not) and two lm rows
+    hw = torch.randn(4, H, device="cuda") * 0.02
+    srows = torch.tensor([48, 10, 149], device="cuda", dtype=torch.int32)
+    lrows = torch.tensor([149, 0], device="cuda", dtype=torch.int32)
+    logits, scores = torch.empty(3, 4, device="cuda"), torch.empty(3, 2, device="cuda")
+    lm_x = torch.empty(2, H, device="cuda", dtype=torch.bfloat16)
+    _lib.check(lib.mmd_final_norm_heads(resid.data_ptr(), parts.data_ptr(), planes, parts.stride(0), w.data_ptr(), srows.data_ptr(), 3,
+                                        lrows.data_ptr(), 2, hw.data_ptr(), logits.data_ptr(), scores.data_ptr(), lm_x.data_ptr(), H, 1e-6,
+                                        prec_of.data_ptr(), pparts.data_ptr(), 2, pparts.stride(0), _s()))
+    ref_l = want[srows.long()] @ hw.t()
+    assert (logits - ref_l).abs().max() < 1e-4
+    assert (scores[:, 0] - ref_l[:, :2].softmax(-1)[:, 1]).abs().max() < 1e-5
+    assert (scores[:, 1] - ref_l[:, 2:].softmax(-1)[:, 1]).abs().max() < 1e-5
+    assert (lm_x.float() - want[lrows.long()]).abs().max() < 5e-2
+
+
 @pytest.mark.parametrize("dtype,normalize", [(torch.uint8, True), (torch.float32, False), (torch.bfloat16, False), (torch.float32, True)])
 def test_im2col(env, dtype, normalize):
     _lib, ops, lib, ctx = env
