@@ -21,6 +21,8 @@ def build_model_and_tokenizer(is_training=False, *, state_dict=None, model_confi
     cfg = model_config or ModelConfig()
     if tokenizer is None:
         tokenizer = SyntheticTokenizer(cfg.vocab)
+    # what build_live_tokenizer_and_update_config writes into the model config (models/tokenization_live.py:118-124)
+    v_id = tokenizer.convert_tokens_to_ids("<image>") if hasattr(tokenizer, "convert_tokens_to_ids") else None
     model = VideoHeadLiveLlavaQwenForCausalLM(cfg, state_dict, device=device, max_context=max_context, kv_pages=kv_pages,
-                                              eos_token_id=getattr(tokenizer, "eos_token_id", None))
+                                              eos_token_id=getattr(tokenizer, "eos_token_id", None), v_placeholder_id=v_id)
     return model, tokenizer

@@ -103,6 +103,7 @@ class PeerStoreEncoder:
         self.hdl = symm.rendezvous(self.buf, self.group)
         # the owner's buffer as seen from this rank (a peer mapping unless this rank is the owner)
         self.dst = self.buf if self.rank == owner else self.hdl.get_buffer(owner, tuple(self.buf.shape), dtype)
+        self._pending = {}                 # owner: signals of the previous encode() that nobody has waited on yet
 
     N_CHANNELS = 15          # signal channels 1..15 (0 is the barrier's); the signal pad holds world x channels words
 
@@ -117,6 +118,13 @@ class PeerStoreEncoder:
         assert n_frames <= self.max_frames
         lo, hi = frame_range(n_frames, self.world, self.rank)
         assert len(local_frames) == hi - lo, (len(local_frames), lo, hi)
+        # Signals of the previous video that the owner never consumed (it stopped early, or never called its ready[i]) would
+        # satisfy THIS video's waits before the data has landed, and a producer's put_signal blocks on a channel that is
+        # still set: consume them first.  Every producer always posts all of its signals, so these waits terminate.
+        for src, batches in self._pending.items():
+            for _, _, ch in batches:
+                self.hdl.wait_signal(src, channel=ch)
+        self._pending = {}
         # nobody may overwrite the owner's buffer while it is still decoding the previous video
         self.hdl.barrier(channel=0)
         for n, b0 in enumerate(range(lo, hi, self.batch)):
@@ -134,6 +142,7 @@ class PeerStoreEncoder:
             if src != self.owner:
                 s_lo, s_hi = frame_range(n_frames, self.world, src)
                 pending[src] = [(b0, min(b0 + self.batch, s_hi), self._channel(n)) for n, b0 in enumerate(range(s_lo, s_hi, self.batch))]
+        self._pending = pending
 
         def ready_fn(i):
             def wait():

@@ -11,11 +11,14 @@ import torch
 
 
 class SyntheticTokenizer:
-    IM_START, IM_END, NEWLINE = 3, 4, 5
+    IM_START, IM_END, NEWLINE, IMAGE = 3, 4, 5, 6      # IMAGE = the '<image>' frame placeholder (config.v_placeholder_id)
 
     def __init__(self, vocab_size, eos_token_id=None):
         self.vocab_size = vocab_size
         self.eos_token_id = self.IM_END if eos_token_id is None else eos_token_id
+
+    def convert_tokens_to_ids(self, token):
+        return {"<|im_start|>": self.IM_START, "<|im_end|>": self.IM_END, "<image>": self.IMAGE}.get(token)
 
     def _words(self, text):
         lo, span = 16, max(self.vocab_size - 16, 1)

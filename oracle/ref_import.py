@@ -149,6 +149,12 @@ def build_reference_model(arch, state_dict=None, dtype=torch.float32, seed=1234)
         video_pooling_stride=arch.pool_stride, frame_num_tokens=arch.frame_tokens,
         frame_resolution=arch.image_size)
     cfg.mm_spatial_pool_mode = arch.pool_mode
+    # fields VideoHeadLiveConfigMixin.__init__ sets from the CLI flags (configuration_live.py:21-35); the installed
+    # transformers' Qwen2Config does not chain to the mixin's __init__, so they are set here
+    for k, v in dict(frame_num_tokens=arch.frame_tokens, frame_resolution=arch.image_size, v_placeholder="<image>",
+                     v_placeholder_id=None, frame_token_cls=False, frame_token_pooled=[7, 7]).items():
+        if getattr(cfg, k, None) is None:
+            setattr(cfg, k, v)
     cfg.oracle_vision_config = vcfg
     torch.manual_seed(seed)
     import contextlib
@@ -170,8 +176,9 @@ def build_reference_model(arch, state_dict=None, dtype=torch.float32, seed=1234)
 # ------------------------------------------------------------------------------------------------------------
 # The reference's OWN frame-loop classes (test/inference.py:20-313 LiveInferForBenchmark, demo/liveinfer.py:60-105
 # LiveInferForDemo) on CPU.  Extra shims, none of which touches the loop's logic:
-#   4. `llava.mm_utils / llava.model.builder / llava.constants / llava.conversation` (test/inference.py:11-14): imported at
-#      module level, never used by the live loop -> empty name stubs.
+#   4. `llava.mm_utils / llava.model.builder / llava.constants / llava.conversation` (test/inference.py:11-14) and
+#      `torchvision.io.read_video` (:7, gone from the installed torchvision): imported at module level, never used by the
+#      live loop -> empty name stubs.
 #   5. `models.build_model_and_tokenizer` (test/inference.py:16,24) returns the model from build_reference_model() and the
 #      tokenizer handed to build_reference_loop(), instead of downloading lmms-lab/llava-onevision-qwen2-7b-ov.
 #   6. device: the loop hard-codes 'cuda' (torch.zeros(..., device='cuda'), .to('cuda')).  The module's `torch` global is
@@ -242,9 +249,14 @@ class TokenizerOnCpu:
 
     def __init__(self, tok):
         self._tok = tok
+        self.decoded = []          # raw id lists handed to decode(): the generated responses, in order
 
     def __getattr__(self, name):
         return getattr(self._tok, name)
+
+    def decode(self, ids, **kw):
+        self.decoded.append([int(i) for i in (ids.tolist() if torch.is_tensor(ids) else ids)])
+        return self._tok.decode(ids, **kw)
 
     def apply_chat_template(self, conversation, **kw):
         try:
@@ -261,6 +273,7 @@ class LegacyCacheModel:
 
     def __init__(self, model):
         self.__dict__["_m"] = model
+        self.__dict__["calls"] = []    # (tokens in the call, top-2 gap of the last position's lm logits)
 
     def __getattr__(self, name):
         return getattr(self._m, name)
@@ -273,7 +286,12 @@ class LegacyCacheModel:
         import copy
         if past_key_values is not None:
             past_key_values = copy.deepcopy(past_key_values)
-        return self._m(*args, past_key_values=past_key_values, **kwargs)
+        # plain tensors inside the model (the device shim's Tensor subclass must not end up in the cache)
+        kwargs = {k: (v.as_subclass(torch.Tensor) if torch.is_tensor(v) else v) for k, v in kwargs.items()}
+        out = self._m(*args, past_key_values=past_key_values, **kwargs)
+        t = out.logits[0, -1].float().topk(2).values
+        self.calls.append((int(kwargs["inputs_embeds"].shape[1]), float(t[0] - t[1])))
+        return out
 
 
 def import_reference_loop():
@@ -286,7 +304,9 @@ def import_reference_loop():
     sys.modules["llava.model.builder"].load_pretrained_model = None
     sys.modules["llava.constants"].IMAGE_TOKEN_INDEX, sys.modules["llava.constants"].DEFAULT_IMAGE_TOKEN = -200, "<image>"
     sys.modules["llava.conversation"].conv_templates = {}
-    sys.modules["peft"].PeftModel = getattr(sys.modules["peft"], "PeftModel")
+    import torchvision.io as tvio
+    if not hasattr(tvio, "read_video"):      # removed from recent torchvision; only the unused load_video() calls it
+        tvio.read_video = None
     models = sys.modules["models"]
     models.fast_greedy_generate = ml.fast_greedy_generate
     models.parse_args = lambda *a, **k: (_ for _ in ()).throw(RuntimeError("CLI parsing is not part of the loop"))

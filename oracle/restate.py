@@ -221,7 +221,7 @@ class LiveLoopOracle:
     def __init__(self, w, arch, *, start_ids, stream_prompt_ids=(), stream_generation_ids=(), eos_token_id=None,
                  frame_fps=2.0, score_heads=("informative_score",), stream_end_prob_threshold=None,
                  stream_end_score_sum_threshold=None, running_list_length=20, remove_assistant_turns=False,
-                 max_new_tokens=200, dtype=torch.float32):
+                 max_new_tokens=200, dtype=torch.float32, repetition_penalty=None):
         if int(stream_end_prob_threshold is not None) + int(stream_end_score_sum_threshold is not None) != 1:
             raise ValueError("only one of stream_end_prob_threshold / stream_end_score_sum_threshold can be set")
         self.w, self.arch, self.dtype = w, arch, dtype
@@ -236,6 +236,8 @@ class LiveLoopOracle:
         self.running_list_length = running_list_length
         self.remove_assistant_turns = remove_assistant_turns
         self.max_new_tokens = max_new_tokens
+        self.repetition_penalty = repetition_penalty
+        self.top2_gaps = []        # (kind, gap between the two largest lm logits) of every argmax the loop takes
         self.reset()
 
     def reset(self):
@@ -250,6 +252,7 @@ class LiveLoopOracle:
         self.debug_data_list = []
         self.stream_end_prob_list = []
         self.stream_end_score_sum = 0
+        self.generated_token_ids = []
 
     def input_video_stream(self, pixels, batch_size=32):
         for b in range(0, len(pixels), batch_size):
@@ -257,9 +260,10 @@ class LiveLoopOracle:
             self.frame_embeds_queue.extend([((r + b) / self.frame_fps, f) for r, f in enumerate(emb)])
 
     def input_query_stream(self, queries):
-        """queries: iterable of (time, token_ids) — already chat-templated user turns."""
+        """queries: iterable of (time, token_ids) — already chat-templated user turns — or (time, f) with f(last_role) -> ids
+        (the template's stream-query prefix depends on the role of the turn before the query, test/inference.py:250)."""
         for t, ids in queries:
-            self.query_queue.append((t, torch.as_tensor(ids, dtype=torch.long)))
+            self.query_queue.append((t, ids if callable(ids) else torch.as_tensor(ids, dtype=torch.long)))
 
     def _encode_frame(self):
         _, frame_embeds = self.frame_embeds_queue.popleft()
@@ -278,9 +282,16 @@ class LiveLoopOracle:
 
     def _encode_query(self):
         _, ids = self.query_queue.popleft()
+        if callable(ids):
+            ids = torch.as_tensor(ids(self.last_role), dtype=torch.long)
         out = model_forward(self.w, self.arch, embed_tokens(self.w, ids).to(self.dtype), self.cache, want_lm_logits=True)
         self.last_ids = out["logits"][-1:].argmax(-1)
+        self._note_gap("query", out["logits"][-1])
         self.last_role = "user"
+
+    def _note_gap(self, kind, logits):
+        t = logits.float().topk(2).values
+        self.top2_gaps.append((kind, float(t[0] - t[1])))
 
     def _generate_response(self):
         L0 = len(self.cache)
@@ -288,8 +299,18 @@ class LiveLoopOracle:
         ids = []
         for _ in range(self.max_new_tokens):
             out = model_forward(self.w, self.arch, x, self.cache, want_lm_logits=True)
-            tok = out["logits"][-1:].argmax(-1)
+            logits = out["logits"][-1].clone()
+            if self.repetition_penalty is not None and self.generated_token_ids:
+                # transformers.RepetitionPenaltyLogitsProcessor on the ids generated so far in this video
+                # (models/modeling_live.py:58-66): score < 0 -> score * p, else score / p
+                idx = torch.tensor(self.generated_token_ids, dtype=torch.long, device=logits.device)
+                sc = logits[idx]
+                logits[idx] = torch.where(sc < 0, sc * self.repetition_penalty, sc / self.repetition_penalty)
+            tok = logits[None].argmax(-1)
+            self._note_gap("generate", logits)
             ids.append(int(tok))
+            if self.repetition_penalty is not None and int(tok) != self.eos_token_id:   # modeling_live.py:68-69
+                self.generated_token_ids.append(int(tok))
             if self.eos_token_id is not None and int(tok) == self.eos_token_id:
                 break
             x = embed_tokens(self.w, tok).to(self.dtype)

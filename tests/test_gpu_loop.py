@@ -185,3 +185,108 @@ def test_peer_store_encoder_two_gpus():
                        timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "max diff vs single-rank encode 0.0" in r.stdout
+
+
+class _RecordingTokenizer:
+    """SyntheticTokenizer that keeps the raw ids of every decoded response."""
+
+    def __init__(self, vocab):
+        from mmduet_b200.tokenization_live import SyntheticTokenizer
+        self._t, self.decoded = SyntheticTokenizer(vocab), []
+
+    def __getattr__(self, name):
+        return getattr(self._t, name)
+
+    def decode(self, ids, **kw):
+        self.decoded.append([int(i) for i in ids.tolist()])
+        return self._t.decode(ids, **kw)
+
+
+@pytest.mark.parametrize("k", [1, 3])
+@pytest.mark.parametrize("name", ["tiny_loop_keep_turns", "tiny_loop_rollback", "tiny_loop_score_sum"])
+def test_cuda_loop_matches_reference_loop_fixture(name, k):
+    """The CUDA loop (LiveInferForBenchmark over the kernels) against what the reference's OWN LiveInferForBenchmark produced
+    on the same seeded video / query / flags (tests/golden/tiny_loop_*.npz, oracle/make_golden_loop.py): scores within
+    2e-2, identical response frames, identical generated token ids (greedy, with and without the HF repetition penalty),
+    identical ids carried after the last turn, identical final context length (rollback).  The fixtures were chosen with a
+    top-2 logit gap >= 0.03 and a score-to-threshold margin >= 0.012 so that identity is a fair demand of a bf16 path."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    torch.set_grad_enabled(False)
+    from mmduet_b200 import build_model_and_tokenizer
+    from mmduet_b200.arguments_live import LiveTestArguments
+    from mmduet_b200.config import ModelConfig
+    from mmduet_b200.inference import LiveInferForBenchmark
+    from tests.test_oracle import loop_case
+    g, flags, arch, w, frames, _, query = loop_case(name)
+    tok = _RecordingTokenizer(arch.vocab)
+    model, _ = build_model_and_tokenizer(state_dict=w, model_config=ModelConfig.from_any(arch), device="cuda:0", max_context=2048,
+                                         tokenizer=tok)
+    infer = LiveInferForBenchmark(LiveTestArguments(frame_fps=2, system_prompt="you watch a video", **flags), model=model, tokenizer=tok)
+    infer.inplace_output_ids = torch.zeros(1, int(g["max_new_tokens"]), device=infer.device, dtype=torch.long)
+    infer.frames_per_step = k
+    infer.input_video_stream(frames)
+    if query:
+        infer.input_query_stream([{"role": "user", "time": query[0], "content": query[1]}])
+    resp = infer.inference()
+    got = np.array([[d["informative_score"], d["relevance_score"]] for d in infer.debug_data_list])
+    err = np.abs(got - g["scores"]).max()
+    print(name, "k", k, "score max-abs", err, "fixture margins: top-2 gap", float(g["min_top2_gap"]), "score", float(g["min_score_margin"]))
+    assert err < TOL, err
+    assert [d["time"] for d in infer.debug_data_list] == g["times"].tolist()
+    assert [r["time"] for r in resp if r["role"] == "assistant"] == g["response_times"].tolist()
+    assert tok.decoded == [[t for t in row if t >= 0] for row in g["generated"].tolist()]
+    assert infer.past_key_values.length == int(g["final_context"])
+    assert infer.last_ids.view(-1).tolist() == g["last_ids"].tolist()
+    assert infer.generated_token_ids == g["generated_token_ids"].tolist()
+    if query:
+        assert [r for r in resp if r["role"] == "user"] == [{"time": query[0], "content": query[1], "role": "user"}]
+
+
+def test_query_turn_matches_oracle(setup):
+    """_encode_query (test/inference.py:248-255): the same chat-templated user turn goes into the oracle loop and into the
+    CUDA loop after two frames; the token kept from the turn (argmax of the last position's lm logits) and the scores of
+    the following frames must agree.  The oracle's top-2 logit gap is reported next to the lm-logit error."""
+    from mmduet_b200.inference import LiveInferForBenchmark
+    arch, w, model, tok, frames = setup
+    infer = LiveInferForBenchmark(_args(stream_end_prob_threshold=1.0), model=model, tokenizer=tok)
+    infer.input_video_stream(frames[:5])
+    infer.input_query_stream([{"role": "user", "time": 1.0, "content": "what is the person doing now"}])
+    loop = _oracle_loop(arch, w, infer, frames[:5], stream_end_prob_threshold=1.0)
+    loop.input_query_stream([(1.0, lambda role: tok.apply_chat_template([{"role": "user", "content": "what is the person doing now"}],
+                                                                        add_stream_query_prompt=role == "stream", add_stream_prompt=True))])
+    # step both loops to just after the query turn
+    for lp in (infer, loop):
+        for _ in range(2):
+            lp._encode_frame()
+            lp.video_time += 0.5
+        lp._encode_query()
+    gap = loop.top2_gaps[-1][1]
+    print("query turn: oracle top-2 gap", gap, "ids", loop.last_ids.tolist(), infer.last_ids.view(-1).tolist())
+    assert infer.last_role == "user" and infer.past_key_values.length == len(loop.cache)
+    if gap > 0.05:
+        assert infer.last_ids.view(-1).tolist() == loop.last_ids.tolist()
+    a, b = infer._encode_frame(), loop._encode_frame()
+    assert abs(a["informative_score"] - b["informative_score"]) < TOL and abs(a["relevance_score"] - b["relevance_score"]) < TOL
+
+
+def test_joint_embed_scatters_frames_at_placeholders(setup):
+    """LiveMixin.joint_embed (models/modeling_live.py:35-48): ids are embedded (clamped to the vocabulary) and the positions
+    holding config.v_placeholder_id are overwritten with visual_embed(frames), in order."""
+    arch, w, model, tok, frames = setup
+    v = model.config.v_placeholder_id
+    assert v == tok.convert_tokens_to_ids("<image>") and v is not None
+    ids = torch.tensor([[7, 8] + [v] * 49 + [9] + [v] * 49 + [10, arch.vocab + 3]], device="cuda")
+    out = model.joint_embed(ids, frames[:2].cuda())
+    assert out.shape == (1, ids.shape[1], arch.hidden)
+    emb = model.visual_embed(frames[:2].cuda())
+    table = model.get_input_embeddings().weight
+    assert torch.equal(out[0, 2:51], emb[:49]) and torch.equal(out[0, 52:101], emb[49:])
+    assert torch.equal(out[0, :2], table[torch.tensor([7, 8], device="cuda")]) and torch.equal(out[0, 51], table[9])
+    assert torch.equal(out[0, -1], table[arch.vocab - 1])                      # clamp(max=vocab_size-1)
+    wd = {k: t.cuda() for k, t in w.items()}
+    ref = R.visual_embed(wd, arch, R.preprocess_frames(frames[:2]).bfloat16().float().cuda())
+    assert (out[0, 2:51].float() - ref[:49]).abs().max() < TOL
+    # forward() on ids + frames = the training-style call of the reference (video_head_live_llava_qwen.py:135-137)
+    o = model(input_ids=ids[:, :51], frames=frames[:1].cuda(), use_cache=True, return_dict=True, logits_to_keep="none")
+    assert o.informative_logits.shape == (1, 51, 2) and o.past_key_values.get_seq_length() == 51

@@ -94,6 +94,8 @@ class _GlooSymm:
 
         def barrier(self, channel=0):
             dist.barrier(self.group)
+            self.sent = {}                       # a new encode() starts: every channel is free again
+            self.staging.fill_(float("nan"))
 
         def put_signal(self, dst_rank, channel=0):
             assert channel not in self.sent, "a signal channel is a binary semaphore: one batch per channel and encode"
@@ -142,6 +144,13 @@ def _peer_worker(rank, world, port, n_frames, owner, q):
             ok = torch.equal(out, want) and enc.hdl.log == [(src, 1 + b) for b in range(n_batches)]
         else:
             ok = out is None and ready is None
+        # second video: the owner walks away without waiting for anything (early stop); third video: the leftover signals
+        # must have been consumed before the new ones are trusted (no stale "frame has landed")
+        enc.encode(n_frames, frames)
+        out, ready = enc.encode(n_frames, frames)
+        if rank == owner:
+            PeerStoreEncoder.wait_all(ready)
+            ok = ok and torch.equal(out, want) and enc.hdl.log == [(src, 1 + b) for b in range(n_batches)] * 3
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
