@@ -253,6 +253,20 @@ MMD_API int mmd_decoder_step(mmd_ctx*, const mmd_dec_weights*, const mmd_kv_pool
                              int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Grounding-score post-processing of the reference's evaluator: for every video v and smoothing window w
+ * (test/evaluate.py:374-392): s = smooth_pred_list(scores[v], w) (:166-167, np.mean with numpy's pairwise summation),
+ * p = normalize_pred_list(s) (:170-173), and for every threshold t: pred = p >= t, counts[w][v][t] = {|pred & gold|,
+ * |pred | gold|} (calculate_iou, :129-137; IoU = counts[0] / counts[1], 0 when the union is empty).  float64 throughout,
+ * bit-identical to the evaluator.  scores [n_videos, t_max] fp64 (rows padded), gold [n_videos, t_max] u8 (is_time_in_span
+ * of each frame time), lens [n_videos]; norm_out (optional) [n_windows, n_videos, t_max] receives p; degenerate
+ * [n_windows, n_videos] is set to 1 where the list is empty (the evaluator raises there); a constant list gives p = nan and
+ * empty predictions, exactly as the evaluator's np.float64 arithmetic does.  n_thresholds <= 64.
+ * ------------------------------------------------------------------------------------------------------------- */
+MMD_API int mmd_grounding_sweep(const double* scores, const unsigned char* gold, const int* lens, int n_videos, int t_max,
+                                const int* windows, int n_windows, const double* thresholds, int n_thresholds, int* counts,
+                                double* norm_out, int* degenerate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Measurement hooks (bench.py): kernels launched by the stage functions so far, and optional CUDA-event timing of
  * named launch sites ("all" or a comma-separated list of mmd_profile_tag_name values) on the launching stream.
  * mmd_profile_stop synchronises on the recorded events and fills ms_sum[tag] / counts[tag] (mmd_profile_num_tags long).

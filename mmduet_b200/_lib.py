@@ -103,6 +103,8 @@ SIGNATURES = {
                              c_int, c_void_p]),
     "mmd_heads": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "mmd_argmax": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    "mmd_grounding_sweep": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                    c_void_p, c_void_p]),
     "mmd_vit_workspace_bytes": (c_int64, [P(VitWeights), c_int]),
     "mmd_vit_forward": (c_int, [c_void_p, P(VitWeights), c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int64,
                                 c_void_p]),

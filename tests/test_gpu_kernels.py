@@ -520,3 +520,33 @@ def test_attention_under_timing_jitter(env):
                         "-k", "(test_vit_attention or test_qkv_finish_and_kv_attention) and tcgen05"], env=envv, cwd=root,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_grounding_sweep_bit_exact(env):
+    """mmd_grounding_sweep == the evaluator's smoothing / min-max / threshold sweep (oracle/evaluate.py, pinned to
+    test/evaluate.py:166-173,363-399), bit for bit: normalised scores as float64, IoU counts as integers, result tables equal."""
+    import numpy as np
+    from mmduet_b200 import postprocess as PP
+    from oracle import evaluate as E
+    from tests.test_postprocess_cpu import _records
+    rng = np.random.default_rng(7)
+    for legacy in (False, True):
+        preds, golds = _records(rng, 9, legacy=legacy)
+        preds.append({"question_id": "two", "debug_data": [{"time": 0.0, "relevance_score": 0.25}, {"time": 0.5, "relevance_score": 0.75}]})
+        golds["two"] = {"timestamps": [[0.5, 0.5]]}
+        final_ref, best_ref = E.grounding_sweep(preds, golds)
+        final, best = PP.grounding_sweep(preds, golds)
+        assert final == final_ref and best == best_ref
+        scores = [[E.debug_entry(e)[1] for e in ex["debug_data"]] for ex in preds]
+        gold = [[E.is_time_in_span(E.debug_entry(e)[0], golds[ex["question_id"]]["timestamps"]) for e in ex["debug_data"]] for ex in preds]
+        counts, norm = PP.sweep_counts(scores, gold, return_normalized=True)
+        for wi, w in enumerate(PP.WINDOWS):
+            for v, s in enumerate(scores):
+                with np.errstate(invalid="ignore"):
+                    want = E.normalize_pred_list(E.smooth_pred_list(s, w))
+                assert np.array_equal(norm[wi, v, :len(s)], np.asarray(want, dtype=np.float64), equal_nan=True), (w, v)
+    # a constant list: the evaluator's np.float64 arithmetic yields nan, no prediction, IoU 0 (union = |gold|)
+    c = PP.sweep_counts([[0.5, 0.5, 0.5]], [[True, False, True]])
+    assert (c[..., 0] == 0).all() and (c[..., 1] == 2).all()
+    with pytest.raises(ValueError):
+        PP.sweep_counts([], [])

@@ -290,3 +290,93 @@ def test_joint_embed_scatters_frames_at_placeholders(setup):
     # forward() on ids + frames = the training-style call of the reference (video_head_live_llava_qwen.py:135-137)
     o = model(input_ids=ids[:, :51], frames=frames[:1].cuda(), use_cache=True, return_dict=True, logits_to_keep="none")
     assert o.informative_logits.shape == (1, 51, 2) and o.past_key_values.get_seq_length() == 51
+
+
+def test_merged_lora_matches_unmerged_forward():
+    """Row f2: the reference runs the base checkpoint with an UNMERGED peft adapter (models/modeling_live.py:117-123; r = 16,
+    alpha = 32 on all seven projections of every decoder layer); here the adapter is folded into the bf16 matrices at load.
+    The merged CUDA model must match the unmerged forward (fp32 oracle on W + (alpha/r) B A, nothing rounded after the merge)
+    at the north-star tolerance, and the adapter must matter (scores move far more than the tolerance when it is dropped)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    torch.set_grad_enabled(False)
+    from mmduet_b200 import build_model_and_tokenizer
+    from mmduet_b200.config import ModelConfig
+    arch = A.SMALL
+    w = R.make_weights(arch, seed=61)
+    g = torch.Generator().manual_seed(62)
+    lora, w_eff = {}, dict(w)
+    for i in range(arch.layers):
+        for mod in ("self_attn.q_proj", "self_attn.k_proj", "self_attn.v_proj", "self_attn.o_proj", "mlp.gate_proj", "mlp.up_proj", "mlp.down_proj"):
+            key = f"model.layers.{i}.{mod}"
+            n, k = w[key + ".weight"].shape
+            a = (torch.randn(16, k, generator=g) * k ** -0.5).bfloat16().float()
+            b = (torch.randn(n, 16, generator=g) * 0.02).bfloat16().float()
+            lora[f"base_model.model.{key}.lora_A.weight"], lora[f"base_model.model.{key}.lora_B.weight"] = a, b
+            w_eff[key + ".weight"] = w[key + ".weight"] + 2.0 * (b @ a)
+    cfg = ModelConfig.from_any(arch)
+    merged, _ = build_model_and_tokenizer(state_dict=w, lora_state_dict=lora, lora_r=16, lora_alpha=32, model_config=cfg, device="cuda:0",
+                                          max_context=1024)
+    base, _ = build_model_and_tokenizer(state_dict=w, model_config=cfg, device="cuda:0", max_context=1024)
+    frames = R.synthetic_frames(6, seed=63)
+    px = R.preprocess_frames(frames).bfloat16().float().cuda()
+    wd = {k: v.cuda() for k, v in w_eff.items()}
+    from oracle import parity as P
+    ref = P.oracle_stream(wd, arch, px, list(range(3, 20)), frames_per_pass=1)
+
+    def run(model):
+        emb = model.visual_embed(frames.cuda())
+        st, L, sc = model.decoder.new_stream(), 0, []
+        for f in range(6):
+            o = model.decoder.step([dict(storage=st, past=L, ids=list(range(3, 20)) if f == 0 else [], frames=emb[f * 49:(f + 1) * 49])])
+            L = o["views"][0].length
+            sc.append(o["scores"][0])
+        return torch.stack(sc)
+    s_merged, s_base = run(merged), run(base)
+    err = (s_merged - ref["scores"]).abs().max().item()
+    moved = (s_base - ref["scores"]).abs().max().item()
+    print("merged LoRA vs unmerged oracle", err, "| base model without the adapter", moved)
+    assert err < TOL, err
+    assert moved > 5 * TOL, "the synthetic adapter does not change the scores enough to test anything"
+
+
+def test_loop_with_a_real_hf_tokenizer(tmp_path):
+    """Row f2: a genuine PreTrainedTokenizerFast (built offline: byte-level BPE, ChatML specials) loaded through
+    build_live_tokenizer_and_update_config drives LiveInferForBenchmark — system prompt, a user query, a generated response —
+    and the CUDA loop agrees with the oracle loop fed the same token ids."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    torch.set_grad_enabled(False)
+    from mmduet_b200 import build_model_and_tokenizer
+    from mmduet_b200.arguments_live import LiveTestArguments
+    from mmduet_b200.config import ModelConfig
+    from mmduet_b200.inference import LiveInferForBenchmark, template_ids
+    from tests.test_ingestion_cpu import offline_tokenizer_dir
+    arch = A.TINY
+    w = R.make_weights(arch, seed=71)
+    d = offline_tokenizer_dir(str(tmp_path / "tok"))
+    model, tok = build_model_and_tokenizer(state_dict=w, llm_pretrained=d, model_config=ModelConfig.from_any(arch), device="cuda:0", max_context=2048)
+    assert type(tok).__name__ in ("PreTrainedTokenizerFast", "TokenizersBackend") or hasattr(tok, "backend_tokenizer")
+    assert model.config.eos_token_id == tok.eos_token_id and model.config.v_placeholder_id == tok.convert_tokens_to_ids("<image>")
+    frames = R.synthetic_frames(6, seed=72)
+    args = LiveTestArguments(frame_fps=2, system_prompt="You watch.", stream_end_prob_threshold=1.0)
+    infer = LiveInferForBenchmark(args, model=model, tokenizer=tok)
+    infer.input_video_stream(frames)
+    infer.input_query_stream([{"role": "user", "time": 1.0, "content": "hi?"}])
+    resp = infer.inference()
+    assert resp == [{"time": 1.0, "content": "hi?", "role": "user"}]
+    loop = R.LiveLoopOracle(w, arch, start_ids=template_ids(tok, [{"role": "system", "content": "You watch."}]),
+                            stream_prompt_ids=template_ids(tok, [{}], add_stream_prompt=True),
+                            stream_generation_ids=template_ids(tok, [{}], add_stream_generation_prompt=True), eos_token_id=tok.eos_token_id,
+                            frame_fps=2, stream_end_prob_threshold=1.0, max_new_tokens=4)
+    loop.input_video_stream(R.preprocess_frames(frames).bfloat16().float())
+    loop.input_query_stream([(1.0, lambda role: template_ids(tok, [{"role": "user", "content": "hi?"}], add_stream_query_prompt=role == "stream",
+                                                             add_stream_prompt=True))])
+    loop.inference()
+    a = np.array([[x["informative_score"], x["relevance_score"]] for x in infer.debug_data_list])
+    b = np.array([[x["informative_score"], x["relevance_score"]] for x in loop.debug_data_list])
+    assert np.abs(a - b).max() < TOL and infer.past_key_values.length == len(loop.cache)
+    # a response through the real tokenizer's decode()
+    infer.inplace_output_ids = torch.zeros(1, 4, device=infer.device, dtype=torch.long)
+    text = infer._generate_response()
+    assert isinstance(text, str) and infer.last_role == "assistant"
