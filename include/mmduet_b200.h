@@ -68,6 +68,7 @@ MMD_API int mmd_set_gemm_2cta(int on);
 #define MMD_EPI_T_SWIGLU_IL 7 /* swap-AB, X rows interleaved (2j = gate_j, 2j+1 = up_j): out_bf16[m][j] = silu(acc[2j]) * acc[2j+1];
                                 out is [M, x_rows / 2]; one accumulator, 256-token tiles (decoder gate/up above 128 tokens) */
 #define MMD_EPI_BF16_HILO 5 /* v = act(acc + bias[n]); out[m,n] = bf16(v), out[m,N+n] = bf16(v - bf16(v)) */
+#define MMD_EPI_BF16_HILO_POOL 8 /* pooling epilogue (see mmd_projector_pool); not reachable through mmd_gemm_bf16 */
 /* OR-ed into `epi` (swap-AB epilogues MMD_EPI_T_F32 / MMD_EPI_T_SWIGLU, y_rows <= 128, K % 64 == 0):
  * Y_HILO: Y is a bf16 hi+lo pair [hi | lo] of width 2K (ldy >= 2K); both halves are multiplied with every weight tile into
  * the same fp32 accumulator, so the weights are streamed once and the activation rounding error drops from 2^-9 to 2^-17.
@@ -172,10 +173,16 @@ MMD_API int mmd_vit_forward(mmd_ctx*, const mmd_vit_weights*, const void* pixels
                             float* resid_out, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * mm_projector + GELU + spatial pooling (a2): gathers the source tokens the pooling reads (169 of 729 for the
- * bilinear 27->7 resize), Linear1 + erf-GELU, Linear2 with an fp32 epilogue, then the tap pooling (bilinear / average
- * weights or max) in fp32 and a single rounding to bf16 (with `hilo` the GEMM inputs carry ~16 mantissa bits).
- * video_head_live_llava_qwen.py:90-91 (connector), :100-119 (post_projector_pooling).
+ * mm_projector + GELU + spatial pooling (a2).  video_head_live_llava_qwen.py:90-91 (connector), :100-119
+ * (post_projector_pooling).  Two launch sequences:
+ *   pooled (pool_group = 4 or 16, linear pooling = bilinear / average, hilo): the source tokens are gathered tap-major
+ *     (pool_group consecutive rows = the taps of one output token, padded with weight-0 taps), Linear1 + erf-GELU runs with the
+ *     POOLING IN ITS EPILOGUE (MMD_EPI_BF16_HILO_POOL: weighted sum over the group's TMEM lanes, fp32, written as a hi+lo
+ *     pair), and Linear2 — which commutes with the linear taps (their weights sum to 1, so the bias is preserved) — runs on
+ *     the n_out pooled rows per frame only (49 instead of 169) and writes the frame tokens directly: gather + 2 GEMMs.
+ *   generic (pool_group = 0; max pooling does not commute with Linear2): gather the distinct source tokens, Linear1 +
+ *     GELU, Linear2 with an fp32 epilogue, tap pooling kernel.
+ * Either way the frame tokens are rounded to bf16 exactly once, at the output.
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct {
   int vit_dim, hidden, n_src_tokens /* S */, n_gather, n_out, max_taps, maxpool;
@@ -185,6 +192,9 @@ typedef struct {
   const int* gather_idx;             /* int32 [n_gather]: source token of each gathered row */
   const int* tap_idx;                /* int32 [n_out, max_taps]: index INTO THE GATHERED set, -1 = end */
   const float* tap_w;                /* fp32 [n_out, max_taps] */
+  int pool_group;                    /* 0 = generic path; 4 / 16 = taps per output token of the pooled path */
+  const int* pool_gather_idx;        /* int32 [n_out * pool_group]: source token of tap slot (o, i) */
+  const float* pool_row_w;           /* fp32 [n_out * pool_group]: its weight (0 for padding slots) */
 } mmd_projector_weights;
 
 MMD_API int64_t mmd_projector_workspace_bytes(const mmd_projector_weights*, int T);

@@ -40,7 +40,8 @@ class VitWeights(ctypes.Structure):
 
 class ProjectorWeights(ctypes.Structure):
     _fields_ = [(n, c_int) for n in ("vit_dim", "hidden", "n_src_tokens", "n_gather", "n_out", "max_taps", "maxpool", "hilo")] + \
-               [(n, c_void_p) for n in ("w1", "b1", "w2", "b2", "gather_idx", "tap_idx", "tap_w")]
+               [(n, c_void_p) for n in ("w1", "b1", "w2", "b2", "gather_idx", "tap_idx", "tap_w")] + \
+               [("pool_group", c_int), ("pool_gather_idx", c_void_p), ("pool_row_w", c_void_p)]
 
 
 class DecLayer(ctypes.Structure):

@@ -394,8 +394,17 @@ int mmd_vit_forward(mmd_ctx* c, const mmd_vit_weights* w, const void* pixels, in
 // projector + pooling
 // ---------------------------------------------------------------------------------------------------------------
 struct ProjBufs { __nv_bfloat16 *g, *a; float* b; };
+static bool proj_pooled(const mmd_projector_weights* w) {
+  return (w->pool_group == 4 || w->pool_group == 16) && w->hilo && !w->maxpool && w->pool_gather_idx != nullptr && w->pool_row_w != nullptr;
+}
 static int64_t proj_carve(const mmd_projector_weights* w, int T, Bump& b, ProjBufs* o) {
   const int f = w->hilo ? 2 : 1;
+  if (proj_pooled(w)) {
+    o->g = b.take<__nv_bfloat16>((int64_t)T * w->n_out * w->pool_group * w->vit_dim * 2);   // tap-major gathered tokens [hi | lo]
+    o->a = b.take<__nv_bfloat16>((int64_t)T * w->n_out * w->hidden * 2);                    // pooled GELU activations [hi | lo]
+    o->b = nullptr;
+    return b.off;
+  }
   o->g = b.take<__nv_bfloat16>((int64_t)T * w->n_gather * w->vit_dim * f);
   o->a = b.take<__nv_bfloat16>((int64_t)T * w->n_gather * w->hidden * f);
   o->b = b.take<float>((int64_t)T * w->n_gather * w->hidden);
@@ -421,6 +430,26 @@ int mmd_projector_pool(mmd_ctx* c, const mmd_projector_weights* w, const float* 
   proj_carve(w, T, b, &buf);
   if (!b.ok) return fail(MMD_ERR_WORKSPACE, "mmd_projector_pool: workspace too small");
   cudaStream_t s = S(stream);
+  if (proj_pooled(w)) {
+    // gather tap-major -> Linear1 + GELU + pooling taps in the epilogue -> Linear2 on the pooled rows, straight into `out`
+    const int G = w->pool_group, Mg = T * w->n_out * G, Mo = T * w->n_out, H = w->hidden, D = w->vit_dim;
+    PRUNK(mmd::launch_gather_rows_f32_to_bf16(vit_resid, w->pool_gather_idx, buf.g, T, w->n_src_tokens, w->n_out * G, D, 1, s), "gather");
+    {
+      mmd::GemmArgs a;
+      a.X = buf.g; a.x_rows = Mg; a.ldx = 2 * (int64_t)D; a.Y = static_cast<const __nv_bfloat16*>(w->w1); a.y_rows = H; a.ldy = 2 * (int64_t)D;
+      a.K = 2 * D; a.epi = mmd::EPI_BF16_HILO_POOL; a.act = mmd::ACT_GELU_ERF; a.bias = w->b1; a.out = buf.a; a.ldo = 2 * (int64_t)H;
+      a.row_w = w->pool_row_w; a.row_w_period = w->n_out * G; a.pool_group = G;
+      PRUN(mmd::gemm_launch(c->gemm, a, s), "proj.0+gelu");
+    }
+    {
+      mmd::GemmArgs a;
+      a.X = buf.a; a.x_rows = Mo; a.ldx = 2 * (int64_t)H; a.Y = static_cast<const __nv_bfloat16*>(w->w2); a.y_rows = H; a.ldy = 2 * (int64_t)H;
+      a.K = 2 * H; a.epi = out_dtype == MMD_DT_F32 ? mmd::EPI_F32 : mmd::EPI_BF16; a.act = mmd::ACT_NONE; a.bias = w->b2; a.out = out; a.ldo = H;
+      a.force_1cta = 1;          // per-thread stores: `out` may be another GPU's memory (PeerStoreEncoder)
+      PRUN(mmd::gemm_launch(c->gemm, a, s), "proj.2");
+    }
+    return check_launch("mmd_projector_pool");
+  }
   const int Mg = T * w->n_gather, H = w->hidden, f = w->hilo ? 2 : 1;
   // Only the source tokens the pooling reads go through the projector (169 of 729 for bilinear 27->7).  With `hilo` the
   // GEMM operands are bf16 hi+lo pairs (K doubled against [W | W]), Linear2 keeps its fp32 accumulator and the pooling

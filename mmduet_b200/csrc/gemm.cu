@@ -44,6 +44,9 @@ struct GemmKernelParams {
   int x_blocked;        // X/X2 tensor maps are 4-D over the tile-blocked weight layout
   int y_lo_off;         // HILO kernels: column offset (elements) of the lo half of the [hi | lo] Y operand (= K)
   int out_hilo;         // EPI_T_SWIGLU: write bf16 hi at [tok, n] and the rounding remainder lo at [tok, x_rows + n]
+  const float* row_w;   // EPI_BF16_HILO_POOL: pooling weight of every X row
+  int pool_group;       // EPI_BF16_HILO_POOL: X rows per pooled output row (4 or 16)
+  int row_w_period;     // > 0: row_w is indexed by row % row_w_period
 };
 
 // HILO: the Y operand (activations, swap-AB) is a bf16 hi+lo pair [hi | lo] (2K wide): every stage carries the hi and the lo
@@ -151,6 +154,51 @@ __device__ __forceinline__ void epilogue_normal(const GemmKernelParams& p, uint3
         }
       }
     }
+}
+
+// Pooling epilogue (EPI_BF16_HILO_POOL): TMEM lane = X row `row` (a gathered source token), G consecutive rows = the taps of one
+// pooled token.  Each lane scales its act(acc + bias) by its tap weight, the G lanes of a group all-reduce by xor-shuffles
+// (G divides 32 and groups never straddle a warp since tiles start at multiples of 32 rows), and lane j of the group writes
+// the 32/G columns [j * 32/G, ...) of the pooled row as bf16 hi and lo: per-thread global stores, the output may be peer memory.
+template <int ACT>
+__device__ __forceinline__ void epilogue_pool(const GemmKernelParams& p, uint32_t t_row, int row, int y0, int c_begin, int c_end) {
+  const int G = p.pool_group;
+  const float wgt = row < p.x_rows ? __ldg(p.row_w + (p.row_w_period > 0 ? row % p.row_w_period : row)) : 0.f;
+  const int j = (int)lane_id() & (G - 1);
+  const int per = 32 / G;                       // columns this lane stores per 32-column chunk
+  const long long orow = row / G;
+  __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo;
+#pragma unroll 1
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    if (y0 + c0 >= p.y_rows) break;  // warp-uniform
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(t_row + c0, v);
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int n = y0 + c0 + i;
+      const float b = (p.bias != nullptr && n < p.y_rows) ? __ldg(p.bias + n) : 0.f;
+      f[i] = wgt * apply_act<ACT>(__uint_as_float(v[i]) + b);
+    }
+    for (int o = 1; o < G; o <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] += __shfl_xor_sync(0xffffffffu, f[i], o);
+    }
+    if (row < p.x_rows) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i / per == j) {                     // resolved per lane; 32/G stores of 2 B hi + 2 B lo (G = 4: 8 columns)
+          const int n = y0 + c0 + i;
+          if (n < p.y_rows) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(f[i]);
+            outp[n] = hi;
+            outp[p.y_rows + n] = __float2bfloat16_rn(f[i] - __bfloat162float(hi));
+          }
+        }
+      }
+    }
+  }
 }
 
 template <int BN, bool DUAL, int EPI, int ACT, bool HILO = false>
@@ -317,7 +365,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       const int xi = xt * BM + lane_row;  // index along X rows (TMEM lane)
       const int y0 = yt * BN;             // first index along Y rows (TMEM column 0)
 
-      if constexpr (EPI == EPI_BF16 || EPI == EPI_RESID_F32 || EPI == EPI_F32 || EPI == EPI_BF16_HILO) {
+      if constexpr (EPI == EPI_BF16_HILO_POOL) {
+        epilogue_pool<ACT>(p, t_row, xi, y0, c_begin, c_end);
+      } else if constexpr (EPI == EPI_BF16 || EPI == EPI_RESID_F32 || EPI == EPI_F32 || EPI == EPI_BF16_HILO) {
         epilogue_normal<EPI, ACT>(p, t_row, xi, y0, c_begin, c_end);
       } else if constexpr (EPI == EPI_T_F32) {
         // swap-AB: lane = n (weight row), column = token. Lanes of a warp write 32 consecutive n -> 128-B stores.
@@ -658,7 +708,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN2;
       const int m_warp = mt * 2 * BM + (int)rank * BM + q * 32;   // first output row of this warp's 32 lanes
-      epilogue_normal_tma<EPI, ACT>(p, &tmOut, t_row, m_warp, nt * BN2, c_begin, c_end, epi_stage_base + (warp - 2) * 4096, ks);
+      if constexpr (EPI == EPI_BF16_HILO_POOL) epilogue_pool<ACT>(p, t_row, m_warp + (int)lane_id(), nt * BN2, c_begin, c_end);
+      else epilogue_normal_tma<EPI, ACT>(p, &tmOut, t_row, m_warp, nt * BN2, c_begin, c_end, epi_stage_base + (warp - 2) * 4096, ks);
       tc_fence_before();
       mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -865,7 +916,7 @@ static int launch_cfg(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
   if ((rc = get_map(c, a.Y, a.y_rows, HILO ? 2 * a.K : a.K, a.ldy, BN, &tmY)) != 0) return rc;
 
   GemmKernelParams p;
-  p.y_lo_off = a.K; p.out_hilo = a.out_hilo;
+  p.y_lo_off = a.K; p.out_hilo = a.out_hilo; p.row_w = a.row_w; p.pool_group = a.pool_group; p.row_w_period = a.row_w_period;
   p.x_rows = a.x_rows; p.y_rows = a.y_rows;
   p.x_tiles = (a.x_rows + BM - 1) / BM;
   p.y_tiles = (a.y_rows + BN - 1) / BN;
@@ -905,9 +956,10 @@ static int launch_2cta(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
   const int splits = (EPI == EPI_F32) ? gemm_effective_splits(a.K, a.k_splits) : 1;
   {
     const bool f32 = (EPI == EPI_RESID_F32 || EPI == EPI_F32);
-    const int width = EPI == EPI_BF16_HILO ? a.y_rows * 2 : (EPI == EPI_SWIGLU_PAIR ? a.y_rows / 2 : a.y_rows);
+    const int width = (EPI == EPI_BF16_HILO || EPI == EPI_BF16_HILO_POOL) ? a.y_rows * 2 : (EPI == EPI_SWIGLU_PAIR ? a.y_rows / 2 : a.y_rows);
+    const int out_rows = EPI == EPI_BF16_HILO_POOL ? a.x_rows / a.pool_group : a.x_rows;   // (the pooling epilogue stores directly; map unused)
     // EPI_F32 always uses the 3-D form (plane coordinate = split index; one plane when there is no split-K)
-    if ((rc = get_out_map(c, a.out, a.x_rows, width, a.ldo, f32, &tmOut, EPI == EPI_F32 ? splits : 0,
+    if ((rc = get_out_map(c, a.out, out_rows, width, a.ldo, f32, &tmOut, EPI == EPI_F32 ? splits : 0,
                           splits > 1 ? a.split_stride : (long long)a.x_rows * a.ldo)) != 0) return rc;
   }
   GemmKernelParams p;
@@ -917,6 +969,7 @@ static int launch_2cta(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
   p.kb_total = (a.K + BK - 1) / BK;
   p.k_splits = splits; p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.split_stride = 0; p.pdl_prefetch_x = 0; p.x_blocked = 0;
+  p.y_lo_off = 0; p.out_hilo = 0; p.row_w = a.row_w; p.pool_group = a.pool_group; p.row_w_period = a.row_w_period;
   const long long tiles = (long long)p.x_tiles * p.y_tiles * splits;
   const int max_clusters = (a.max_ctas > 0 ? a.max_ctas : c->num_sms) / 2;
   const int clusters = (int)(tiles < max_clusters ? tiles : max_clusters);
@@ -940,7 +993,7 @@ static int launch_2cta(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
 template <int EPI, int ACT>
 static int launch_normal(GemmContext* c, const GemmArgs& a, cudaStream_t s) {
   if (a.y_rows % 8 != 0) { g_gemm_err = "normal-orientation GEMM needs N % 8 == 0"; return -2; }
-  if (g_gemm_use_2cta && (a.x_rows >= 1024 || a.force_2cta) && a.y_rows >= 192) {
+  if (g_gemm_use_2cta && !a.force_1cta && (a.x_rows >= 1024 || a.force_2cta) && a.y_rows >= 192) {
     // N = 1152 (out_proj / fc2 / patch embed) tiles exactly by 192
     if constexpr (EPI == EPI_RESID_F32 || EPI == EPI_F32) {
       static const bool no192 = getenv("MMD_NO_BN192") != nullptr;
@@ -970,6 +1023,14 @@ int gemm_launch(GemmContext* c, const GemmArgs& a, cudaStream_t s) {
     case EPI_BF16_HILO:
       if (a.act == ACT_GELU_ERF) return launch_normal<EPI_BF16_HILO, ACT_GELU_ERF>(c, a, s);
       if (a.act == ACT_NONE) return launch_normal<EPI_BF16_HILO, ACT_NONE>(c, a, s);
+      break;
+    case EPI_BF16_HILO_POOL:
+      if (a.row_w == nullptr || (a.pool_group != 4 && a.pool_group != 16) || a.x_rows % a.pool_group != 0 || a.ldo < 2 * (int64_t)a.y_rows) {
+        g_gemm_err = "pooling epilogue needs row_w, pool_group 4 or 16 dividing x_rows, ldo >= 2N";
+        return -2;
+      }
+      if (a.act == ACT_GELU_ERF) return launch_normal<EPI_BF16_HILO_POOL, ACT_GELU_ERF>(c, a, s);
+      if (a.act == ACT_NONE) return launch_normal<EPI_BF16_HILO_POOL, ACT_NONE>(c, a, s);
       break;
     case EPI_SWIGLU_PAIR:
       if (a.y_rows % 256 != 0) { g_gemm_err = "swiglu-pair gemm needs N % 256 == 0"; return -2; }

@@ -21,6 +21,10 @@ enum GemmEpi : int {
   EPI_T_SWIGLU_IL = 7, // swap-AB, ONE operand with interleaved rows (2j = gate_j, 2j+1 = up_j): out_bf16[m, j] = silu(acc[2j]) * acc[2j+1];
                        // single accumulator, 256-token tiles (UMMA N = 256 instead of 2 x 128); out is [M, x_rows/2]
   EPI_BF16_HILO = 5, // v = act(acc + bias[n]); out_bf16[m, n] = hi = bf16(v); out_bf16[m, N + n] = bf16(v - hi)  (ldo >= 2N)
+  // Spatial pooling in the epilogue: every group of `pool_group` (4 or 16) consecutive X rows is one pooled output row,
+  // v[g, n] = sum_i row_w[g*G + i] * act(acc[g*G + i, n] + bias[n]) (fp32, combined across TMEM lanes by shuffles), written as
+  // a hi+lo pair like EPI_BF16_HILO; out is [x_rows / G, 2N].  mm_projector.0 + GELU + the bilinear / average taps.
+  EPI_BF16_HILO_POOL = 8,
 };
 enum GemmAct : int { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2 };
 
@@ -43,6 +47,10 @@ struct GemmArgs {
   int force_2cta = 0;                 // use the CTA-pair kernel even for M < 1024 (decoder passes with >= ~200 tokens)
   // swap-AB kernels (EPI_T_F32 / EPI_T_SWIGLU), at most 128 Y rows: Y is a bf16 hi+lo pair [hi | lo] of width 2K (ldy >= 2K);
   // each weight tile is multiplied with both halves into the same accumulator ("precise rows")
+  const float* row_w = nullptr;       // EPI_BF16_HILO_POOL: one pooling weight per X row
+  int pool_group = 0;                 // EPI_BF16_HILO_POOL: rows per pooled output (4 or 16; x_rows % pool_group == 0)
+  int row_w_period = 0;               // > 0: row_w holds one period (a frame) and is indexed by row % period
+  int force_1cta = 0;                 // single-CTA kernel with per-thread global stores (outputs in peer memory)
   int y_hilo = 0;
   int out_hilo = 0;                   // EPI_T_SWIGLU: out row = [hi | lo], lo at column x_rows (ldo >= 2 * x_rows)
 };

@@ -117,10 +117,23 @@ class VisionEngine:
             t = dict(w1=_bf16(torch.cat([sd["model.mm_projector.0.weight"]] * rep, 1), dev), b1=_f32(sd["model.mm_projector.0.bias"], dev),
                      w2=_bf16(torch.cat([sd["model.mm_projector.2.weight"]] * rep, 1), dev), b2=_f32(sd["model.mm_projector.2.bias"], dev),
                      gather_idx=gidx.to(dev), tap_idx=tidx.to(dev).contiguous(), tap_w=tw.to(dev).contiguous())
+            # Linear pooling (bilinear / average; tap weights sum to 1) commutes with Linear2, so it runs in Linear1's epilogue:
+            # tap-major gather, `pool_group` (4 or 16) consecutive rows per output token, weight-0 padding slots
+            pool_group = 0
+            if projector_hilo and cfg.pool_mode != "max" and max_taps <= 16 and os.environ.get("MMD_PROJ_GENERIC") != "1":
+                pool_group = 4 if max_taps <= 4 else 16
+                src = torch.zeros(taps.shape[0], pool_group, dtype=torch.int32)
+                wgt = torch.zeros(taps.shape[0], pool_group, dtype=torch.float32)
+                for o in range(taps.shape[0]):
+                    nz = (taps[o] != 0).nonzero().flatten()
+                    src[o, :len(nz)] = nz.to(torch.int32)
+                    src[o, len(nz):] = int(nz[0])
+                    wgt[o, :len(nz)] = taps[o, nz]
+                t["pool_gather_idx"], t["pool_row_w"] = src.flatten().to(dev), wgt.flatten().to(dev)
             keep.append(t)
             self.proj = _lib.ProjectorWeights(vit_dim=D, hidden=cfg.hidden, n_src_tokens=cfg.patches, n_gather=int(gidx.numel()),
                                               n_out=self.tokens_per_frame, max_taps=max_taps, maxpool=int(cfg.pool_mode == "max"),
-                                              hilo=int(projector_hilo),
+                                              hilo=int(projector_hilo), pool_group=pool_group,
                                               **{k: v.data_ptr() for k, v in t.items()})
         self._keep = keep
         self._ws = {}
