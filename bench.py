@@ -516,9 +516,12 @@ def parity_block(sd, cfg, frames_dev, prefix, emb32, scores_by_k):
             rep = P.parity_report(ref, sc, emb32 if k == max(scores_by_k) else None)
             out[f"frames_per_pass_{k}"] = {kk: (round(v, 6) if isinstance(v, float) else v) for kk, v in rep.items()}
         main = out[f"frames_per_pass_{max(scores_by_k)}"]
-        out.update(emb_maxabs=main.get("emb_maxabs"), score_maxabs=max(out[f"frames_per_pass_{k}"]["score_maxabs"] for k in scores_by_k),
-                   crossings_match=all(out[f"frames_per_pass_{k}"]["crossings_match"] for k in scores_by_k),
-                   min_margin=main["min_margin"])
+        reps = [out[f"frames_per_pass_{k}"] for k in scores_by_k]
+        out.update(emb_maxabs=main.get("emb_maxabs"), score_maxabs=max(r["score_maxabs"] for r in reps),
+                   crossings_match=all(r["crossings_match"] for r in reps), min_margin=main["min_margin"],
+                   flips_outside_noise=sum(len(r["flips_outside_noise"]) for r in reps),
+                   crossings_match_widest_gap=all(r["widest_gap_near_quantile"]["crossings_match"] for r in reps),
+                   min_margin_widest_gap=main["widest_gap_near_quantile"]["min_margin"])
         out["emb_bf16_out_maxabs"] = round(float((emb32.bfloat16().float() - ref["emb"]).abs().max()), 6)
         del w32, ref
         torch.cuda.empty_cache()

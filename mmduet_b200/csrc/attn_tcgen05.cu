@@ -74,8 +74,33 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn_b(uint32_t M, uint32_t N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// A format: 1 = bf16, 0 = f16 (the P operand when it is produced by packed half-precision exponentials); B = V is bf16
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_mn_b(uint32_t M, uint32_t N, uint32_t a_bf16 = 1u) {
+  return (1u << 4) | (a_bf16 << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// Packed exponentials (MMD_EXP_F16X2, experiment, default OFF): ex2.approx.f16x2 / ex2.approx.ftz.bf16x2 would halve the
+// MUFU work if the unit were packed, and the f16x2 result could be the PV product's A operand as it is (P as f16 read from
+// TMEM, V stays bf16).  On sm_100a it is not: ptxas lowers either form to TWO scalar ops (MUFU.EX2.F16 Rd, Rs and
+// MUFU.EX2.F16 Rd, Rs.H1) plus a PRMT, i.e. the same MUFU count as two fp32 ex2 and one more ALU op
+// (cuobjdump of this file with -DMMD_EXP_F16X2=1: 64 MUFU.EX2.F16 per kernel for 32 packed ex2).  Kept for the record.
+#ifndef MMD_EXP_F16X2
+#define MMD_EXP_F16X2 0
+#endif
+__device__ __forceinline__ uint32_t ex2_f16x2(float lo, float hi) {
+  uint32_t h, r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(h));
+  return r;
+}
+__device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ float h2_sum_f32(uint32_t h) {
+  float lo, hi;
+  asm("{ .reg .b16 l, u; mov.b32 {l, u}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, u; }" : "=f"(lo), "=f"(hi) : "r"(h));
+  return lo + hi;
 }
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
@@ -297,7 +322,7 @@ __device__ __forceinline__ void attention_pipeline(const Params& prm, int n_item
     const int qi = warp - (TA_SOFTMAX_WARPS + TA_LOADER_WARPS);
     if (qi < TA_QT && elect_one()) {
       constexpr uint32_t idesc_qk = umma_idesc_bf16(TA_BM, TA_BN);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16_mn_b(TA_BM, DHP);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16_mn_b(TA_BM, DHP, MMD_EXP_F16X2 ? 0u : 1u);
       // One thread issues everything, so its instruction count per tile is on the critical path: the descriptors' high
       // words are constants and the low words (start address | LBO) advance by immediates.
       constexpr uint32_t HI = (1024u >> 4) | (1u << 14) | (2u << 29);              // SBO | version 1 | SWIZZLE_128B
@@ -464,6 +489,19 @@ __device__ __forceinline__ void attention_pipeline(const Params& prm, int n_item
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] = fmaf(val(cur, 32 * c + i), sl2, -msc);
           uint32_t pk[16];
+#if MMD_EXP_F16X2
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = ex2_f16x2(x[2 * i], x[2 * i + 1]);
+          if constexpr (!ONES_COL) {
+            // row sum of the ROUNDED probabilities: pairwise f16x2 tree over the 32 keys (depth 4), then fp32
+            uint32_t t8[8], t4[4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t8[i] = hadd2_u32(pk[2 * i], pk[2 * i + 1]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) t4[i] = hadd2_u32(t8[2 * i], t8[2 * i + 1]);
+            rs += h2_sum_f32(hadd2_u32(hadd2_u32(t4[0], t4[1]), hadd2_u32(t4[2], t4[3])));
+          }
+#else
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
 #if MMD_EXP_MODE == 3   // timing experiment only: no exponential at all
@@ -479,6 +517,7 @@ __device__ __forceinline__ void attention_pipeline(const Params& prm, int n_item
               rs += __uint_as_float(pk[i] << 16) + __uint_as_float(pk[i] & 0xffff0000u);
             }
           }
+#endif
           tmem_st_32x32b_x16(t_row + sb * TA_BN + 16 * c, pk);
         }
         l_run += rs;

@@ -328,6 +328,8 @@ int launch_resid_add_layernorm(float* x, const float* planes, int n_planes, long
 // residual update from `prec_partial` (the hi/lo side GEMM's planes [n_prec_planes][P][H]) instead of `partial`, and get a
 // second, [hi | lo] (2H wide) copy of the normalised row in `out_hilo[j]`.  prec_of_row == nullptr with out_hilo != nullptr
 // means every row is precise (j = row) and `partial` already is the precise result (single-frame steps).
+constexpr int kMaxPlanes = 8;   // split-K planes whose loads are issued together (more are added in a plain loop)
+
 struct PreciseRows {
   const int* prec_of_row = nullptr;
   const float* prec_partial = nullptr;
@@ -355,9 +357,16 @@ __global__ void resid_add_rmsnorm_kernel(float* __restrict__ resid, const float*
   float ss = 0.f;
   for (int c = threadIdx.x; c < H4; c += NT) {
     float4 v = reinterpret_cast<float4*>(resid + row * H)[c];
-    for (int p = 0; p < np; ++p) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(src + p * ps) + c);
-      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    // all plane loads of this chunk are issued before the first add (the step is latency-bound: 49 rows, <= 8 planes in L2)
+    float4 a[kMaxPlanes];
+#pragma unroll
+    for (int p = 0; p < kMaxPlanes; ++p)
+      a[p] = p < np ? __ldg(reinterpret_cast<const float4*>(src + p * ps) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < kMaxPlanes; ++p) { v.x += a[p].x; v.y += a[p].y; v.z += a[p].z; v.w += a[p].w; }
+    for (int p = kMaxPlanes; p < np; ++p) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src + p * ps) + c);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
     }
     if (np > 0) reinterpret_cast<float4*>(resid + row * H)[c] = v;
     reinterpret_cast<float4*>(row_sh)[c] = v;
@@ -397,12 +406,15 @@ int launch_resid_add_rmsnorm_precise(float* resid, const float* partial, int n_p
                                      const float* prec_partial, int n_prec_planes, long long prec_plane_stride, __nv_bfloat16* out_hilo,
                                      cudaStream_t s) {
   if (H % 4 != 0 || rows <= 0) return rows == 0 ? 0 : -2;
-  constexpr int NT = 256;
   PreciseRows pr;
   pr.prec_of_row = prec_of_row; pr.prec_partial = prec_partial; pr.n_prec_planes = n_prec_planes;
   pr.prec_plane_stride = prec_plane_stride; pr.out_hilo = out_hilo;
-  launch_k(resid_add_rmsnorm_kernel<NT>, dim3((unsigned)rows), dim3(NT), H * sizeof(float), s, resid, partial, n_planes,
-           plane_stride, w, out_bf16, out_f32, H, eps, pr);
+  if (rows <= 256 && H >= 2048)   // few rows (single-frame steps): one float4 chunk or two per thread, every load in flight at once
+    launch_k(resid_add_rmsnorm_kernel<512>, dim3((unsigned)rows), dim3(512), H * sizeof(float), s, resid, partial, n_planes,
+             plane_stride, w, out_bf16, out_f32, H, eps, pr);
+  else
+    launch_k(resid_add_rmsnorm_kernel<256>, dim3((unsigned)rows), dim3(256), H * sizeof(float), s, resid, partial, n_planes,
+             plane_stride, w, out_bf16, out_f32, H, eps, pr);
   return 0;
 }
 
@@ -435,9 +447,15 @@ __global__ void final_norm_heads_kernel(const float* __restrict__ resid, const f
   float ss = 0.f;
   for (int c = threadIdx.x; c < H4; c += NT) {
     float4 v = reinterpret_cast<const float4*>(resid + row * H)[c];
-    for (int p = 0; p < np; ++p) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(src + p * ps) + c);
-      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    float4 a[kMaxPlanes];
+#pragma unroll
+    for (int p = 0; p < kMaxPlanes; ++p)
+      a[p] = p < np ? __ldg(reinterpret_cast<const float4*>(src + p * ps) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < kMaxPlanes; ++p) { v.x += a[p].x; v.y += a[p].y; v.z += a[p].z; v.w += a[p].w; }
+    for (int p = kMaxPlanes; p < np; ++p) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(src + p * ps) + c);
+      v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
     }
     reinterpret_cast<float4*>(row_sh)[c] = v;
     ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
@@ -528,12 +546,23 @@ __global__ void qkv_finish_kernel(const float* __restrict__ partial, int n_plane
 #pragma unroll
     for (int i = 0; i < 8; ++i) { x0[i] = 0.f; x1[i] = 0.f; }
   }
-  for (int p = 0; p < n_planes; ++p) {
-    const float* pl = partial + p * plane_stride + (long long)tok * N;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(pl + col0)), b = __ldg(reinterpret_cast<const float4*>(pl + col0 + 4));
-    const float4 c = __ldg(reinterpret_cast<const float4*>(pl + col1)), d = __ldg(reinterpret_cast<const float4*>(pl + col1 + 4));
-    x0[0] += a.x; x0[1] += a.y; x0[2] += a.z; x0[3] += a.w; x0[4] += b.x; x0[5] += b.y; x0[6] += b.z; x0[7] += b.w;
-    x1[0] += c.x; x1[1] += c.y; x1[2] += c.z; x1[3] += c.w; x1[4] += d.x; x1[5] += d.y; x1[6] += d.z; x1[7] += d.w;
+  for (int p0 = 0; p0 < n_planes; p0 += 4) {      // four planes' loads (16 x 16 B per thread) in flight together
+    float4 a[4], b[4], c[4], d[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool on = p0 + i < n_planes;
+      const float* pl = partial + (long long)(on ? p0 + i : 0) * plane_stride + (long long)tok * N;
+      a[i] = on ? __ldg(reinterpret_cast<const float4*>(pl + col0)) : z;
+      b[i] = on ? __ldg(reinterpret_cast<const float4*>(pl + col0 + 4)) : z;
+      c[i] = on ? __ldg(reinterpret_cast<const float4*>(pl + col1)) : z;
+      d[i] = on ? __ldg(reinterpret_cast<const float4*>(pl + col1 + 4)) : z;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      x0[0] += a[i].x; x0[1] += a[i].y; x0[2] += a[i].z; x0[3] += a[i].w; x0[4] += b[i].x; x0[5] += b[i].y; x0[6] += b[i].z; x0[7] += b[i].w;
+      x1[0] += c[i].x; x1[1] += c[i].y; x1[2] += c[i].z; x1[3] += c[i].w; x1[4] += d[i].x; x1[5] += d[i].y; x1[6] += d[i].z; x1[7] += d[i].w;
+    }
   }
   if (head < Hq + Hkv) {  // q and k are rotated (rotate_half convention)
     const int pos = tok_pos[tok];

@@ -58,15 +58,31 @@ def crossings(scores, thr):
 
 
 def parity_report(ref, got_scores, got_emb=None, head=0, q=0.8):
-    """ref: oracle_stream() result; got_scores [T,2]; got_emb [T*n,H] (optional).  All comparisons in float64 on the host."""
+    """ref: oracle_stream() result; got_scores [T,2]; got_emb [T*n,H] (optional).  All comparisons in float64 on the host.
+
+    Decisions are compared at TWO thresholds: the oracle's q-quantile itself (np.quantile lands INSIDE a gap
+    between two neighbouring scores, at 0.2 of it for 120 frames, so its margin can be arbitrarily small) and the middle of the
+    widest gap between neighbouring oracle scores in the [q - 0.05, q + 0.05] quantile band.  `flips_outside_noise` counts the
+    frames whose decision differs although their oracle score is further from the threshold than the measured score error —
+    the number that must be 0 for any implementation within tolerance."""
     rs = ref["scores"].double().cpu().numpy()
     gs = torch.as_tensor(got_scores).double().cpu().numpy()
-    thr = threshold_at_quantile(rs[:, head], q)
-    rc, gc = crossings(rs[:, head], thr), crossings(gs[:, head], thr)
-    rep = {"score_maxabs": float(np.abs(rs - gs).max()),
-           "threshold": thr, "threshold_rule": f"oracle {int(q * 100)}th-percentile of head {head} (0 = informative)",
-           "crossings_match": rc == gc, "n_crossings": len(rc), "crossings_ref": rc[:32], "crossings_got": gc[:32],
-           "min_margin": float(np.abs(rs[:, head] - thr).min())}
+    err = float(np.abs(rs - gs).max())
+    r, g = rs[:, head], gs[:, head]
+
+    def at(thr):
+        rc, gc = crossings(r, thr), crossings(g, thr)
+        flips = sorted(set(rc) ^ set(gc))
+        return {"threshold": thr, "crossings_match": rc == gc, "n_crossings": len(rc), "flips": flips,
+                "flips_outside_noise": [i for i in flips if abs(r[i] - thr) > err], "min_margin": float(np.abs(r - thr).min()),
+                "crossings_ref": rc[:32], "crossings_got": gc[:32]}
+    main = at(threshold_at_quantile(r, q))
+    so = np.sort(r)
+    lo, hi = int(np.floor((q - 0.05) * (len(so) - 1))), int(np.ceil((q + 0.05) * (len(so) - 1)))
+    j = lo + int(np.argmax(so[lo + 1:hi + 1] - so[lo:hi]))
+    gap = at(float((so[j] + so[j + 1]) / 2))
+    rep = {"score_maxabs": err, "threshold_rule": f"oracle {int(q * 100)}th-percentile of head {head} (0 = informative)", **main,
+           "widest_gap_near_quantile": {k: gap[k] for k in ("threshold", "crossings_match", "n_crossings", "flips", "min_margin")}}
     if got_emb is not None:
         re = ref["emb"].float()
         ge = got_emb.float().to(re.device)

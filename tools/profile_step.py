@@ -1,7 +1,10 @@
 """Small, fixed kernel sequence for ncu (launch list / --set full captures).  Never a source of bench numbers.
   python tools/profile_step.py step        one 32-frame encode + two 10-frame decoder passes at ~3k context (full-size model)
   python tools/profile_step.py gate_up     the dominant weight-streaming GEMM alone (M=1960 = 40 frames per pass, and M=49), 4 launches each
-  python tools/profile_step.py vit         one ViT layer's kernels at batch 32"""
+  python tools/profile_step.py vit         one ViT layer's kernels at batch 32
+  python tools/profile_step.py stream40    bench.py's default stream shape: 40-frame encode + one 40-frame decoder pass (1960 tokens) at ~2k context
+  python tools/profile_step.py k1          live mode: one single-frame encode + 3 single-frame decoder steps at ~3k context
+Wrap in `ncu --nvtx --nvtx-include "profiled/" ...` to keep only the kernels of the NVTX range."""
 import os
 import sys
 
@@ -41,6 +44,36 @@ if mode == "vit":
     for _ in range(3):
         vis.visual_embed(fr, normalize=True)
     torch.cuda.synchronize()
+    sys.exit(0)
+
+if mode in ("stream40", "k1"):
+    vis = VisionEngine(cfg, sd, dev)
+    dec = DecoderEngine(cfg, sd, dev, max_context=8192, max_tokens=2048)
+    n_f = 40 if mode == "stream40" else 1
+    fr = synthetic_frames(40, seed=1, device=dev)
+    emb = vis.visual_embed(fr, normalize=True)
+    st, L = dec.new_stream(), 0
+    rows40 = [49 * (j + 1) - 1 for j in range(40)]
+    for p in range(2 if mode == "stream40" else 1):   # warm-up: ~2k (stream40: 4k) tokens of context, every kernel variant seen once
+        out = dec.step([dict(storage=st, past=L, ids=[], frames=emb, score_rows=rows40)], score="frame_ends")
+        L = out["views"][0].length
+    if mode == "k1":
+        for f in range(25):
+            out = dec.step([dict(storage=st, past=L, ids=[], frames=emb[f * 49:(f + 1) * 49])])
+            L = out["views"][0].length
+        vis.visual_embed(fr[:1], normalize=True)
+    torch.cuda.synchronize()
+    torch.cuda.nvtx.range_push("profiled")
+    e = vis.visual_embed(fr[:n_f], normalize=True)
+    if mode == "stream40":
+        out = dec.step([dict(storage=st, past=L, ids=[], frames=e, score_rows=rows40)], score="frame_ends")
+    else:
+        for f in range(3):
+            out = dec.step([dict(storage=st, past=L, ids=[], frames=emb[f * 49:(f + 1) * 49])])
+            L = out["views"][0].length
+    torch.cuda.synchronize()
+    torch.cuda.nvtx.range_pop()
+    print("context", out["views"][0].length, "scores", out["scores"][:2].tolist())
     sys.exit(0)
 
 vis = VisionEngine(cfg, sd, dev)
