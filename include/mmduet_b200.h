@@ -141,6 +141,10 @@ MMD_API int mmd_tap_pool(const void* in, int in_dtype, void* out, int out_dtype,
  * test/inference.py:243-244).  head_w fp32 [4,H] = {inf0, inf1, rel0, rel1}. */
 MMD_API int mmd_heads(const float* hidden_f32, const int* rows, const float* head_w, float* logits_out, float* scores_out,
                       int n_rows, int H, void* stream);
+/* SigLIP attention-pooling head (the CLS token of models/vision_live.py:26-30 = vision_outputs.pooler_output): one probe query
+ * per frame over the S patch tokens.  q fp32 [H*dh]: the projected probe times dh^-0.5 (a constant of the weights);
+ * kv bf16 [T*S, 2*H*dh] = [K | V] of the head's in-projection; out fp32 [T, H*dh] (before the head's out_proj). */
+MMD_API int mmd_probe_attention(const float* q, const void* kv, float* out, int T, int S, int H, int dh, void* stream);
 /* Greedy token pick with the HF repetition penalty (models/modeling_live.py:51-77). */
 MMD_API int mmd_argmax(const float* logits, int64_t V, const int64_t* penal_ids, int n_penal, float penalty,
                        int64_t* out_id, void* stream);

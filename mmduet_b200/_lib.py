@@ -103,6 +103,7 @@ SIGNATURES = {
     "mmd_tap_pool": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                              c_int, c_void_p]),
     "mmd_heads": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "mmd_probe_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mmd_argmax": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     "mmd_grounding_sweep": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                     c_void_p, c_void_p]),

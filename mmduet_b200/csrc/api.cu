@@ -171,8 +171,10 @@ int mmd_set_gemm_2cta(int on) {
 }
 
 int mmd_set_attention_impl(int impl) {
-  if (impl < 0 || impl > 2) return fail(MMD_ERR_ARG, "mmd_set_attention_impl: 0 (mma.sync), 1 (tcgen05) or 2 (auto)");
-  mmd::g_attention_impl = impl;
+  // bit 2 (value 4) switches the decode kernel OFF (diagnostics / A-B measurements); the low two bits select the general kernels
+  if (impl < 0 || (impl & 3) > 2 || impl > 7) return fail(MMD_ERR_ARG, "mmd_set_attention_impl: 0 (mma.sync), 1 (tcgen05) or 2 (auto), +4 = no decode kernel");
+  mmd::g_attention_impl = impl & 3;
+  mmd::g_kv_decode = (impl & 4) ? 0 : 1;
   return 0;
 }
 
@@ -290,6 +292,12 @@ int mmd_heads(const float* hidden_f32, const int* rows, const float* head_w, flo
               int H, void* stream) {
   RUNK(mmd::launch_heads(hidden_f32, rows, head_w, logits_out, scores_out, n_rows, H, S(stream)), "mmd_heads");
   return check_launch("mmd_heads");
+}
+
+int mmd_probe_attention(const float* q, const void* kv, float* out, int T, int S_, int H, int dh, void* stream) {
+  if (q == nullptr || kv == nullptr || out == nullptr) return fail(MMD_ERR_ARG, "mmd_probe_attention: null argument");
+  RUNK(mmd::launch_probe_attention(q, static_cast<const __nv_bfloat16*>(kv), out, T, S_, H, dh, S(stream)), "mmd_probe_attention");
+  return check_launch("mmd_probe_attention");
 }
 
 int mmd_argmax(const float* logits, int64_t V, const int64_t* penal_ids, int n_penal, float penalty, int64_t* out_id, void* stream) {
@@ -473,6 +481,7 @@ struct DecBufs {
 constexpr int kMaxPrecRows = 128;   // rows carried as bf16 hi+lo pairs (one <= 128-token tile of the swap-AB GEMM)
 constexpr int kMaxSplits = 8;
 constexpr int kMaxAttnSplits = 32;
+constexpr int kMaxDecodeSplits = 64;   // decode kernel (<= 2 tokens per stream): one stream over all SMs
 static int64_t dec_carve(const mmd_dec_weights* w, int max_tokens, int max_lm_rows, Bump& b, DecBufs* o) {
   const int64_t M = max_tokens;
   const int H = w->hidden, QD = w->q_heads * w->head_dim, NQKV = (w->q_heads + 2 * w->kv_heads) * w->head_dim;
@@ -486,8 +495,9 @@ static int64_t dec_carve(const mmd_dec_weights* w, int max_tokens, int max_lm_ro
   o->q = b.take<__nv_bfloat16>(M * QD);
   o->attn = b.take<__nv_bfloat16>(M * QD);
   o->h = b.take<__nv_bfloat16>(M * w->mlp);
-  o->o_part = b.take<float>((int64_t)kMaxAttnSplits * M * QD);
-  o->ml_part = b.take<float>((int64_t)kMaxAttnSplits * M * w->q_heads * 2);
+  const int64_t part_rows = kMaxAttnSplits * M > 2 * kMaxDecodeSplits ? kMaxAttnSplits * M : 2 * kMaxDecodeSplits;
+  o->o_part = b.take<float>(part_rows * QD);
+  o->ml_part = b.take<float>(part_rows * w->q_heads * 2);
   o->lm_x = b.take<__nv_bfloat16>((int64_t)(max_lm_rows > 0 ? max_lm_rows : 1) * H);
   return b.off;
 }
@@ -546,7 +556,11 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
   const int s_down = choose_splits(c->num_sms, H, I, M);
   const int s_down_p = side_prec ? choose_splits(c->num_sms, H, I, P) : 1;
   int attn_splits = mmd::kv_attention_pick_splits(st->max_n_q * (Hq / Hkv), Hkv, st->n_streams, st->max_kv_len, c->num_sms);
-  if (attn_splits > kMaxAttnSplits) attn_splits = kMaxAttnSplits;
+  {   // the partial buffers hold kMaxAttnSplits x M rows, or kMaxDecodeSplits splits of <= 16 rows (dec_carve)
+    const int64_t cap_rows = kMaxAttnSplits * (int64_t)M > 2 * kMaxDecodeSplits ? kMaxAttnSplits * (int64_t)M : 2 * kMaxDecodeSplits;
+    while (attn_splits > 1 && (int64_t)attn_splits * M > cap_rows) --attn_splits;
+    if (attn_splits > kMaxDecodeSplits) attn_splits = kMaxDecodeSplits;
+  }
   // Swap-AB + split-K (weights on the 128 UMMA rows, all SMs busy) wins up to ~1200 tokens per pass on this model
   // (measured: 8/10/24-frame passes, profiles/r01_decoder_paths.md); the normal-orientation CTA-pair path (UMMA M = 256,
   // TMA-store epilogue, interleaved gate/up + pairwise SwiGLU) only pays off for much larger multi-stream batches.

@@ -812,6 +812,83 @@ int launch_argmax(const float* partial, int n_planes, long long plane_stride, in
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// SigLIP attention-pooling head, the attention itself: ONE learned probe query per frame attends over the S patch tokens
+// (SiglipMultiheadAttentionPoolingHead -> nn.MultiheadAttention, TF:models/siglip/modeling_siglip.py; the CLS token of
+// models/vision_live.py:26-30).  q [H*dh] fp32 is the projected probe, already scaled by dh^-0.5 (a constant of the
+// weights); kv bf16 [T*S, 2*H*dh] = [K | V] from the in-projection GEMM.  One block per (frame, head): scores and softmax
+// in fp32 shared memory, V accumulation split over the warps.  out fp32 [T, H*dh].
+// ------------------------------------------------------------------------------------------------------------
+__global__ void probe_attention_kernel(const float* __restrict__ q, const __nv_bfloat16* __restrict__ kv, float* __restrict__ out,
+                                       int S, int H, int dh) {
+  extern __shared__ float psm[];                 // S scores, then (warps x dh) partial outputs
+  __shared__ float red[32];
+  const int t = blockIdx.x, h = blockIdx.y, D = H * dh;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const __nv_bfloat16* kbase = kv + (long long)t * S * 2 * D + h * dh;
+  const float* qh = q + h * dh;
+  float mx = -INFINITY;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const __nv_bfloat16* kr = kbase + (long long)s * 2 * D;
+    float acc = 0.f;
+    for (int d = 0; d < dh; d += 2) {
+      const float2 kf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(kr + d));
+      acc = fmaf(kf.x, qh[d], fmaf(kf.y, qh[d + 1], acc));
+    }
+    psm[s] = acc;
+    mx = fmaxf(mx, acc);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < nw; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const float p = expf(psm[s] - mx);
+    psm[s] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < nw; ++i) sum += red[i];
+  // V: warp w takes keys w, w + nw, ...; lane covers dims lane, lane + 32, ... (dh <= 128)
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int s = warp; s < S; s += nw) {
+    const float p = psm[s];
+    const __nv_bfloat16* vr = kbase + (long long)s * 2 * D + D;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int d = lane + 32 * i;
+      if (d < dh) acc[i] = fmaf(p, __bfloat162float(vr[d]), acc[i]);
+    }
+  }
+  float* part = psm + S;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int d = lane + 32 * i;
+    if (d < dh) part[warp * dh + d] = acc[i];
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < dh; d += blockDim.x) {
+    float o = 0.f;
+    for (int w2 = 0; w2 < nw; ++w2) o += part[w2 * dh + d];
+    out[(long long)t * D + h * dh + d] = o / sum;
+  }
+}
+int launch_probe_attention(const float* q, const __nv_bfloat16* kv, float* out, int T, int S, int H, int dh, cudaStream_t s) {
+  if (T <= 0) return 0;
+  if (dh > 128 || dh % 2 != 0 || S <= 0 || H <= 0) return -2;
+  const int threads = 256;
+  const size_t smem = (size_t)(S + (threads / 32) * dh) * sizeof(float);
+  if (smem > 48 * 1024) return -2;
+  probe_attention_kernel<<<dim3(T, H), threads, smem, s>>>(q, kv, out, S, H, dh);
+  return 0;
+}
+
 // out[row, :] = bf16(sum_s partial[s][row, :] + bias)   (generic split-K finish for small-M linear layers)
 __global__ void splitk_finish_bf16_kernel(const float* __restrict__ partial, int n_planes, long long plane_stride,
                                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int N, int act) {

@@ -38,6 +38,7 @@ int launch_gather_rows_bf16_to_f32(const __nv_bfloat16* table, const __nv_bfloat
 int launch_gather_rows_f32_to_bf16(const float* src, const int* idx, __nv_bfloat16* dst, int T, int S, int G, int D, int hilo, cudaStream_t s);
 int launch_tap_pool(const void* in, int in_dtype, void* out, int out_dtype, const int* tap_idx, const float* tap_w, int T,
                     int n_in, int n_out, int max_taps, int D, int maxpool, cudaStream_t s);
+int launch_probe_attention(const float* q, const __nv_bfloat16* kv, float* out, int T, int S, int H, int dh, cudaStream_t s);
 int launch_heads(const float* hidden_f32, const int* rows, const float* head_w, float* logits_out, float* scores_out, int n_rows,
                  int H, cudaStream_t s);
 int launch_argmax(const float* partial, int n_planes, long long plane_stride, int V, const long long* penal_ids, int n_penal,
@@ -48,6 +49,7 @@ int launch_splitk_finish_bf16(const float* partial, int n_planes, long long plan
 int launch_vit_attention(const __nv_bfloat16* qkv, __nv_bfloat16* out, int T, int S, int H, int dh, int split_hi_lo, cudaStream_t s);
 
 extern int g_attention_impl;  // 0 = mma.sync attention kernels (default), 1 = tcgen05/TMEM attention kernels
+extern int g_kv_decode;       // 1 (default): <= 16 stacked query rows -> HBM-streaming decode kernel (kv_decode_attention.cu)
 int kv_attention_pick_splits(int max_rows, int Hkv, int n_streams, int max_kv_len, int num_sms);
 int launch_kv_attention(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, const int* stream_desc, const int* block_tables,
                         int n_streams, int max_n_q, int total_q, int max_kv_len, float* o_part, float* ml_part, __nv_bfloat16* out,

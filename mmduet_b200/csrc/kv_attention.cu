@@ -250,19 +250,22 @@ __global__ void kv_attention_combine_kernel(const float* __restrict__ o_part, co
   const long long grow = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (grow >= part_stride_rows) return;
   const int lane = threadIdx.x & 31;
-  float2 ml = make_float2(-INFINITY, 0.f);
+  // lane l owns the (m, l) pairs of splits l and l + 32 (up to 64 splits: the decode kernel spreads one stream over all SMs)
+  float2 ml = make_float2(-INFINITY, 0.f), ml2 = make_float2(-INFINITY, 0.f);
   if (lane < n_splits) ml = __ldg(reinterpret_cast<const float2*>(ml_part + ((long long)lane * part_stride_rows + grow) * 2));
-  float mmax = ml.x;
+  if (lane + 32 < n_splits) ml2 = __ldg(reinterpret_cast<const float2*>(ml_part + ((long long)(lane + 32) * part_stride_rows + grow) * 2));
+  float mmax = fmaxf(ml.x, ml2.x);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mmax = fmaxf(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
   const float w_mine = (ml.x == -INFINITY) ? 0.f : exp2f(ml.x - mmax);
-  float lsum = w_mine * ml.y;
+  const float w_mine2 = (ml2.x == -INFINITY) ? 0.f : exp2f(ml2.x - mmax);
+  float lsum = w_mine * ml.y + w_mine2 * ml2.y;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
   for (int s = 0; s < n_splits; ++s) {
-    const float w = __shfl_sync(0xffffffffu, w_mine, s);
+    const float w = s < 32 ? __shfl_sync(0xffffffffu, w_mine, s) : __shfl_sync(0xffffffffu, w_mine2, s - 32);
     const float4 o = __ldg(reinterpret_cast<const float4*>(o_part + ((long long)s * part_stride_rows + grow) * KA_DH) + lane);
     acc.x += w * o.x; acc.y += w * o.y; acc.z += w * o.z; acc.w += w * o.w;
   }
@@ -290,7 +293,15 @@ int launch_kv_attention_tc_main(const __nv_bfloat16* q, const __nv_bfloat16* kv_
                                 int n_streams, int max_n_q, int total_q, float* o_part, float* ml_part, int Hq, int Hkv, int n_splits,
                                 cudaStream_t s);
 
+bool kv_decode_applicable(int max_rows);
+int kv_decode_pick_splits(int Hkv, int n_streams, int max_kv_len, int num_sms);
+int launch_kv_decode_attention(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, const int* stream_desc, const int* block_tables,
+                               int n_streams, int total_q, float* o_part, float* ml_part, int Hq, int Hkv, int n_splits, cudaStream_t s);
+// 1 (default): passes with <= 16 stacked query rows per KV head (token-by-token generation) take the HBM-streaming decode kernel
+int g_kv_decode = 1;
+
 int kv_attention_pick_splits(int max_rows, int Hkv, int n_streams, int max_kv_len, int num_sms) {
+  if (g_kv_decode && kv_decode_applicable(max_rows)) return kv_decode_pick_splits(Hkv, n_streams, max_kv_len, num_sms);
   // mma.sync kernel: 128 query rows per CTA, two CTAs per SM; tcgen05 kernel: 256 rows per CTA, one CTA per SM
   const bool tc = kv_use_tc(max_rows, max_kv_len);
   const int rows_per_cta = tc ? 2 * KA_BM : KA_BM;
@@ -320,7 +331,7 @@ int launch_kv_attention(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, c
                         int n_streams, int max_n_q, int total_q, int max_kv_len, float* o_part, float* ml_part, __nv_bfloat16* out,
                         int Hq, int Hkv, int dh, int page_tokens, int n_splits, cudaStream_t s) {
   if (n_streams <= 0 || total_q <= 0) return 0;
-  if (dh != KA_DH || page_tokens != KA_BN || Hq % Hkv != 0 || n_splits < 1 || n_splits > 32) return -2;   // combine: one lane per split
+  if (dh != KA_DH || page_tokens != KA_BN || Hq % Hkv != 0 || n_splits < 1 || n_splits > 64) return -2;   // combine: two splits per lane
   constexpr int SMEM = (KA_BM + 4 * KA_BN) * KA_LDS * 2;
   static PerDeviceFlag attr;
   if (!attr.cur()) {
@@ -332,7 +343,12 @@ int launch_kv_attention(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, c
   dim3 grid(q_tiles * Hkv, n_splits, n_streams);
   const float scale_log2e = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
   const long long part_rows = (long long)total_q * Hq;
-  if (kv_use_tc(max_n_q * G, max_kv_len)) {
+  if (g_kv_decode && kv_decode_applicable(max_n_q * G)) {
+    const int rc = launch_kv_decode_attention(q, kv_layer, stream_desc, block_tables, n_streams, total_q, o_part, ml_part, Hq, Hkv, n_splits, s);
+    if (rc != 0) return rc;
+  } else if (n_splits > 32) {
+    return -2;
+  } else if (kv_use_tc(max_n_q * G, max_kv_len)) {
     const int rc = launch_kv_attention_tc_main(q, kv_layer, stream_desc, block_tables, n_streams, max_n_q, total_q, o_part, ml_part, Hq,
                                                Hkv, n_splits, s);
     if (rc != 0) return rc;

@@ -106,8 +106,19 @@ class VisionEngine:
                                    n_layers=self.n_layers, k_pad=self.k_pad, attn_out_split=int(attn_out_split), patch_w=pw.data_ptr(), patch_b=patch_b.data_ptr(),
                                    pos_emb=pos.data_ptr(), layers=layers)
         self.post_ln = None
+        self.cls_head = None
         if legacy_post_ln:
             self.post_ln = (_f32(sd[VT + "post_layernorm.weight"], dev), _f32(sd[VT + "post_layernorm.bias"], dev))
+            if VT + "head.probe" in sd:
+                # SiglipMultiheadAttentionPoolingHead (frame_token_cls): the probe's query is a constant of the weights
+                hp = VT + "head."
+                w_in, b_in = sd[hp + "attention.in_proj_weight"].float(), sd[hp + "attention.in_proj_bias"].float()
+                q = (sd[hp + "probe"].float().view(1, D) @ w_in[:D].t() + b_in[:D]) * (D // cfg.vit_heads) ** -0.5
+                self.cls_head = dict(q=_f32(q.view(-1), dev), kv_w=_bf16(w_in[D:], dev), kv_b=_f32(b_in[D:], dev),
+                                     out_w=_bf16(sd[hp + "attention.out_proj.weight"], dev), out_b=_f32(sd[hp + "attention.out_proj.bias"], dev),
+                                     ln_w=_f32(sd[hp + "layernorm.weight"], dev), ln_b=_f32(sd[hp + "layernorm.bias"], dev),
+                                     fc1_w=_bf16(sd[hp + "mlp.fc1.weight"], dev), fc1_b=_f32(sd[hp + "mlp.fc1.bias"], dev),
+                                     fc2_w=_bf16(sd[hp + "mlp.fc2.weight"], dev), fc2_b=_f32(sd[hp + "mlp.fc2.bias"], dev))
         self.proj = None
         if with_projector:
             taps = pooling_taps(cfg.grid, cfg.pool_stride, cfg.pool_mode)
@@ -197,17 +208,42 @@ class VisionEngine:
             _lib.check(rc, "mmd_projector_pool")
         return out
 
-    def legacy_encode(self, frames_0_255, frame_token_pooled=(7, 7)):
-        """models/vision_live.py:11-31 semantics: rescale+normalize, all layers, post_layernorm, adaptive_avg_pool2d."""
+    def _cls_tokens(self, normed, T):
+        """pooler_output of the SigLIP vision model for T frames: attention pooling over the post-layernormed patch tokens
+        (probe attention on CUDA cores, every linear layer through the tcgen05 GEMM), then residual MLP.  -> fp32 [T, D]."""
+        from . import ops
+        h, D, S = self.cls_head, self.cfg.vit_dim, self.cfg.patches
+        x = normed.to(torch.bfloat16)                                                      # dtype cast (plumbing)
+        kv = ops.gemm(x, h["kv_w"], bias=h["kv_b"])                                         # [T*S, 2D] bf16
+        att = torch.empty(T, D, dtype=torch.float32, device=self.device)
+        rc = self.lib.mmd_probe_attention(h["q"].data_ptr(), kv.data_ptr(), att.data_ptr(), T, S, self.cfg.vit_heads, D // self.cfg.vit_heads,
+                                          _lib.stream_ptr())
+        _lib.check(rc, "mmd_probe_attention")
+        res = ops.gemm(att.to(torch.bfloat16), h["out_w"], bias=h["out_b"], epi=_lib.EPI_F32)    # residual [T, D] fp32
+        hb = torch.empty(T, D, dtype=torch.bfloat16, device=self.device)
+        rc = self.lib.mmd_layernorm(res.data_ptr(), h["ln_w"].data_ptr(), h["ln_b"].data_ptr(), hb.data_ptr(), 0, T, D, 1e-6, _lib.stream_ptr())
+        _lib.check(rc, "mmd_layernorm")
+        mid = ops.gemm(hb, h["fc1_w"], bias=h["fc1_b"], act=_lib.ACT_GELU_TANH)
+        ops.gemm(mid, h["fc2_w"], bias=h["fc2_b"], out=res, epi=_lib.EPI_RESID_F32)
+        return res
+
+    def legacy_encode(self, frames_0_255, frame_token_pooled=(7, 7), frame_token_cls=False):
+        """models/vision_live.py:11-31 semantics: rescale+normalize, all layers, post_layernorm, adaptive_avg_pool2d to
+        `frame_token_pooled` (None/empty: no spatial tokens) and, with frame_token_cls, the pooler_output as the first token."""
         if self.post_ln is None:
             raise _lib.MmdError("legacy_encode needs legacy_post_ln=True (post_layernorm weights)")
+        if frame_token_cls and self.cls_head is None:
+            raise _lib.MmdError("frame_token_cls needs the vision model's head.* weights (SigLIP attention-pooling head)")
+        if not frame_token_pooled and not frame_token_cls:
+            raise ValueError("frame_token_pooled must be set when frame_token_cls is False")
         outs = []
-        key = tuple(frame_token_pooled)
-        if key not in self._legacy_taps:
+        key = tuple(frame_token_pooled) if frame_token_pooled else None
+        if key is not None and key not in self._legacy_taps:
             gidx, tidx, tw, max_taps = taps_to_tables(pooling_taps(self.cfg.grid, 0, "adaptive", key))
             assert gidx.numel() == self.cfg.patches
             self._legacy_taps[key] = (tidx.to(self.device).contiguous(), tw.to(self.device).contiguous(), max_taps, tidx.shape[0])
-        tidx, tw, max_taps, n_out = self._legacy_taps[key]
+        if key is not None:
+            tidx, tw, max_taps, n_out = self._legacy_taps[key]
         D, S = self.cfg.vit_dim, self.cfg.patches
         for b in range(0, frames_0_255.shape[0], self.MAX_BATCH):
             chunk = frames_0_255[b:b + self.MAX_BATCH]
@@ -217,11 +253,16 @@ class VisionEngine:
             rc = self.lib.mmd_layernorm(resid.data_ptr(), self.post_ln[0].data_ptr(), self.post_ln[1].data_ptr(), normed.data_ptr(), 1,
                                         T * S, D, 1e-6, _lib.stream_ptr())
             _lib.check(rc, "mmd_layernorm")
-            out = torch.empty(T, n_out, D, dtype=torch.float32, device=self.device)
-            rc = self.lib.mmd_tap_pool(normed.data_ptr(), _lib.DT_F32, out.data_ptr(), _lib.DT_F32, tidx.data_ptr(), tw.data_ptr(), T, S,
-                                       n_out, max_taps, D, 0, _lib.stream_ptr())
-            _lib.check(rc, "mmd_tap_pool")
-            outs.append(out)
+            parts = []
+            if frame_token_cls:
+                parts.append(self._cls_tokens(normed, T)[:, None])
+            if key is not None:
+                out = torch.empty(T, n_out, D, dtype=torch.float32, device=self.device)
+                rc = self.lib.mmd_tap_pool(normed.data_ptr(), _lib.DT_F32, out.data_ptr(), _lib.DT_F32, tidx.data_ptr(), tw.data_ptr(), T, S,
+                                           n_out, max_taps, D, 0, _lib.stream_ptr())
+                _lib.check(rc, "mmd_tap_pool")
+                parts.append(out)
+            outs.append(parts[0] if len(parts) == 1 else torch.cat(parts, 1))
         return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
 

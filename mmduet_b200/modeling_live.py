@@ -227,12 +227,9 @@ def fast_greedy_generate(*, model, inputs_embeds, past_key_values, eos_token_id,
 # legacy entry (models/vision_live.py)
 # ------------------------------------------------------------------------------------------------------------
 def _siglip_vision_encode(vision_model: VisionEngine, frames, frame_token_cls: bool = False, frame_token_pooled=(7, 7), **kwargs):
-    """models/vision_live.py:11-31: frames are raw 0..255 values (float or uint8)."""
-    if frame_token_cls:
-        raise NotImplementedError("frame_token_cls (SigLIP attention-pool head) is not on the accelerated path")
-    if not frame_token_pooled:
-        raise ValueError("frame_token_pooled must be set when frame_token_cls is False")
-    return vision_model.legacy_encode(frames, tuple(frame_token_pooled))
+    """models/vision_live.py:11-31: frames are raw 0..255 values (float or uint8) -> [T, (1 +) ph*pw, D]: the optional CLS
+    token (pooler_output of the SigLIP attention-pooling head) followed by the adaptive-avg-pooled spatial tokens."""
+    return vision_model.legacy_encode(frames, tuple(frame_token_pooled) if frame_token_pooled else None, frame_token_cls=bool(frame_token_cls))
 
 
 def build_live_vision(config, state_dict=None, device="cuda"):

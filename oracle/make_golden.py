@@ -60,22 +60,27 @@ def golden_legacy(arch, name, seed, n_frames):
     vm = SiglipVisionModel(vcfg).vision_model.eval()
     sd = {k[len(R.VT):]: v for k, v in w.items() if k.startswith(R.VT)}
     missing, unexpected = vm.load_state_dict(sd, strict=False)
-    assert not unexpected and all(m.startswith("head.") for m in missing), (missing, unexpected)
+    assert not unexpected and not missing, (missing, unexpected)
     frames = R.synthetic_frames(n_frames, seed=seed + 1).float()
     with torch.no_grad():
         out = vl._siglip_vision_encode(vm, frames, frame_token_cls=False, frame_token_pooled=(7, 7))
-    np.savez_compressed(os.path.join(OUT, name + ".npz"), seed=seed, n_frames=n_frames, tokens=out.numpy())
-    print(name, out.shape)
+        cls_sp = vl._siglip_vision_encode(vm, frames, frame_token_cls=True, frame_token_pooled=(3, 3))     # [T, 1 + 9, D]
+        cls_only = vl._siglip_vision_encode(vm, frames, frame_token_cls=True, frame_token_pooled=None)      # [T, 1, D]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), seed=seed, n_frames=n_frames, tokens=out.numpy(), cls_tokens=cls_sp.numpy(),
+                        cls_only=cls_only.numpy())
+    print(name, out.shape, cls_sp.shape, cls_only.shape)
 
 
 def main():
+    import sys
     os.makedirs(OUT, exist_ok=True)
     torch.set_grad_enabled(False)
     torch.set_num_threads(8)
-    golden_stream(A.TINY, "tiny_stream_bilinear", seed=11, n_frames=4, prefix_len=9)
-    golden_stream(A.TINY, "tiny_stream_average", seed=12, n_frames=2, prefix_len=5, pool_mode="average")
-    golden_stream(A.TINY, "tiny_stream_max", seed=13, n_frames=2, prefix_len=5, pool_mode="max")
-    golden_stream(A.SMALL, "small_stream_bilinear", seed=21, n_frames=3, prefix_len=13)
+    if "--legacy-only" not in sys.argv:
+        golden_stream(A.TINY, "tiny_stream_bilinear", seed=11, n_frames=4, prefix_len=9)
+        golden_stream(A.TINY, "tiny_stream_average", seed=12, n_frames=2, prefix_len=5, pool_mode="average")
+        golden_stream(A.TINY, "tiny_stream_max", seed=13, n_frames=2, prefix_len=5, pool_mode="max")
+        golden_stream(A.SMALL, "small_stream_bilinear", seed=21, n_frames=3, prefix_len=13)
     golden_legacy(A.TINY, "tiny_legacy_vision", seed=31, n_frames=2)
 
 

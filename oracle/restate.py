@@ -97,14 +97,40 @@ def preprocess_frames(frames_u8):
 # ------------------------------------------------------------------------------------------------------------
 # legacy entry: models/vision_live.py:11-31 (_siglip_vision_encode on an HF SiglipVisionModel.vision_model)
 # ------------------------------------------------------------------------------------------------------------
-def legacy_siglip_vision_encode(w, arch, frames_0_255, frame_token_pooled=(7, 7)):
-    """normalize(frames/255, .5, .5) -> all `vit_layers_total` layers -> post_layernorm -> adaptive_avg_pool2d."""
+def siglip_pooling_head(w, arch, h):
+    """SiglipMultiheadAttentionPoolingHead (TF:models/siglip/modeling_siglip.py): a learned probe attends over the patch tokens
+    (nn.MultiheadAttention, batch_first), then x + MLP(LayerNorm(x)); returns [T, D] = vision_outputs.pooler_output."""
+    hp = VT + "head."
+    T, S, D = h.shape
+    H, dh = arch.vit_heads, arch.vit_head_dim
+    w_in, b_in = w[hp + "attention.in_proj_weight"], w[hp + "attention.in_proj_bias"]
+    q = F.linear(w[hp + "probe"].expand(T, 1, D), w_in[:D], b_in[:D]).view(T, 1, H, dh).transpose(1, 2)
+    k = F.linear(h, w_in[D:2 * D], b_in[D:2 * D]).view(T, S, H, dh).transpose(1, 2)
+    v = F.linear(h, w_in[2 * D:], b_in[2 * D:]).view(T, S, H, dh).transpose(1, 2)
+    a = torch.softmax((q * dh ** -0.5) @ k.transpose(-1, -2), dim=-1)
+    o = (a @ v).transpose(1, 2).reshape(T, 1, D)
+    x = F.linear(o, w[hp + "attention.out_proj.weight"], w[hp + "attention.out_proj.bias"])
+    y = F.layer_norm(x, (D,), w[hp + "layernorm.weight"], w[hp + "layernorm.bias"], 1e-6)
+    y = F.linear(F.gelu(F.linear(y, w[hp + "mlp.fc1.weight"], w[hp + "mlp.fc1.bias"]), approximate="tanh"),
+                 w[hp + "mlp.fc2.weight"], w[hp + "mlp.fc2.bias"])
+    return (x + y)[:, 0]
+
+
+def legacy_siglip_vision_encode(w, arch, frames_0_255, frame_token_pooled=(7, 7), frame_token_cls=False):
+    """models/vision_live.py:11-31: normalize(frames/255, .5, .5) -> all `vit_layers_total` layers -> post_layernorm ->
+    adaptive_avg_pool2d spatial tokens, optionally preceded by the CLS token (pooler_output)."""
     x = (frames_0_255 * 0.00392156862745098 - 0.5) / 0.5
     h = siglip_tower(w, arch, x, n_layers=arch.vit_layers_total)
     h = F.layer_norm(h, (h.shape[-1],), w[VT + "post_layernorm.weight"], w[VT + "post_layernorm.bias"], 1e-6)
-    s = int(math.sqrt(h.shape[1]))
-    sp = F.adaptive_avg_pool2d(h.reshape(h.shape[0], s, s, h.shape[-1]).permute(0, 3, 1, 2), frame_token_pooled)
-    return sp.flatten(2, 3).permute(0, 2, 1)
+    sp = None
+    if frame_token_pooled:
+        s = int(math.sqrt(h.shape[1]))
+        sp = F.adaptive_avg_pool2d(h.reshape(h.shape[0], s, s, h.shape[-1]).permute(0, 3, 1, 2), tuple(frame_token_pooled))
+        sp = sp.flatten(2, 3).permute(0, 2, 1)
+        if not frame_token_cls:
+            return sp
+    cls = siglip_pooling_head(w, arch, h)[:, None]
+    return cls if sp is None else torch.cat([cls, sp], dim=1)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -387,6 +413,21 @@ def make_weights(arch, seed=1234, device="cpu", dtype=torch.float32, round_bf16=
     if legacy_post_ln:
         w[VT + "post_layernorm.weight"] = 1.0 + rnd(D, std=0.05)
         w[VT + "post_layernorm.bias"] = rnd(D, std=0.05)
+        # attention-pooling head (frame_token_cls); its own generator so that no other tensor of the dict depends on it
+        g_main, g = g, torch.Generator(device=gen_dev).manual_seed(seed + 977)
+        hp = VT + "head."
+        w[hp + "probe"] = rnd(1, 1, D, std=1.0)
+        w[hp + "attention.in_proj_weight"] = rnd(3 * D, D, std=D ** -0.5)
+        w[hp + "attention.in_proj_bias"] = rnd(3 * D, std=0.02)
+        w[hp + "attention.out_proj.weight"] = rnd(D, D, std=D ** -0.5)
+        w[hp + "attention.out_proj.bias"] = rnd(D, std=0.02)
+        w[hp + "layernorm.weight"] = 1.0 + rnd(D, std=0.05)
+        w[hp + "layernorm.bias"] = rnd(D, std=0.05)
+        w[hp + "mlp.fc1.weight"] = rnd(Dm, D, std=(2.0 / (D + Dm)) ** 0.5)
+        w[hp + "mlp.fc1.bias"] = rnd(Dm, std=0.02)
+        w[hp + "mlp.fc2.weight"] = rnd(D, Dm, std=(2.0 / (D + Dm)) ** 0.5)
+        w[hp + "mlp.fc2.bias"] = rnd(D, std=0.02)
+        g = g_main
     H = arch.hidden
     w["model.mm_projector.0.weight"] = rnd(H, D, std=(3 * D) ** -0.5)
     w["model.mm_projector.0.bias"] = rnd(H, std=0.02)

@@ -378,8 +378,9 @@ def test_qkv_finish_and_kv_attention(env, attn_impl):
     assert (got.float() - k0).abs().max() < 5e-2
 
 
-@pytest.mark.parametrize("L,n_q,splits", [(8192, 49, (0, 1, 5)), (30000, 49, (0, 13, 32)), (58832, 49, (0, 7, 32)), (58800, 1, (0, 32)),
-                                           (5912, 1960, (0, 1, 4)), (29432, 490, (0, 3)), (2047, 49, (0, 2)), (2048, 49, (0, 2))])
+@pytest.mark.parametrize("L,n_q,splits", [(8192, 49, (0, 1, 5)), (30000, 49, (0, 13, 32)), (58832, 49, (0, 7, 32)), (58800, 1, (0, 32, 64)),
+                                           (5912, 1960, (0, 1, 4)), (29432, 490, (0, 3)), (2047, 49, (0, 2)), (2048, 49, (0, 2)),
+                                           (1, 1, (0, 1)), (63, 1, (0,)), (65, 2, (0, 2)), (3333, 2, (0, 37)), (200, 1, (0, 64))])
 def test_kv_attention_long_context(env, L, n_q, splits):
     """Paged KV-append attention at the contexts of BASELINE configs[1] (5.9k), configs[2] (29.4k) and configs[4] (58.8k),
     1..32 KV splits, auto implementation (tcgen05 front end from 2k context) and forced tcgen05, against a dense fp32
@@ -412,12 +413,15 @@ def test_kv_attention_long_context(env, L, n_q, splits):
         ref[:, h * G:(h + 1) * G] = torch.einsum("gqk,kd->qgd", torch.softmax(sc, -1), v[:, h].float())
         del sc
     ref = ref.reshape(n_q, Hq * dh)
-    for impl in (2, 1):
+    # n_q <= 2 (<= 16 stacked rows per KV head): the HBM-streaming decode kernel, up to 64 splits; 6 = auto with it switched off
+    for impl in ((2, 6) if n_q <= 2 else (2, 1)):
         _lib.check(lib.mmd_set_attention_impl(impl))
         try:
             for ns in splits:
+                if ns > 32 and impl != 2:
+                    continue
                 n_s = ns or lib.mmd_kv_attention_splits(ctx, n_q, Hq, Hkv, 1, L)
-                assert 1 <= n_s <= 32
+                assert 1 <= n_s <= (64 if n_q <= 2 else 32)
                 o_part = torch.full((n_s, n_q * Hq, dh), float("nan"), device="cuda")
                 ml = torch.full((n_s, n_q * Hq, 2), float("nan"), device="cuda")
                 out = torch.full((n_q, Hq * dh), float("nan"), device="cuda", dtype=torch.bfloat16)
@@ -550,3 +554,20 @@ def test_grounding_sweep_bit_exact(env):
     assert (c[..., 0] == 0).all() and (c[..., 1] == 2).all()
     with pytest.raises(ValueError):
         PP.sweep_counts([], [])
+
+
+@pytest.mark.parametrize("T,S,H,dh", [(2, 729, 16, 72), (1, 100, 2, 72), (3, 50, 4, 128)])
+def test_probe_attention(env, T, S, H, dh):
+    """One probe query per frame over S keys (SigLIP attention-pooling head) vs dense fp32."""
+    _lib, ops, lib, ctx = env
+    D = H * dh
+    torch.manual_seed(S)
+    q = torch.randn(D, device="cuda") * dh ** -0.5
+    kv = (torch.randn(T * S, 2 * D, device="cuda") * 1.5).bfloat16()
+    out = torch.full((T, D), float("nan"), device="cuda")
+    _lib.check(lib.mmd_probe_attention(q.data_ptr(), kv.data_ptr(), out.data_ptr(), T, S, H, dh, _s()))
+    k = kv[:, :D].float().view(T, S, H, dh).transpose(1, 2)
+    v = kv[:, D:].float().view(T, S, H, dh).transpose(1, 2)
+    a = torch.softmax(torch.einsum("hd,thsd->ths", q.view(H, dh), k), -1)
+    ref = torch.einsum("ths,thsd->thd", a, v).reshape(T, D)
+    assert (out - ref).abs().max() < 1e-4
