@@ -277,6 +277,67 @@ __global__ void kv_attention_combine_kernel(const float* __restrict__ o_part, co
   *reinterpret_cast<uint2*>(out + grow * KA_DH + lane * 4) = pk;
 }
 
+// The same merge for FEW rows and MANY splits (token-by-token decode: 28 rows x up to 64 splits): one block per row, the
+// eight warps take the splits round-robin so that every partial row is in flight at once (a single warp walking 37 splits
+// in order costs ~7 us of dependent L2 latency), then a shared-memory reduction.  Same arithmetic order per warp as above
+// is not required: fp32 sums of <= 64 non-negative-weighted terms, the result is rounded to bf16.
+__global__ void kv_attention_combine_wide_kernel(const float* __restrict__ o_part, const float* __restrict__ ml_part,
+                                                 __nv_bfloat16* __restrict__ out, int n_splits, long long part_stride_rows) {
+  __shared__ float sw[64];
+  __shared__ float4 sacc[8][32];
+  __shared__ float s_l;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const long long grow = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    float2 ml = make_float2(-INFINITY, 0.f), ml2 = make_float2(-INFINITY, 0.f);
+    if (lane < n_splits) ml = __ldg(reinterpret_cast<const float2*>(ml_part + ((long long)lane * part_stride_rows + grow) * 2));
+    if (lane + 32 < n_splits) ml2 = __ldg(reinterpret_cast<const float2*>(ml_part + ((long long)(lane + 32) * part_stride_rows + grow) * 2));
+    float mmax = fmaxf(ml.x, ml2.x);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mmax = fmaxf(mmax, __shfl_xor_sync(0xffffffffu, mmax, o));
+    const float w1 = (ml.x == -INFINITY) ? 0.f : exp2f(ml.x - mmax), w2 = (ml2.x == -INFINITY) ? 0.f : exp2f(ml2.x - mmax);
+    float lsum = w1 * ml.y + w2 * ml2.y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    sw[lane] = w1;
+    sw[lane + 32] = w2;
+    if (lane == 0) s_l = lsum;
+  }
+  // the O rows do not depend on the weights: issue this warp's loads (<= 8 splits) before waiting for them
+  float4 v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int s = warp + 8 * i;
+    v[i] = s < n_splits ? __ldg(reinterpret_cast<const float4*>(o_part + ((long long)s * part_stride_rows + grow) * KA_DH) + lane)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int s = warp + 8 * i;
+    const float w = s < n_splits ? sw[s] : 0.f;
+    acc.x += w * v[i].x; acc.y += w * v[i].y; acc.z += w * v[i].z; acc.w += w * v[i].w;
+  }
+  sacc[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float4 a = sacc[w][lane];
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    const float inv = 1.f / s_l;
+    __nv_bfloat162 lo = __floats2bfloat162_rn(acc.x * inv, acc.y * inv), hi = __floats2bfloat162_rn(acc.z * inv, acc.w * inv);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(out + grow * KA_DH + lane * 4) = pk;
+  }
+}
+
 }  // namespace
 
 // 0 = mma.sync kernels, 1 = tcgen05/TMEM kernels (attn_tcgen05.cu), 2 = auto: tcgen05 for the ViT and for decoder steps
@@ -356,7 +417,10 @@ int launch_kv_attention(const __nv_bfloat16* q, const __nv_bfloat16* kv_layer, c
     launch_k(kv_attention_kernel, grid, dim3(KA_THREADS), SMEM, s, q, kv_layer, stream_desc, block_tables, o_part, ml_part, Hq, Hkv,
              n_splits, part_rows, scale_log2e);
   }
-  launch_k(kv_attention_combine_kernel, dim3((unsigned)((part_rows + 7) / 8)), dim3(256), 0, s, o_part, ml_part, out, n_splits, part_rows);
+  if (part_rows <= 512 && n_splits > 4)   // few rows, many splits: one block per row, all partial rows in flight
+    launch_k(kv_attention_combine_wide_kernel, dim3((unsigned)part_rows), dim3(256), 0, s, o_part, ml_part, out, n_splits, part_rows);
+  else
+    launch_k(kv_attention_combine_kernel, dim3((unsigned)((part_rows + 7) / 8)), dim3(256), 0, s, o_part, ml_part, out, n_splits, part_rows);
   return 0;
 }
 

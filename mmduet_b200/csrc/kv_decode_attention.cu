@@ -15,6 +15,7 @@
 
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 namespace mmd {
 
@@ -25,8 +26,7 @@ constexpr int KD_BN = 64;        // keys per tile == tokens per KV page
 constexpr int KD_DH = 128;
 constexpr int KD_LDS = 136;      // padded smem row (bf16 elements): conflict-free ldmatrix
 constexpr int KD_WARPS = 4, KD_THREADS = 32 * KD_WARPS;
-constexpr int KD_STAGES = 4;
-constexpr int KD_SMEM = (KD_ROWS + 2 * KD_STAGES * KD_BN) * KD_LDS * 2;
+constexpr int kd_smem(int stages) { return (KD_ROWS + 2 * stages * KD_BN) * KD_LDS * 2; }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -51,7 +51,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(KD_THREADS, 1)
+template <int KD_STAGES, int MIN_CTAS>
+__global__ void __launch_bounds__(KD_THREADS, MIN_CTAS)
 kv_decode_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv_layer,
                            const int* __restrict__ stream_desc, const int* __restrict__ block_tables, float* __restrict__ o_part,
                            float* __restrict__ ml_part, int Hq, int Hkv, int n_splits, long long part_stride_rows, float scale_log2e) {
@@ -252,10 +253,20 @@ kv_decode_attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloa
 
 bool kv_decode_applicable(int max_rows) { return max_rows <= KD_ROWS; }
 
-// one CTA per SM: as many splits as fill the GPU, at least one page each, at most what the combine kernel merges (64)
+// shape of the launch: 0 = one CTA per SM with a 5-page ring, 1 = two CTAs per SM with 3-page rings (MMD_KD_VARIANT, measured)
+static int kd_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MMD_KD_VARIANT");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
+// as many splits as fill the GPU, at least one page each, at most what the combine kernel merges (64)
 int kv_decode_pick_splits(int Hkv, int n_streams, int max_kv_len, int num_sms) {
   const int tiles = (max_kv_len + KD_BN - 1) / KD_BN;
-  int s = num_sms / (Hkv * n_streams > 0 ? Hkv * n_streams : 1);
+  int s = (kd_variant() == 1 ? 2 : 1) * num_sms / (Hkv * n_streams > 0 ? Hkv * n_streams : 1);
   if (s > tiles) s = tiles;
   if (s > 64) s = 64;
   return s < 1 ? 1 : s;
@@ -265,12 +276,17 @@ int launch_kv_decode_attention(const __nv_bfloat16* q, const __nv_bfloat16* kv_l
                                int n_streams, int total_q, float* o_part, float* ml_part, int Hq, int Hkv, int n_splits, cudaStream_t s) {
   static PerDeviceFlag attr;
   if (!attr.cur()) {
-    if (cudaFuncSetAttribute(kv_decode_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KD_SMEM) != cudaSuccess) return -4;
+    if (cudaFuncSetAttribute(kv_decode_attention_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kd_smem(5)) != cudaSuccess) return -4;
+    if (cudaFuncSetAttribute(kv_decode_attention_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kd_smem(3)) != cudaSuccess) return -4;
     attr.cur() = true;
   }
   const float scale_log2e = (1.0f / sqrtf((float)KD_DH)) * 1.4426950408889634f;
-  launch_k(kv_decode_attention_kernel, dim3(Hkv, n_splits, n_streams), dim3(KD_THREADS), KD_SMEM, s, q, kv_layer, stream_desc, block_tables,
-           o_part, ml_part, Hq, Hkv, n_splits, (long long)total_q * Hq, scale_log2e);
+  if (kd_variant() == 1)
+    launch_k(kv_decode_attention_kernel<3, 2>, dim3(Hkv, n_splits, n_streams), dim3(KD_THREADS), kd_smem(3), s, q, kv_layer, stream_desc,
+             block_tables, o_part, ml_part, Hq, Hkv, n_splits, (long long)total_q * Hq, scale_log2e);
+  else
+    launch_k(kv_decode_attention_kernel<5, 1>, dim3(Hkv, n_splits, n_streams), dim3(KD_THREADS), kd_smem(5), s, q, kv_layer, stream_desc,
+             block_tables, o_part, ml_part, Hq, Hkv, n_splits, (long long)total_q * Hq, scale_log2e);
   return 0;
 }
 
