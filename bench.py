@@ -543,21 +543,24 @@ def configs2_frame_parallel(vis, dec, cfg, dev, world, rank, chunk):
     Timed on the device from before the first encode launch to the last score, max over ranks."""
     import torch
     import torch.distributed as dist
-    from mmduet_b200.parallel import FrameParallelEncoder, PeerStoreEncoder, frame_range
+    from mmduet_b200.parallel import FrameParallelEncoder, PeerStoreEncoder, encoder_frame_range
     from mmduet_b200.random_init import synthetic_frames
     n, tpf, H = CONFIGS2_FRAMES, vis.tokens_per_frame, cfg.hidden
     k = max(chunk, 1)
     frames = synthetic_frames(n, seed=7, device=dev)              # the same video on every rank; each encodes its slice
-    lo, hi = frame_range(n, world, rank)
+    # the decoder-owning rank does not encode when there are other ranks: its sequential decoder stream is the serial term,
+    # so it starts on the first batch as soon as that lands while ranks 1..N-1 keep encoding
+    encoders = list(range(1, world)) if world > 1 else [0]
+    lo, hi = encoder_frame_range(n, encoders, rank)
     exchange = "none (1 GPU)"
     enc = None
     if world > 1:
         try:
             enc = PeerStoreEncoder(lambda fr, dst: vis.visual_embed(fr, normalize=True, out=dst), tpf, H, max_frames=n, device=dev,
-                                   owner=0, batch=40)
+                                   owner=0, batch=40, encoders=encoders)
             exchange = "peer stores into the owner's HBM (symmetric memory over NVLink), per-batch signals, no collective"
         except Exception as e:  # noqa: BLE001
-            enc = FrameParallelEncoder(lambda fr: vis.visual_embed(fr, normalize=True), tpf, H, device=dev, owner=0, batch=40)
+            enc = FrameParallelEncoder(lambda fr: vis.visual_embed(fr, normalize=True), tpf, H, device=dev, owner=0, batch=40, encoders=encoders)
             exchange = f"NCCL isend/irecv per 40-frame batch (symmetric memory unavailable: {type(e).__name__})"
     dec._ensure_ws(49 * k, 1)
     if dec.max_context < n * tpf:
@@ -638,7 +641,8 @@ def configs2_frame_parallel(vis, dec, cfg, dev, world, rank, chunk):
         res = {"workload": "BASELINE.json configs[2]: one 600-frame video (5 min @ 2 fps), encoder sharded over the ranks, frame tokens "
                            "exchanged to rank 0, which decodes the whole stream (final context 29.4k tokens) and applies the running-sum rule "
                            "(threshold 2, informative head); responses not generated (remove_assistant_turns: context-neutral)",
-               "frames": n, "n_encoder_ranks": world, "exchange": exchange, "decoder_frames_per_pass": k,
+               "frames": n, "n_ranks": world, "n_encoder_ranks": len(encoders), "decoder_rank_also_encodes": world == 1, "exchange": exchange,
+               "decoder_frames_per_pass": k,
                "ms": ms, "frames_per_s": n / (ms / 1e3), "encode_exchange_only_ms": enc_ms, "owner_decode_only_ms": dec_ms,
                "final_context_tokens": int(L), "responses": len(resp), "first_response_frames": resp[:8],
                "tokens_bit_identical_to_single_rank_encode": ident,

@@ -22,6 +22,15 @@ def frame_range(n_frames, world, rank):
     return start, start + base + (1 if rank < extra else 0)
 
 
+def encoder_frame_range(n_frames, encoders, rank):
+    """Frame range of `rank` when only the ranks in `encoders` (ascending) encode; (0, 0) for a rank that does not.  Leaving the
+    decoder-owning rank out lets it start decoding the first batch while the others are still encoding: the owner's decoder
+    stream is the serial term of the pipeline, so nothing else should sit on its GPU."""
+    if rank not in encoders:
+        return 0, 0
+    return frame_range(n_frames, len(encoders), encoders.index(rank))
+
+
 def videos_for_rank(n_videos, world, rank):
     return list(range(rank, n_videos, world))
 
@@ -30,24 +39,27 @@ class FrameParallelEncoder:
     """encode_fn(frames[b0:b1]) -> tokens [(b1-b0)*tokens_per_frame, hidden].  Every rank encodes its frame range in
     batches; non-owner ranks isend each finished batch, the owner irecvs straight into the frame-ordered output."""
 
-    def __init__(self, encode_fn, tokens_per_frame, hidden, dtype=torch.bfloat16, device="cuda", owner=0, batch=32, group=None):
+    def __init__(self, encode_fn, tokens_per_frame, hidden, dtype=torch.bfloat16, device="cuda", owner=0, batch=32, group=None,
+                 encoders=None):
         self.encode_fn, self.tpf, self.hidden, self.dtype, self.device = encode_fn, tokens_per_frame, hidden, dtype, device
         self.owner, self.batch, self.group = owner, batch, group
+        self.encoders = sorted(encoders) if encoders is not None else None      # ranks that encode (default: all)
 
     def encode(self, n_frames, local_frames):
         """local_frames: this rank's slice (frame_range) of the video.  Returns (tokens, ready) on the owner — `ready[i]`
         is a callable that blocks until frame i's tokens have arrived — and (None, None) elsewhere."""
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        lo, hi = frame_range(n_frames, world, rank)
+        encoders = self.encoders if self.encoders is not None else list(range(world))
+        lo, hi = encoder_frame_range(n_frames, encoders, rank)
         assert len(local_frames) == hi - lo, (len(local_frames), lo, hi)
         is_owner = rank == self.owner
         out, recvs = None, {}
         if is_owner:
             out = torch.empty(n_frames * self.tpf, self.hidden, dtype=self.dtype, device=self.device)
-            for src in range(world):
+            for src in encoders:
                 if src == rank:
                     continue
-                s_lo, s_hi = frame_range(n_frames, world, src)
+                s_lo, s_hi = encoder_frame_range(n_frames, encoders, src)
                 for b0 in range(s_lo, s_hi, self.batch):
                     b1 = min(b0 + self.batch, s_hi)
                     recvs[(b0, b1)] = dist.irecv(out[b0 * self.tpf:b1 * self.tpf], src=src, group=self.group)
@@ -92,13 +104,14 @@ class PeerStoreEncoder:
     embed_into(frames[b0:b1], dst[(b1-b0)*tokens_per_frame, hidden]) must write the tokens of those frames into dst."""
 
     def __init__(self, embed_into, tokens_per_frame, hidden, max_frames, device, owner=0, batch=32, group=None, symm=None,
-                 dtype=torch.bfloat16):
+                 dtype=torch.bfloat16, encoders=None):
         if symm is None:                   # injectable: the CPU tests drive the same control flow through a gloo-backed stand-in
             import torch.distributed._symmetric_memory as symm
         self.embed_into, self.tpf, self.hidden, self.device = embed_into, tokens_per_frame, hidden, device
         self.owner, self.batch, self.max_frames = owner, batch, max_frames
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.encoders = sorted(encoders) if encoders is not None else list(range(self.world))   # ranks that encode
         self.buf = symm.empty(max_frames * tokens_per_frame, hidden, dtype=dtype, device=device)
         self.hdl = symm.rendezvous(self.buf, self.group)
         # the owner's buffer as seen from this rank (a peer mapping unless this rank is the owner)
@@ -116,7 +129,7 @@ class PeerStoreEncoder:
         """Returns (tokens, ready) on the owner (tokens is a view of the symmetric buffer, valid until the next encode;
         ready[i]() makes the current stream wait until frame i has landed) and (None, None) elsewhere."""
         assert n_frames <= self.max_frames
-        lo, hi = frame_range(n_frames, self.world, self.rank)
+        lo, hi = encoder_frame_range(n_frames, self.encoders, self.rank)
         assert len(local_frames) == hi - lo, (len(local_frames), lo, hi)
         # Signals of the previous video that the owner never consumed (it stopped early, or never called its ready[i]) would
         # satisfy THIS video's waits before the data has landed, and a producer's put_signal blocks on a channel that is
@@ -138,9 +151,9 @@ class PeerStoreEncoder:
         if self.rank != self.owner:
             return None, None
         pending = {}                                           # src rank -> list of its batches, in sending order
-        for src in range(self.world):
+        for src in self.encoders:
             if src != self.owner:
-                s_lo, s_hi = frame_range(n_frames, self.world, src)
+                s_lo, s_hi = encoder_frame_range(n_frames, self.encoders, src)
                 pending[src] = [(b0, min(b0 + self.batch, s_hi), self._channel(n)) for n, b0 in enumerate(range(s_lo, s_hi, self.batch))]
         self._pending = pending
 

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from mmduet_b200.parallel import FrameParallelEncoder, PeerStoreEncoder, frame_range, gather_results, videos_for_rank
+from mmduet_b200.parallel import encoder_frame_range, FrameParallelEncoder, PeerStoreEncoder, frame_range, gather_results, videos_for_rank
 
 
 def test_partitions_cover_everything_once():
@@ -122,25 +122,26 @@ class _GlooSymm:
         return _GlooSymm.Handle(tensor, group)
 
 
-def _peer_worker(rank, world, port, n_frames, owner, q):
+def _peer_worker(rank, world, port, n_frames, owner, q, owner_encodes=True):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         tpf, hidden = 3, 4
-        lo, hi = frame_range(n_frames, world, rank)
+        encoders = list(range(world)) if owner_encodes else [r for r in range(world) if r != owner]
+        lo, hi = encoder_frame_range(n_frames, encoders, rank)
         frames = torch.arange(lo, hi, dtype=torch.float32)
 
         def embed_into(fr, dst):
             dst.copy_((fr[:, None] * 10 + torch.arange(tpf)[None, :]).reshape(-1, 1).expand(-1, hidden))
 
         enc = PeerStoreEncoder(embed_into, tpf, hidden, max_frames=n_frames, device="cpu", owner=owner, batch=2, symm=_GlooSymm,
-                               dtype=torch.float32)
+                               dtype=torch.float32, encoders=encoders)
         out, ready = enc.encode(n_frames, frames)
         if rank == owner:
             PeerStoreEncoder.wait_all(ready)
             want = (torch.arange(n_frames)[:, None] * 10 + torch.arange(tpf)[None, :]).reshape(-1, 1).expand(-1, hidden).float()
             src = 1 - owner
-            n_batches = (frame_range(n_frames, world, src)[1] - frame_range(n_frames, world, src)[0] + 1) // 2
+            n_batches = (encoder_frame_range(n_frames, encoders, src)[1] - encoder_frame_range(n_frames, encoders, src)[0] + 1) // 2
             ok = torch.equal(out, want) and enc.hdl.log == [(src, 1 + b) for b in range(n_batches)]
         else:
             ok = out is None and ready is None
@@ -156,12 +157,13 @@ def _peer_worker(rank, world, port, n_frames, owner, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_frames,owner", [(7, 0), (12, 1)])
-def test_peer_store_encoder_world2_control_flow(n_frames, owner):
+@pytest.mark.parametrize("n_frames,owner,owner_encodes", [(7, 0, True), (12, 1, True), (9, 0, False)])
+def test_peer_store_encoder_world2_control_flow(n_frames, owner, owner_encodes):
+    """owner_encodes=False: the decoder-owning rank only receives (what bench.py's configs[2] measurement does for N > 1)."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, n_frames, owner, q)) for r in range(2)]
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, n_frames, owner, q, owner_encodes)) for r in range(2)]
     for p_ in procs:
         p_.start()
     res = dict(q.get(timeout=120) for _ in range(2))
