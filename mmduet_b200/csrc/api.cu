@@ -475,7 +475,7 @@ int mmd_projector_pool(mmd_ctx* c, const mmd_projector_weights* w, const float* 
 // decoder step
 // ---------------------------------------------------------------------------------------------------------------
 struct DecBufs {
-  float *resid, *planes, *planes_p, *o_part, *ml_part;
+  float *resid, *planes, *graw, *o_part, *ml_part;
   __nv_bfloat16 *x, *q, *attn, *h, *lm_x, *xp2, *hp2;
 };
 constexpr int kMaxPrecRows = 128;   // rows carried as bf16 hi+lo pairs (one <= 128-token tile of the swap-AB GEMM)
@@ -486,15 +486,17 @@ static int64_t dec_carve(const mmd_dec_weights* w, int max_tokens, int max_lm_ro
   const int64_t M = max_tokens;
   const int H = w->hidden, QD = w->q_heads * w->head_dim, NQKV = (w->q_heads + 2 * w->kv_heads) * w->head_dim;
   const int nmax = NQKV > H ? NQKV : H;
+  // passes above 128 tokens append 2 rows (hi, lo) per precise row to the activation matrices of q/k/v, gate/up and down
+  const int64_t Mx = M > kMaxPrecRows ? M + 2 * kMaxPrecRows : M;
   o->resid = b.take<float>(M * H);
-  o->planes = b.take<float>((int64_t)kMaxSplits * M * nmax);
-  o->planes_p = b.take<float>((int64_t)kMaxSplits * kMaxPrecRows * H);
+  o->planes = b.take<float>((int64_t)kMaxSplits * Mx * nmax);
+  o->graw = b.take<float>(M > kMaxPrecRows ? (int64_t)2 * kMaxPrecRows * 2 * w->mlp : 1);   // raw (gate, up) of the appended rows
   o->xp2 = b.take<__nv_bfloat16>((int64_t)kMaxPrecRows * 2 * H);
   o->hp2 = b.take<__nv_bfloat16>((int64_t)kMaxPrecRows * 2 * w->mlp);
-  o->x = b.take<__nv_bfloat16>(M * H);
+  o->x = b.take<__nv_bfloat16>(Mx * H);
   o->q = b.take<__nv_bfloat16>(M * QD);
   o->attn = b.take<__nv_bfloat16>(M * QD);
-  o->h = b.take<__nv_bfloat16>(M * w->mlp);
+  o->h = b.take<__nv_bfloat16>(Mx * w->mlp);
   const int64_t part_rows = kMaxAttnSplits * M > 2 * kMaxDecodeSplits ? kMaxAttnSplits * M : 2 * kMaxDecodeSplits;
   o->o_part = b.take<float>(part_rows * QD);
   o->ml_part = b.take<float>(part_rows * w->q_heads * 2);
@@ -535,26 +537,28 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
   // "Precise rows": the scores are read at a handful of rows (one per frame) and their error is dominated by the bf16 rounding
   // of the MLP operands ON THOSE ROWS (tools/noise_floor_decoder.py: x_mlp 0.012, h 0.007 of a 0.018 total; other rows' noise
   // averages out through attention).  Those rows therefore carry their GEMM operands as bf16 hi+lo pairs:
-  //   all_prec  (M <= 128, single-frame / query / generation steps): every row, inside the main swap-AB kernels (the step is
-  //             HBM-bound, the second MMA per weight tile is free); q/k/v, gate/up and down operands are hi+lo.
-  //   side_prec (M > 128): the <= 128 listed rows get a second, skinny gate/up + down pass per layer whose result replaces the
-  //             main pass's residual update for those rows (weights re-streamed: +1.75 ms per pass at the 7B size).
+  //   all_prec (M <= 128, single-frame / query / generation steps): every row, inside the main swap-AB kernels (the step is
+  //            HBM-bound, the second MMA per weight tile is free); q/k/v, gate/up and down operands are [hi | lo], 2K wide.
+  //   app_prec (M > 128): the <= 128 listed rows are APPENDED to the activation matrices of q/k/v, gate/up and down as two
+  //            extra rows each (row M + j = hi, row M + P + j = lo), so they ride through the main GEMMs (weights streamed once,
+  //            usually inside the last, partly filled token tile); a linear layer's precise output is the sum of the two rows'
+  //            outputs, taken by the consumer (RoPE / norm kernels); gate/up writes the appended rows' raw pre-activations and a
+  //            small kernel applies SwiGLU to gate_hi + gate_lo, up_hi + up_lo.
   const bool prec_ok = c->precise && H % 64 == 0 && I % 64 == 0;
   const bool all_prec = prec_ok && M <= kMaxPrecRows;
   const int P = st->n_prec_rows;
-  const bool side_prec = prec_ok && !all_prec && P > 0 && P <= kMaxPrecRows && st->prec_rows != nullptr && st->prec_of_row != nullptr;
-  __nv_bfloat16* xmain = all_prec ? nullptr : buf.x;         // plain bf16 normalised rows (unused when every row is hi+lo)
-  __nv_bfloat16* x_hilo = (all_prec || side_prec) ? buf.xp2 : nullptr;
-  const int* prec_of_row = side_prec ? st->prec_of_row : nullptr;
+  const bool app_prec = prec_ok && !all_prec && P > 0 && P <= kMaxPrecRows && st->prec_rows != nullptr && st->prec_of_row != nullptr;
+  const int Mt = app_prec ? M + 2 * P : M;                   // activation rows of the GEMMs that carry the appended rows
+  __nv_bfloat16* xmain = all_prec ? nullptr : buf.x;         // plain bf16 normalised rows (unused when every row is [hi | lo])
+  const int* prec_of_row = app_prec ? st->prec_of_row : nullptr;
   // inputs_embeds = cat(embed_tokens(prefix ids), frame tokens) -> fp32 residual stream   (test/inference.py:235-238)
   PRUNK(mmd::launch_gather_rows_bf16_to_f32(static_cast<const __nv_bfloat16*>(w->embed), static_cast<const __nv_bfloat16*>(st->frame_tokens),
                                            st->src_row, buf.resid, M, H, s), "embed/concat");
-  PRUNK(mmd::launch_resid_add_rmsnorm_precise(buf.resid, nullptr, 0, 0, w->layers[0].ln1_w, xmain, nullptr, M, H, w->rms_eps, nullptr,
-                                             nullptr, 0, 0, all_prec ? buf.xp2 : nullptr, s), "input_layernorm");
-  const int s_qkv = choose_splits(c->num_sms, NQKV, H, M);
+  PRUNK(mmd::launch_resid_add_rmsnorm_precise(buf.resid, nullptr, 0, 0, w->layers[0].ln1_w, xmain, nullptr, M, H, w->rms_eps, prec_of_row,
+                                             nullptr, 0, 0, all_prec ? buf.xp2 : nullptr, s, 0, app_prec ? 1 : 0, P), "input_layernorm");
+  const int s_qkv = choose_splits(c->num_sms, NQKV, H, Mt);
   const int s_o = choose_splits(c->num_sms, H, QD, M);
-  const int s_down = choose_splits(c->num_sms, H, I, M);
-  const int s_down_p = side_prec ? choose_splits(c->num_sms, H, I, P) : 1;
+  const int s_down = choose_splits(c->num_sms, H, I, Mt);
   int attn_splits = mmd::kv_attention_pick_splits(st->max_n_q * (Hq / Hkv), Hkv, st->n_streams, st->max_kv_len, c->num_sms);
   {   // the partial buffers hold kMaxAttnSplits x M rows, or kMaxDecodeSplits splits of <= 16 rows (dec_carve)
     const int64_t cap_rows = kMaxAttnSplits * (int64_t)M > 2 * kMaxDecodeSplits ? kMaxAttnSplits * (int64_t)M : 2 * kMaxDecodeSplits;
@@ -564,16 +568,16 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
   // Swap-AB + split-K (weights on the 128 UMMA rows, all SMs busy) wins up to ~1200 tokens per pass on this model
   // (measured: 8/10/24-frame passes, profiles/r01_decoder_paths.md); the normal-orientation CTA-pair path (UMMA M = 256,
   // TMA-store epilogue, interleaved gate/up + pairwise SwiGLU) only pays off for much larger multi-stream batches.
-  const bool big = M >= 2048;
+  const bool big = M >= 2048;      // (kernel choices follow the pass size M, not M + appended rows: measured thresholds)
   // q/k/v, o and down (plain fp32 outputs) already win in the normal-orientation CTA-pair kernel from 1024 tokens
   // (measured at 1960 tokens: -5 %, -5 %, -10 %: no split-K planes, whole waves of 256x256 tiles); gate/up keeps the
   // swap-AB SwiGLU epilogue up to 2048.
   const bool pair_qkv = M >= 1024, pair_o = M >= 1024, pair_down = M >= 1024;
-  auto gemm_big_f32 = [&](const void* act, const void* wt, int N, int K, int splits, int* eff) -> int {
+  auto gemm_big_f32 = [&](const void* act, int rows, const void* wt, int N, int K, int splits, int* eff) -> int {
     mmd::GemmArgs a;
-    a.X = static_cast<const __nv_bfloat16*>(act); a.x_rows = M; a.ldx = K;
+    a.X = static_cast<const __nv_bfloat16*>(act); a.x_rows = rows; a.ldx = K;
     a.Y = static_cast<const __nv_bfloat16*>(wt); a.y_rows = N; a.ldy = K; a.K = K;
-    a.epi = mmd::EPI_F32; a.out = buf.planes; a.ldo = N; a.k_splits = splits; a.split_stride = (int64_t)M * N; a.force_2cta = 1;
+    a.epi = mmd::EPI_F32; a.out = buf.planes; a.ldo = N; a.k_splits = splits; a.split_stride = (int64_t)rows * N; a.force_2cta = 1;
     *eff = mmd::gemm_effective_splits(K, splits);
     return mmd::gemm_launch(c->gemm, a, s);
   };
@@ -584,22 +588,23 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
     a.epi = mmd::EPI_T_SWIGLU; a.out = out2; a.ldo = 2 * (int64_t)I; a.y_hilo = 1; a.out_hilo = 1;
     return mmd::gemm_launch(c->gemm, a, s);
   };
-  int eff = 1, eff_p = 0;   // split-K planes of the pending residual update (main / precise side pass)
+  int eff = 1;   // split-K planes of the pending residual update
   for (int l = 0; l < w->n_layers; ++l) {
     const mmd_dec_layer& L = w->layers[l];
     if (all_prec) PRUN(gemm_T_partials(c, buf.xp2, M, L.qkv_w, NQKV, H, s_qkv, buf.planes, s, &eff, true), "qkv_proj");
-    else if (pair_qkv) PRUN(gemm_big_f32(buf.x, L.qkv_w, NQKV, H, 1, &eff), "qkv_proj");
-    else PRUN(gemm_T_partials(c, buf.x, M, L.qkv_w, NQKV, H, s_qkv, buf.planes, s, &eff), "qkv_proj");
+    else if (pair_qkv) PRUN(gemm_big_f32(buf.x, Mt, L.qkv_w, NQKV, H, 1, &eff), "qkv_proj");
+    else PRUN(gemm_T_partials(c, buf.x, Mt, L.qkv_w, NQKV, H, s_qkv, buf.planes, s, &eff), "qkv_proj");
     __nv_bfloat16* kv_layer = static_cast<__nv_bfloat16*>(pool->pool) + (int64_t)l * pool->layer_stride;
-    PRUNK(mmd::launch_qkv_finish(buf.planes, eff, (int64_t)M * NQKV, L.qkv_b, w->rope_cos, w->rope_sin, st->tok_pos, st->tok_slot,
-                                buf.q, kv_layer, M, Hq, Hkv, dh, MMD_PAGE_TOKENS, s), "qkv_finish");
+    PRUNK(mmd::launch_qkv_finish(buf.planes, eff, (int64_t)Mt * NQKV, L.qkv_b, w->rope_cos, w->rope_sin, st->tok_pos, st->tok_slot,
+                                buf.q, kv_layer, M, Hq, Hkv, dh, MMD_PAGE_TOKENS, s, prec_of_row, P), "qkv_finish");
     PRUNK2(mmd::launch_kv_attention(buf.q, kv_layer, st->stream_desc, st->block_tables, st->n_streams, st->max_n_q, M, st->max_kv_len, buf.o_part,
                                   buf.ml_part, buf.attn, Hq, Hkv, dh, MMD_PAGE_TOKENS, attn_splits, s), "kv_attention");
-    if (pair_o) PRUN(gemm_big_f32(buf.attn, L.o_w, H, QD, 1, &eff), "o_proj");
+    if (pair_o) PRUN(gemm_big_f32(buf.attn, M, L.o_w, H, QD, 1, &eff), "o_proj");
     else PRUN(gemm_T_partials(c, buf.attn, M, L.o_w, H, QD, s_o, buf.planes, s, &eff), "o_proj");
-    // resid += o_proj; x = RMSNorm(resid) (bf16 for the main pass, [hi | lo] for the precise rows)
+    // resid += o_proj; x = RMSNorm(resid): bf16 rows (+ the appended hi / lo rows of the precise rows), or [hi | lo] for every row
     PRUNK(mmd::launch_resid_add_rmsnorm_precise(buf.resid, buf.planes, eff, (int64_t)M * H, L.ln2_w, xmain, nullptr, M, H, w->rms_eps,
-                                               prec_of_row, nullptr, 0, 0, x_hilo, s), "post_attention_layernorm");
+                                               prec_of_row, nullptr, 0, 0, all_prec ? buf.xp2 : nullptr, s, 0, app_prec ? 1 : 0, P),
+          "post_attention_layernorm");
     const __nv_bfloat16* gu = static_cast<const __nv_bfloat16*>(L.gate_up_w);
     if (all_prec) {
       PRUN(gate_up_hilo(gu, buf.xp2, M, buf.hp2), "gate_up_swiglu");
@@ -607,36 +612,39 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
     } else {
       mmd::GemmArgs a;
       if (big) {   // interleaved (gate, up) columns, SwiGLU on adjacent accumulator columns
-        a.X = buf.x; a.x_rows = M; a.ldx = H; a.Y = gu; a.y_rows = 2 * I; a.ldy = H; a.K = H;
+        a.X = buf.x; a.x_rows = Mt; a.ldx = H; a.Y = gu; a.y_rows = 2 * I; a.ldy = H; a.K = H;
         a.epi = mmd::EPI_SWIGLU_PAIR; a.out = buf.h; a.ldo = I; a.force_2cta = 1;
       } else if (M > 1024 && I % 2 == 0) {   // (at 490 tokens the two-accumulator form is still 7 % faster: 4 re-reads only)
         // swap-AB on the interleaved matrix as ONE operand: a single accumulator per 128 weight rows (64 gate/up pairs on
         // adjacent TMEM lanes) leaves room for 256-token tiles, i.e. UMMA N = 256 instead of 2 x 128 (ncu at 1960 tokens:
         // tensor pipe 87.8 % active vs 80.6 % with two accumulators; L2->SM traffic is the same 6.5 GB either way)
-        a.X = gu; a.x_rows = 2 * I; a.ldx = H; a.Y = buf.x; a.y_rows = M; a.ldy = H; a.K = H;
+        a.X = gu; a.x_rows = 2 * I; a.ldx = H; a.Y = buf.x; a.y_rows = Mt; a.ldy = H; a.K = H;
         a.epi = mmd::EPI_T_SWIGLU_IL; a.out = buf.h; a.ldo = I;
       } else {     // swap-AB: gate rows and up rows of the interleaved matrix as two strided operands
-        a.X = gu; a.X2 = gu + H; a.x_rows = I; a.ldx = 2 * (int64_t)H; a.Y = buf.x; a.y_rows = M; a.ldy = H; a.K = H;
+        a.X = gu; a.X2 = gu + H; a.x_rows = I; a.ldx = 2 * (int64_t)H; a.Y = buf.x; a.y_rows = Mt; a.ldy = H; a.K = H;
         a.epi = mmd::EPI_T_SWIGLU; a.out = buf.h; a.ldo = I;
       }
+      if (app_prec) { a.raw_out = buf.graw; a.raw_from = M; a.ld_raw = 2 * (int64_t)I; }
       PRUN(mmd::gemm_launch(c->gemm, a, s), "gate_up_swiglu");
-      if (side_prec) PRUN(gate_up_hilo(gu, buf.xp2, P, buf.hp2), "gate_up_precise");
-      if (pair_down) PRUN(gemm_big_f32(buf.h, L.down_w, H, I, 3, &eff), "down_proj");
-      else PRUN(gemm_T_partials(c, buf.h, M, L.down_w, H, I, s_down, buf.planes, s, &eff), "down_proj");
-      if (side_prec) PRUN(gemm_T_partials(c, buf.hp2, P, L.down_w, H, I, s_down_p, buf.planes_p, s, &eff_p, true), "down_precise");
+      if (app_prec)   // h rows M .. M + 2P: SwiGLU of (gate_hi + gate_lo, up_hi + up_lo) as a hi row and a lo row
+        PRUNK(mmd::launch_swiglu_from_raw(buf.graw, 2 * (int64_t)I, buf.h + (int64_t)M * I, I, P, I, s), "gate_up_precise");
+      if (pair_down) PRUN(gemm_big_f32(buf.h, Mt, L.down_w, H, I, 3, &eff), "down_proj");
+      else PRUN(gemm_T_partials(c, buf.h, Mt, L.down_w, H, I, s_down, buf.planes, s, &eff), "down_proj");
     }
-    if (l + 1 < w->n_layers)   // resid += down_proj (precise rows: from the side pass); x = RMSNorm(resid) for the next layer
-      PRUNK(mmd::launch_resid_add_rmsnorm_precise(buf.resid, buf.planes, eff, (int64_t)M * H, w->layers[l + 1].ln1_w, xmain, nullptr, M, H,
-                                                 w->rms_eps, prec_of_row, side_prec ? buf.planes_p : nullptr, eff_p, (int64_t)P * H,
-                                                 all_prec ? buf.xp2 : nullptr, s), "next_layernorm");
+    if (l + 1 < w->n_layers)   // resid += down_proj (precise rows: their hi + lo copies' outputs); x = RMSNorm(resid) for the next layer
+      PRUNK(mmd::launch_resid_add_rmsnorm_precise(buf.resid, buf.planes, eff, (int64_t)Mt * H, w->layers[l + 1].ln1_w, xmain, nullptr, M, H,
+                                                 w->rms_eps, prec_of_row, app_prec ? buf.planes + (int64_t)M * H : nullptr, eff,
+                                                 (int64_t)Mt * H, all_prec ? buf.xp2 : nullptr, s, (int64_t)P * H, app_prec ? 1 : 0, P),
+            "next_layernorm");
   }
   // final norm on the rows that are read only, with the informative/relevance heads as its epilogue (+ bf16 rows for lm_head)
   if (st->n_score_rows > 0 && (st->score_rows == nullptr || st->head_logits_out == nullptr || st->scores_out == nullptr || w->heads_w == nullptr))
     return fail(MMD_ERR_ARG, "mmd_decoder_step: score rows requested without buffers");
   if (st->n_score_rows > 0 || st->n_lm_rows > 0)
-    PRUNK(mmd::launch_final_norm_heads(buf.resid, buf.planes, eff, (int64_t)M * H, w->final_norm_w, st->score_rows, st->n_score_rows,
+    PRUNK(mmd::launch_final_norm_heads(buf.resid, buf.planes, eff, (int64_t)Mt * H, w->final_norm_w, st->score_rows, st->n_score_rows,
                                       st->lm_rows, st->n_lm_rows, w->heads_w, st->head_logits_out, st->scores_out, buf.lm_x, H, w->rms_eps,
-                                      prec_of_row, side_prec ? buf.planes_p : nullptr, eff_p, (int64_t)P * H, s), "final_norm_heads");
+                                      prec_of_row, app_prec ? buf.planes + (int64_t)M * H : nullptr, eff, (int64_t)Mt * H, s, (int64_t)P * H),
+          "final_norm_heads");
   if (st->n_lm_rows > 0) {
     int e2 = 1;
     PRUN(gemm_T_partials(c, buf.lm_x, st->n_lm_rows, w->lm_head, w->vocab, H, 1, st->lm_logits_out, s, &e2), "lm_head");

@@ -336,6 +336,13 @@ struct PreciseRows {
   int n_prec_planes = 0;
   long long prec_plane_stride = 0;
   __nv_bfloat16* out_hilo = nullptr;
+  // "appended rows" form (passes above 128 tokens): the precise rows travel through the MAIN GEMMs as 2P extra activation rows,
+  // [n_rows + j] = hi and [n_rows + P + j] = lo of precise row j, so the weights are streamed once.  On the way in, the
+  // residual update of precise row j is prec_partial[j] + prec_partial[j + pair_offset / H] (the hi and lo rows' outputs);
+  // on the way out, the normalised row is also written to out_bf16 rows n_rows + j (hi) and n_rows + n_prec + j (lo).
+  long long pair_offset = 0;     // elements between the hi and the lo output row inside a plane (0: single row)
+  int append_base = -1;          // n_rows of the main pass (>= 0 switches the appended output rows on)
+  int n_prec = 0;
 };
 
 template <int NT>
@@ -353,7 +360,8 @@ __global__ void resid_add_rmsnorm_kernel(float* __restrict__ resid, const float*
   const float* src = partial + row * H;
   int np = n_planes;
   long long ps = plane_stride;
-  if (j >= 0 && pr.prec_partial != nullptr) { src = pr.prec_partial + j * H; np = pr.n_prec_planes; ps = pr.prec_plane_stride; }
+  long long pair = 0;
+  if (j >= 0 && pr.prec_partial != nullptr) { src = pr.prec_partial + j * H; np = pr.n_prec_planes; ps = pr.prec_plane_stride; pair = pr.pair_offset; }
   float ss = 0.f;
   for (int c = threadIdx.x; c < H4; c += NT) {
     float4 v = reinterpret_cast<float4*>(resid + row * H)[c];
@@ -364,6 +372,13 @@ __global__ void resid_add_rmsnorm_kernel(float* __restrict__ resid, const float*
       a[p] = p < np ? __ldg(reinterpret_cast<const float4*>(src + p * ps) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int p = 0; p < kMaxPlanes; ++p) { v.x += a[p].x; v.y += a[p].y; v.z += a[p].z; v.w += a[p].w; }
+    if (pair != 0) {             // the lo copy's output row of a precise row (appended-rows form)
+#pragma unroll
+      for (int p = 0; p < kMaxPlanes; ++p)
+        a[p] = p < np ? __ldg(reinterpret_cast<const float4*>(src + pair + p * ps) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < kMaxPlanes; ++p) { v.x += a[p].x; v.y += a[p].y; v.z += a[p].z; v.w += a[p].w; }
+    }
     for (int p = kMaxPlanes; p < np; ++p) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(src + p * ps) + c);
       v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
@@ -384,31 +399,38 @@ __global__ void resid_add_rmsnorm_kernel(float* __restrict__ resid, const float*
     o.y = pack2(o2, o3);
     if (out_bf16 != nullptr) reinterpret_cast<uint2*>(out_bf16 + row * H)[c] = o;
     if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + row * H)[c] = make_float4(o0, o1, o2, o3);
-    if (j >= 0 && pr.out_hilo != nullptr) {
+    if (j >= 0 && (pr.out_hilo != nullptr || pr.append_base >= 0)) {
       const float2 h0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.x));
       const float2 h1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o.y));
       uint2 l;
       l.x = pack2(o0 - h0.x, o1 - h0.y);
       l.y = pack2(o2 - h1.x, o3 - h1.y);
-      uint2* d = reinterpret_cast<uint2*>(pr.out_hilo + j * 2 * H);
-      d[c] = o;
-      d[H4 + c] = l;
+      if (pr.out_hilo != nullptr) {
+        uint2* d = reinterpret_cast<uint2*>(pr.out_hilo + j * 2 * H);
+        d[c] = o;
+        d[H4 + c] = l;
+      }
+      if (pr.append_base >= 0 && out_bf16 != nullptr) {
+        reinterpret_cast<uint2*>(out_bf16 + (pr.append_base + j) * H)[c] = o;
+        reinterpret_cast<uint2*>(out_bf16 + (pr.append_base + pr.n_prec + j) * H)[c] = l;
+      }
     }
   }
 }
 int launch_resid_add_rmsnorm(float* resid, const float* partial, int n_planes, long long plane_stride, const float* w,
                              __nv_bfloat16* out_bf16, float* out_f32, long long rows, int H, float eps, cudaStream_t s) {
   return launch_resid_add_rmsnorm_precise(resid, partial, n_planes, plane_stride, w, out_bf16, out_f32, rows, H, eps, nullptr, nullptr, 0,
-                                          0, nullptr, s);
+                                          0, nullptr, s, 0, 0, 0);
 }
 int launch_resid_add_rmsnorm_precise(float* resid, const float* partial, int n_planes, long long plane_stride, const float* w,
                                      __nv_bfloat16* out_bf16, float* out_f32, long long rows, int H, float eps, const int* prec_of_row,
                                      const float* prec_partial, int n_prec_planes, long long prec_plane_stride, __nv_bfloat16* out_hilo,
-                                     cudaStream_t s) {
+                                     cudaStream_t s, long long pair_offset, int append_rows, int n_prec) {
   if (H % 4 != 0 || rows <= 0) return rows == 0 ? 0 : -2;
   PreciseRows pr;
   pr.prec_of_row = prec_of_row; pr.prec_partial = prec_partial; pr.n_prec_planes = n_prec_planes;
   pr.prec_plane_stride = prec_plane_stride; pr.out_hilo = out_hilo;
+  pr.pair_offset = pair_offset; pr.append_base = append_rows ? (int)rows : -1; pr.n_prec = n_prec;
   if (rows <= 256 && H >= 2048)   // few rows (single-frame steps): one float4 chunk or two per thread, every load in flight at once
     launch_k(resid_add_rmsnorm_kernel<512>, dim3((unsigned)rows), dim3(512), H * sizeof(float), s, resid, partial, n_planes,
              plane_stride, w, out_bf16, out_f32, H, eps, pr);
@@ -443,7 +465,8 @@ __global__ void final_norm_heads_kernel(const float* __restrict__ resid, const f
   const float* src = partial + row * H;
   int np = n_planes;
   long long ps = plane_stride;
-  if (j >= 0 && pr.prec_partial != nullptr) { src = pr.prec_partial + j * H; np = pr.n_prec_planes; ps = pr.prec_plane_stride; }
+  long long pair = 0;
+  if (j >= 0 && pr.prec_partial != nullptr) { src = pr.prec_partial + j * H; np = pr.n_prec_planes; ps = pr.prec_plane_stride; pair = pr.pair_offset; }
   float ss = 0.f;
   for (int c = threadIdx.x; c < H4; c += NT) {
     float4 v = reinterpret_cast<const float4*>(resid + row * H)[c];
@@ -453,6 +476,13 @@ __global__ void final_norm_heads_kernel(const float* __restrict__ resid, const f
       a[p] = p < np ? __ldg(reinterpret_cast<const float4*>(src + p * ps) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int p = 0; p < kMaxPlanes; ++p) { v.x += a[p].x; v.y += a[p].y; v.z += a[p].z; v.w += a[p].w; }
+    if (pair != 0) {             // the lo copy's output row of a precise row (appended-rows form)
+#pragma unroll
+      for (int p = 0; p < kMaxPlanes; ++p)
+        a[p] = p < np ? __ldg(reinterpret_cast<const float4*>(src + pair + p * ps) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < kMaxPlanes; ++p) { v.x += a[p].x; v.y += a[p].y; v.z += a[p].z; v.w += a[p].w; }
+    }
     for (int p = kMaxPlanes; p < np; ++p) {
       const float4 b = __ldg(reinterpret_cast<const float4*>(src + p * ps) + c);
       v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
@@ -502,7 +532,7 @@ __global__ void final_norm_heads_kernel(const float* __restrict__ resid, const f
 int launch_final_norm_heads(const float* resid, const float* partial, int n_planes, long long plane_stride, const float* w,
                             const int* score_rows, int n_score, const int* lm_rows, int n_lm, const float* head_w, float* logits_out,
                             float* scores_out, __nv_bfloat16* lm_x, int H, float eps, const int* prec_of_row, const float* prec_partial,
-                            int n_prec_planes, long long prec_plane_stride, cudaStream_t s) {
+                            int n_prec_planes, long long prec_plane_stride, cudaStream_t s, long long pair_offset) {
   if (H % 4 != 0 || n_score < 0 || n_lm < 0) return -2;
   if (n_score + n_lm == 0) return 0;
   if ((n_score > 0 && (score_rows == nullptr || head_w == nullptr || logits_out == nullptr || scores_out == nullptr)) ||
@@ -511,8 +541,39 @@ int launch_final_norm_heads(const float* resid, const float* partial, int n_plan
   constexpr int NT = 256;
   PreciseRows pr;
   pr.prec_of_row = prec_of_row; pr.prec_partial = prec_partial; pr.n_prec_planes = n_prec_planes; pr.prec_plane_stride = prec_plane_stride;
+  pr.pair_offset = pair_offset;
   launch_k(final_norm_heads_kernel<NT>, dim3((unsigned)(n_score + n_lm)), dim3(NT), H * sizeof(float), s, resid, partial, n_planes,
            plane_stride, w, score_rows, n_score, lm_rows, head_w, logits_out, scores_out, lm_x, H, eps, pr);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// SwiGLU of the precise rows from the raw pre-activations their hi and lo copies produced in the main gate/up GEMM:
+//   g = raw[j][2i] + raw[P + j][2i],  u = raw[j][2i+1] + raw[P + j][2i+1],  h = silu(g) * u
+// written as two appended activation rows of the down projection: h_rows[j] = bf16(h), h_rows[P + j] = bf16(h - bf16(h)).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void swiglu_from_raw_kernel(const float* __restrict__ raw, long long ld_raw, __nv_bfloat16* __restrict__ h_rows, long long ldh,
+                                       int P, int I) {
+  pdl_prologue();
+  const int j = blockIdx.y;
+  const float* hi = raw + (long long)j * ld_raw;
+  const float* lo = raw + (long long)(P + j) * ld_raw;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 2; i < I; i += gridDim.x * blockDim.x * 2) {
+    const float4 a = *reinterpret_cast<const float4*>(hi + 2 * i), b = *reinterpret_cast<const float4*>(lo + 2 * i);
+    const float g0 = a.x + b.x, u0 = a.y + b.y, g1 = a.z + b.z, u1 = a.w + b.w;
+    const float h0 = g0 / (1.0f + __expf(-g0)) * u0, h1 = g1 / (1.0f + __expf(-g1)) * u1;
+    const uint32_t hp = pack2(h0, h1);
+    const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hp));
+    *reinterpret_cast<uint32_t*>(h_rows + (long long)j * ldh + i) = hp;
+    *reinterpret_cast<uint32_t*>(h_rows + (long long)(P + j) * ldh + i) = pack2(h0 - hf.x, h1 - hf.y);
+  }
+}
+int launch_swiglu_from_raw(const float* raw, long long ld_raw, __nv_bfloat16* h_rows, long long ldh, int P, int I, cudaStream_t s) {
+  if (P <= 0) return 0;
+  if (I % 2 != 0 || ld_raw % 4 != 0 || ldh % 2 != 0) return -2;
+  int bx = (I / 2 + 255) / 256;
+  if (bx > 16) bx = 16;
+  launch_k(swiglu_from_raw_kernel, dim3(bx, P), dim3(256), 0, s, raw, ld_raw, h_rows, ldh, P, I);
   return 0;
 }
 
@@ -526,7 +587,8 @@ __global__ void qkv_finish_kernel(const float* __restrict__ partial, int n_plane
                                   const float* __restrict__ bias, const float* __restrict__ cos_tab,
                                   const float* __restrict__ sin_tab, const int* __restrict__ tok_pos,
                                   const int* __restrict__ tok_slot, __nv_bfloat16* __restrict__ q_out,
-                                  __nv_bfloat16* __restrict__ kv_layer, int Hq, int Hkv, int dh, int page_tokens) {
+                                  __nv_bfloat16* __restrict__ kv_layer, int Hq, int Hkv, int dh, int page_tokens,
+                                  const int* __restrict__ prec_of_row, int n_prec) {
   // one block per token; 8 threads per head, thread t handles the 8 rotation pairs (d, d + dh/2) with d in [8t', 8t'+8)
   // (dh = 128: half = 64 = 8 threads x 8 elements): 32-B vector loads of the split-K planes, 16-B bf16 stores
   pdl_prologue();
@@ -546,13 +608,19 @@ __global__ void qkv_finish_kernel(const float* __restrict__ partial, int n_plane
 #pragma unroll
     for (int i = 0; i < 8; ++i) { x0[i] = 0.f; x1[i] = 0.f; }
   }
+  // precise rows (appended-rows form): the token's projections are the sum of its hi copy's and its lo copy's output rows
+  // (rows M + j and M + P + j of every plane) instead of its own row
+  const int pj = prec_of_row != nullptr ? prec_of_row[tok] : -1;
+  const int n_src = pj >= 0 ? 2 : 1;
+  for (int srcs = 0; srcs < n_src; ++srcs)
   for (int p0 = 0; p0 < n_planes; p0 += 4) {      // four planes' loads (16 x 16 B per thread) in flight together
     float4 a[4], b[4], c[4], d[4];
+    const long long row = pj >= 0 ? (long long)gridDim.x + pj + (srcs ? n_prec : 0) : tok;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       const bool on = p0 + i < n_planes;
-      const float* pl = partial + (long long)(on ? p0 + i : 0) * plane_stride + (long long)tok * N;
+      const float* pl = partial + (long long)(on ? p0 + i : 0) * plane_stride + row * N;
       a[i] = on ? __ldg(reinterpret_cast<const float4*>(pl + col0)) : z;
       b[i] = on ? __ldg(reinterpret_cast<const float4*>(pl + col0 + 4)) : z;
       c[i] = on ? __ldg(reinterpret_cast<const float4*>(pl + col1)) : z;
@@ -595,12 +663,13 @@ __global__ void qkv_finish_kernel(const float* __restrict__ partial, int n_plane
 }
 int launch_qkv_finish(const float* partial, int n_planes, long long plane_stride, const float* bias, const float* cos_tab,
                       const float* sin_tab, const int* tok_pos, const int* tok_slot, __nv_bfloat16* q_out,
-                      __nv_bfloat16* kv_layer, int M, int Hq, int Hkv, int dh, int page_tokens, cudaStream_t s) {
+                      __nv_bfloat16* kv_layer, int M, int Hq, int Hkv, int dh, int page_tokens, cudaStream_t s, const int* prec_of_row,
+                      int n_prec) {
   if (M <= 0) return 0;
   const int heads = Hq + 2 * Hkv;
   if (dh != 128 || heads * 8 > 1024) return -2;
   launch_k(qkv_finish_kernel, dim3(M), dim3(heads * 8), 0, s, partial, n_planes, plane_stride, bias, cos_tab, sin_tab, tok_pos, tok_slot,
-           q_out, kv_layer, Hq, Hkv, dh, page_tokens);
+           q_out, kv_layer, Hq, Hkv, dh, page_tokens, prec_of_row, n_prec);
   return 0;
 }
 

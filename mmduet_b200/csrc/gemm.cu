@@ -47,6 +47,9 @@ struct GemmKernelParams {
   const float* row_w;   // EPI_BF16_HILO_POOL: pooling weight of every X row
   int pool_group;       // EPI_BF16_HILO_POOL: X rows per pooled output row (4 or 16)
   int row_w_period;     // > 0: row_w is indexed by row % row_w_period
+  float* raw_out;       // SwiGLU epilogues: raw fp32 (gate, up) pairs of the tokens >= raw_from (precise rows' hi / lo copies)
+  int raw_from;
+  long long ld_raw;
 };
 
 // HILO: the Y operand (activations, swap-AB) is a bf16 hi+lo pair [hi | lo] (2K wide): every stage carries the hi and the lo
@@ -401,6 +404,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_row + c0, v);
           tmem_ld_wait();
+          if (p.raw_out != nullptr && y0 + c0 + 32 > p.raw_from && n_ok) {   // warp-uniform: only the chunks holding appended rows
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {                   // lanes hold consecutive interleaved rows: a 128-B store per token
+              const int tk = y0 + c0 + j;
+              if (tk >= p.raw_from && tk < p.y_rows) p.raw_out[(long long)(tk - p.raw_from) * p.ld_raw + xi] = __uint_as_float(v[j]);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float mine = __uint_as_float(v[j]);
@@ -433,6 +443,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
               if (tok < p.y_rows) {
                 const float gv = __uint_as_float(g[j]);
                 const float uv = __uint_as_float(u[j]);
+                if (p.raw_out != nullptr && tok >= p.raw_from)
+                  *reinterpret_cast<float2*>(p.raw_out + (long long)(tok - p.raw_from) * p.ld_raw + 2 * xi) = make_float2(gv, uv);
                 const float s = gv / (1.0f + __expf(-gv));
                 const __nv_bfloat16 hi = __float2bfloat16_rn(s * uv);
                 outp[(long long)tok * p.ldo + xi] = hi;
@@ -475,6 +487,15 @@ __device__ __forceinline__ void epilogue_normal_tma(const GemmKernelParams& p, c
         uint32_t v[32];
         tmem_ld_32x32b_x32(t_row + c0 + 32 * h, v);
         tmem_ld_wait();
+        if (p.raw_out != nullptr) {     // appended precise rows: raw (gate, up) pairs, this lane's row, 32 columns
+          const int row = m_warp + lane;
+          if (row >= p.raw_from && row < p.x_rows) {
+            float4* dst = reinterpret_cast<float4*>(p.raw_out + (long long)(row - p.raw_from) * p.ld_raw + y0 + c0 + 32 * h);
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              dst[g] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]), __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+          }
+        }
 #pragma unroll
         for (int g = 0; g < 8; ++g) {   // 4 accumulator columns -> 2 outputs -> one packed word
           const float g0 = __uint_as_float(v[4 * g]), u0 = __uint_as_float(v[4 * g + 1]);
@@ -917,6 +938,7 @@ static int launch_cfg(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
 
   GemmKernelParams p;
   p.y_lo_off = a.K; p.out_hilo = a.out_hilo; p.row_w = a.row_w; p.pool_group = a.pool_group; p.row_w_period = a.row_w_period;
+  p.raw_out = a.raw_out; p.raw_from = a.raw_from; p.ld_raw = a.ld_raw;
   p.x_rows = a.x_rows; p.y_rows = a.y_rows;
   p.x_tiles = (a.x_rows + BM - 1) / BM;
   p.y_tiles = (a.y_rows + BN - 1) / BN;
@@ -970,6 +992,7 @@ static int launch_2cta(GemmContext* c, const GemmArgs& a, cudaStream_t stream) {
   p.k_splits = splits; p.kb_per_split = (p.kb_total + splits - 1) / splits;
   p.bias = a.bias; p.out = a.out; p.ldo = a.ldo; p.split_stride = 0; p.pdl_prefetch_x = 0; p.x_blocked = 0;
   p.y_lo_off = 0; p.out_hilo = 0; p.row_w = a.row_w; p.pool_group = a.pool_group; p.row_w_period = a.row_w_period;
+  p.raw_out = a.raw_out; p.raw_from = a.raw_from; p.ld_raw = a.ld_raw;
   const long long tiles = (long long)p.x_tiles * p.y_tiles * splits;
   const int max_clusters = (a.max_ctas > 0 ? a.max_ctas : c->num_sms) / 2;
   const int clusters = (int)(tiles < max_clusters ? tiles : max_clusters);

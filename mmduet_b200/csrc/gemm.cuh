@@ -51,6 +51,12 @@ struct GemmArgs {
   int pool_group = 0;                 // EPI_BF16_HILO_POOL: rows per pooled output (4 or 16; x_rows % pool_group == 0)
   int row_w_period = 0;               // > 0: row_w holds one period (a frame) and is indexed by row % period
   int force_1cta = 0;                 // single-CTA kernel with per-thread global stores (outputs in peer memory)
+  // SwiGLU epilogues (EPI_T_SWIGLU, EPI_T_SWIGLU_IL, EPI_SWIGLU_PAIR): tokens >= raw_from are the appended hi / lo rows of the
+  // "precise rows"; for them the raw fp32 pre-activations are written to raw_out[(token - raw_from) * ld_raw + 2j + {0: gate,
+  // 1: up}] (the nonlinearity needs gate_hi + gate_lo first; swiglu_from_raw finishes them).  raw_out == nullptr: off.
+  float* raw_out = nullptr;
+  int raw_from = 0;
+  int64_t ld_raw = 0;
   int y_hilo = 0;
   int out_hilo = 0;                   // EPI_T_SWIGLU: out row = [hi | lo], lo at column x_rows (ldo >= 2 * x_rows)
 };

@@ -24,15 +24,18 @@ int launch_resid_add_rmsnorm(float* resid, const float* partial, int n_planes, l
 int launch_resid_add_rmsnorm_precise(float* resid, const float* partial, int n_planes, long long plane_stride, const float* w,
                                      __nv_bfloat16* out_bf16, float* out_f32, long long rows, int H, float eps, const int* prec_of_row,
                                      const float* prec_partial, int n_prec_planes, long long prec_plane_stride, __nv_bfloat16* out_hilo,
-                                     cudaStream_t s);
+                                     cudaStream_t s, long long pair_offset = 0, int append_rows = 0, int n_prec = 0);
+// SwiGLU of the precise rows from the raw (gate, up) pre-activations of their hi and lo copies -> two appended bf16 rows each
+int launch_swiglu_from_raw(const float* raw, long long ld_raw, __nv_bfloat16* h_rows, long long ldh, int P, int I, cudaStream_t s);
 // final RMSNorm fused with the informative/relevance heads on the score rows (+ bf16 normalised rows for lm_head)
 int launch_final_norm_heads(const float* resid, const float* partial, int n_planes, long long plane_stride, const float* w,
                             const int* score_rows, int n_score, const int* lm_rows, int n_lm, const float* head_w, float* logits_out,
                             float* scores_out, __nv_bfloat16* lm_x, int H, float eps, const int* prec_of_row, const float* prec_partial,
-                            int n_prec_planes, long long prec_plane_stride, cudaStream_t s);
+                            int n_prec_planes, long long prec_plane_stride, cudaStream_t s, long long pair_offset = 0);
 int launch_qkv_finish(const float* partial, int n_planes, long long plane_stride, const float* bias, const float* cos_tab,
                       const float* sin_tab, const int* tok_pos, const int* tok_slot, __nv_bfloat16* q_out,
-                      __nv_bfloat16* kv_layer, int M, int Hq, int Hkv, int dh, int page_tokens, cudaStream_t s);
+                      __nv_bfloat16* kv_layer, int M, int Hq, int Hkv, int dh, int page_tokens, cudaStream_t s,
+                      const int* prec_of_row = nullptr, int n_prec = 0);
 int launch_gather_rows_bf16_to_f32(const __nv_bfloat16* table, const __nv_bfloat16* other, const int* src_row, float* dst,
                                    long long rows, int H, cudaStream_t s);
 int launch_gather_rows_f32_to_bf16(const float* src, const int* idx, __nv_bfloat16* dst, int T, int S, int G, int D, int hilo, cudaStream_t s);
