@@ -88,6 +88,7 @@ class StreamSession:
         self.fps = None
         self.lock = threading.Lock()   # the demo re-enters the step from another thread (demo/app.py:84-85)
         self.view = None
+        self._copy_stream = None
         self.step_ms = None            # set to a list to record host wall-clock ms of every frame pass (bench.py)
         self.clear()
 
@@ -112,13 +113,32 @@ class StreamSession:
         return self.view.length if self.view else 0
 
     # ---- input ----
-    def push_video(self, video_frames, batch=32):
+    def push_video(self, video_frames, batch=None):
         """uint8 [T,3,384,384] frames (what test/datasets.py yields; rescale/normalise happen inside the patch-embed kernel) or
-        already-processed float pixel_values."""
-        video_frames = video_frames.to(self.device, non_blocking=True)
-        for b in range(0, len(video_frames), batch):
-            tokens = self.model.visual_embed(video_frames[b:b + batch]).split(self.n_tok)
-            self.frames.extend(((b + r) / self.fps, t) for r, t in enumerate(tokens))
+        already-processed float pixel_values.  Frames are independent through the encoder, so the batch size (the reference
+        uses 32, test/inference.py:208) does not change any value: the encoder's preferred batch is used, and host frames are
+        uploaded batch by batch on a copy stream so that batch i+1 crosses PCIe while batch i is being encoded."""
+        batch = batch or self.model.vision.MAX_BATCH
+        n = len(video_frames)
+        if video_frames.device == self.device:
+            chunks = [(video_frames[b:b + batch], None) for b in range(0, n, batch)]
+        else:
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            main = torch.cuda.current_stream(self.device)
+            chunks = []
+            with torch.cuda.stream(self._copy_stream):
+                for b in range(0, n, batch):
+                    dev = video_frames[b:b + batch].to(self.device, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(self._copy_stream)
+                    dev.record_stream(main)
+                    chunks.append((dev, ev))
+        for i, (dev, ev) in enumerate(chunks):
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
+            tokens = self.model.visual_embed(dev).split(self.n_tok)
+            self.frames.extend(((i * batch + r) / self.fps, t) for r, t in enumerate(tokens))
 
     def push_queries(self, conversation):
         self.queries.extend((t["time"], t["content"]) for t in conversation if t["role"] == "user")
