@@ -407,7 +407,9 @@ __device__ __forceinline__ void attention_pipeline(const Params& prm, int n_item
     constexpr int NSM = 32 * TA_SOFTMAX_WARPS;
     int total_tiles = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) total_tiles += Front(prm, item).n_tiles();
+#ifndef MMD_ATTN_NO_ALT
     if (qi == 1 && total_tiles > 0) named_bar_arrive(1, NSM);
+#endif
     int g0 = 0, it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       Front fe(prm, item);
@@ -476,7 +478,9 @@ __device__ __forceinline__ void attention_pipeline(const Params& prm, int n_item
             m_ref = m_new;
           }
         }
+#ifndef MMD_ATTN_NO_ALT
         named_bar_sync(1 + qi, NSM);
+#endif
         if (row == 0) TRACE_EV(qi, g, 3);
         const float msc = (m_ref == -INFINITY) ? 0.f : m_ref * sl2;
         // probabilities -> bf16 P tile, written back into TMEM over the S buffer they came from (two keys per 32-bit
@@ -510,8 +514,12 @@ __device__ __forceinline__ void attention_pipeline(const Params& prm, int n_item
             const float p0 = exp_on_fma_pipe(i) ? exp2_poly(x[2 * i]) : exp2f(x[2 * i]);
             const float p1 = exp_on_fma_pipe(i) ? exp2_poly(x[2 * i + 1]) : exp2f(x[2 * i + 1]);
 #endif
+#ifdef MMD_P_TRUNC      // experiment: bf16 pair by taking the high halves (one PRMT on the ALU pipe) instead of F2FP.BF16.PACK_AB
+            pk[i] = __byte_perm(__float_as_uint(p0), __float_as_uint(p1), 0x7632);
+#else
             __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
             pk[i] = *reinterpret_cast<uint32_t*>(&h);
+#endif
             if constexpr (!ONES_COL) {
               // row sum of the ROUNDED probabilities (numerator and denominator stay consistent under the stale base)
               rs += __uint_as_float(pk[i] << 16) + __uint_as_float(pk[i] & 0xffff0000u);
@@ -521,7 +529,9 @@ __device__ __forceinline__ void attention_pipeline(const Params& prm, int n_item
           tmem_st_32x32b_x16(t_row + sb * TA_BN + 16 * c, pk);
         }
         l_run += rs;
+#ifndef MMD_ATTN_NO_ALT
         if (qi == 0 || g + 1 < total_tiles) named_bar_arrive(2 - qi, NSM);
+#endif
         if (row == 0) TRACE_EV(qi, g, 4);
         tmem_st_wait();
         if (row == 0) TRACE_EV(qi, g, 5);
