@@ -258,7 +258,7 @@ static int kd_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("MMD_KD_VARIANT");
-    v = e ? atoi(e) : 1;
+    v = e ? atoi(e) : 0;
   }
   return v;
 }
