@@ -380,3 +380,45 @@ def test_loop_with_a_real_hf_tokenizer(tmp_path):
     infer.inplace_output_ids = torch.zeros(1, 4, device=infer.device, dtype=torch.long)
     text = infer._generate_response()
     assert isinstance(text, str) and infer.last_role == "assistant"
+
+
+def test_many_videos_leave_no_pages_or_memory_behind():
+    """Production soak in miniature: 18 videos in a row (three passes over six videos of different length, half of them with a
+    user query) through ONE LiveInferForBenchmark, responses generated and assistant turns rolled back, reset() between videos
+    as test/inference.py:347-349 does: every KV page is back in the pool after each reset, and the third pass leaves exactly
+    the allocator footprint and the results of the second (nothing accumulates, nothing depends on history)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    torch.set_grad_enabled(False)
+    from mmduet_b200 import build_model_and_tokenizer
+    from mmduet_b200.config import ModelConfig
+    from mmduet_b200.inference import LiveInferForBenchmark
+    arch = A.SMALL
+    w = R.make_weights(arch, seed=92)
+    model, tok = build_model_and_tokenizer(state_dict=w, model_config=ModelConfig.from_any(arch), device="cuda:0", max_context=2048,
+                                           kv_pages=96)
+    dec = model.decoder
+    n_free = len(dec._free)
+    infer = LiveInferForBenchmark(_args(stream_end_score_sum_threshold=1.5, remove_assistant_turns=True), model=model, tokenizer=tok)
+    infer.inplace_output_ids = torch.zeros(1, 6, device=infer.device, dtype=torch.long)
+    videos = [R.synthetic_frames(10 + v % 3, seed=100 + v) for v in range(6)]
+    mem, results, n_resp = [], [], 0
+    for epoch in range(3):
+        for v, frames in enumerate(videos):
+            infer.reset()
+            assert len(dec._free) == n_free, f"pass {epoch} video {v}: {n_free - len(dec._free)} pages still held after reset()"
+            infer.set_fps(fps=2)
+            infer.input_video_stream(frames)
+            if v % 2:
+                infer.input_query_stream([{"role": "user", "time": 1.0, "content": "what is happening"}])
+            turns = infer.inference()
+            n_resp += sum(t["role"] == "assistant" for t in turns)
+            assert len(infer.debug_data_list) == len(frames)
+            torch.cuda.synchronize()
+            mem.append(torch.cuda.memory_allocated())
+            results.append((turns, [d["informative_score"] for d in infer.debug_data_list]))
+    infer.reset()
+    assert len(dec._free) == n_free
+    assert n_resp > 0                                     # the soak did generate and roll back
+    assert mem[12:] == mem[6:12], mem
+    assert results[12:] == results[6:12] == results[:6]
