@@ -10,6 +10,8 @@
  * nothing on the device (the caller provides workspaces sized by the *_workspace_bytes functions) and never
  * synchronise; the return value is 0 or a negative MMD_ERR_* code with a thread-local message available from
  * mmd_last_error().  There is no CPU fallback: mmd_create fails on anything that is not an sm_100 device.
+ * Kernels launch on the CURRENT device: every call that takes an mmd_ctx refuses (MMD_ERR_ARG) to run while a device other
+ * than the context's is current, instead of launching on the wrong GPU.
  */
 #ifndef MMDUET_B200_H_
 #define MMDUET_B200_H_

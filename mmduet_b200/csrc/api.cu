@@ -78,13 +78,26 @@ struct ProfScope {
   ~ProfScope() { if (b) cudaEventRecord(b, s); }
 };
 
-#define CHECK_CTX(c) do { if ((c) == nullptr) return fail(MMD_ERR_ARG, "null context"); } while (0)
+// Kernels launch on the CURRENT device and shared-memory attributes are kept per device: a context used while another
+// device is current would run on the wrong GPU's memory, so it is refused.
+static int ctx_device_mismatch(const struct mmd_ctx* c);
+#define CHECK_CTX(c) do { if ((c) == nullptr) return fail(MMD_ERR_ARG, "null context"); \
+                          if (int rc_ = ctx_device_mismatch(c)) return rc_; } while (0)
 #define RUN(expr, what) do { int rc_ = (expr); if (rc_ != 0) return fail(rc_, std::string(what) + ": " + mmd::gemm_last_error()); } while (0)
 #define RUNK(expr, what) do { int rc_ = (expr); if (rc_ != 0) return fail(rc_, std::string(what) + ": bad arguments"); } while (0)
 // stage-function variants: count the launch and time it when profiling is on (needs `c` and `s` in scope)
 #define PRUN(expr, what) do { ProfScope ps_(c, what, s, 1); int rc_ = (expr); if (rc_ != 0) return fail(rc_, std::string(what) + ": " + mmd::gemm_last_error()); } while (0)
 #define PRUNK(expr, what) do { ProfScope ps_(c, what, s, 1); int rc_ = (expr); if (rc_ != 0) return fail(rc_, std::string(what) + ": bad arguments"); } while (0)
 #define PRUNK2(expr, what) do { ProfScope ps_(c, what, s, 2); int rc_ = (expr); if (rc_ != 0) return fail(rc_, std::string(what) + ": bad arguments"); } while (0)
+
+static int ctx_device_mismatch(const mmd_ctx* c) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess) return fail(MMD_ERR_CUDA, "cudaGetDevice failed");
+  if (cur != c->device)
+    return fail(MMD_ERR_ARG, "context belongs to device " + std::to_string(c->device) + " but device " + std::to_string(cur) +
+                                 " is current (call cudaSetDevice / torch.cuda.set_device first)");
+  return 0;
+}
 
 static int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

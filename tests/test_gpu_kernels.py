@@ -571,3 +571,18 @@ def test_probe_attention(env, T, S, H, dh):
     a = torch.softmax(torch.einsum("hd,thsd->ths", q.view(H, dh), k), -1)
     ref = torch.einsum("ths,thsd->thd", a, v).reshape(T, D)
     assert (out - ref).abs().max() < 1e-4
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_context_refuses_the_wrong_current_device(env):
+    """A context created for device 0 must not launch while device 1 is current (kernels go to the current device)."""
+    _lib, ops, lib, ctx = env
+    x = torch.zeros(128, 64, device="cuda:0", dtype=torch.bfloat16)
+    out = torch.zeros(128, 128, device="cuda:0", dtype=torch.bfloat16)
+    with torch.cuda.device(1):
+        rc = lib.mmd_gemm_bf16(ctx, _lib.EPI_BF16, _lib.ACT_NONE, x.data_ptr(), None, 128, 64, x.data_ptr(), 128, 64, 64, None,
+                               out.data_ptr(), 128, 1, 0, torch.cuda.current_stream().cuda_stream)
+    assert rc != 0 and b"is current" in lib.mmd_last_error()
+    rc = lib.mmd_gemm_bf16(ctx, _lib.EPI_BF16, _lib.ACT_NONE, x.data_ptr(), None, 128, 64, x.data_ptr(), 128, 64, 64, None,
+                           out.data_ptr(), 128, 1, 0, _s())
+    assert rc == 0
