@@ -262,6 +262,12 @@ typedef struct {
    * hi+lo inside the main kernels and ignore these fields. */
   int n_prec_rows; const int* prec_rows;     /* int32 [n_prec_rows] row indices, ascending */
   const int* prec_of_row;            /* int32 [n_tokens]: index into prec_rows, or -1 */
+  /* Layer-pipeline stages (one video's decoder split by layers over several GPUs; the weights struct of a stage lists its
+   * own layers only): resid_in != NULL starts the pass from this fp32 residual stream [n_tokens, H] instead of the
+   * embedding lookup (src_row / frame_tokens unused); resid_out != NULL writes the residual stream after the stage's last
+   * layer there and skips model.norm, the heads and lm_head (score / lm rows still select the precise rows). */
+  const float* resid_in;
+  float* resid_out;
 } mmd_step;
 
 MMD_API int64_t mmd_decoder_workspace_bytes(mmd_ctx*, const mmd_dec_weights*, int max_tokens, int max_lm_rows);

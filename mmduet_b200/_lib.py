@@ -63,7 +63,8 @@ class Step(ctypes.Structure):
                 ("tok_slot", c_void_p), ("n_streams", c_int), ("stream_desc", c_void_p), ("block_tables", c_void_p),
                 ("max_n_q", c_int), ("max_kv_len", c_int), ("n_score_rows", c_int), ("score_rows", c_void_p),
                 ("head_logits_out", c_void_p), ("scores_out", c_void_p), ("n_lm_rows", c_int), ("lm_rows", c_void_p),
-                ("lm_logits_out", c_void_p), ("n_prec_rows", c_int), ("prec_rows", c_void_p), ("prec_of_row", c_void_p)]
+                ("lm_logits_out", c_void_p), ("n_prec_rows", c_int), ("prec_rows", c_void_p), ("prec_of_row", c_void_p),
+                ("resid_in", c_void_p), ("resid_out", c_void_p)]
 
 
 P = ctypes.POINTER

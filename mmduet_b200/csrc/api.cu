@@ -533,8 +533,11 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
   if (w->head_dim != 128 || w->q_heads % w->kv_heads != 0 || w->hidden % 8 != 0 || w->mlp % 8 != 0)
     return fail(MMD_ERR_ARG, "mmd_decoder_step: unsupported architecture (head_dim 128, dims multiples of 8)");
   if (st->n_streams <= 0 || st->stream_desc == nullptr || st->block_tables == nullptr || st->tok_pos == nullptr ||
-      st->tok_slot == nullptr || st->src_row == nullptr)
+      st->tok_slot == nullptr || (st->src_row == nullptr && st->resid_in == nullptr))
     return fail(MMD_ERR_ARG, "mmd_decoder_step: incomplete step description");
+  if (st->resid_in == nullptr && w->embed == nullptr) return fail(MMD_ERR_ARG, "mmd_decoder_step: no embedding table and no resid_in");
+  if (st->resid_out == nullptr && (st->n_score_rows > 0 || st->n_lm_rows > 0) && w->final_norm_w == nullptr)
+    return fail(MMD_ERR_ARG, "mmd_decoder_step: this stage has no final norm (pass resid_out)");
   if (st->max_kv_len > w->max_pos) return fail(MMD_ERR_ARG, "mmd_decoder_step: context exceeds the RoPE table (max_pos)");
   if (st->n_lm_rows > 0 && (w->lm_head == nullptr || st->lm_logits_out == nullptr || st->lm_rows == nullptr))
     return fail(MMD_ERR_ARG, "mmd_decoder_step: lm rows requested without lm_head / output buffer");
@@ -565,8 +568,13 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
   __nv_bfloat16* xmain = all_prec ? nullptr : buf.x;         // plain bf16 normalised rows (unused when every row is [hi | lo])
   const int* prec_of_row = app_prec ? st->prec_of_row : nullptr;
   // inputs_embeds = cat(embed_tokens(prefix ids), frame tokens) -> fp32 residual stream   (test/inference.py:235-238)
-  PRUNK(mmd::launch_gather_rows_bf16_to_f32(static_cast<const __nv_bfloat16*>(w->embed), static_cast<const __nv_bfloat16*>(st->frame_tokens),
-                                           st->src_row, buf.resid, M, H, s), "embed/concat");
+  if (st->resid_in != nullptr) {   // a later stage of a layer pipeline: the residual stream arrives from the previous stage
+    if (cudaMemcpyAsync(buf.resid, st->resid_in, (size_t)M * H * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+      return fail(MMD_ERR_CUDA, "mmd_decoder_step: copy of resid_in failed");
+  } else {
+    PRUNK(mmd::launch_gather_rows_bf16_to_f32(static_cast<const __nv_bfloat16*>(w->embed), static_cast<const __nv_bfloat16*>(st->frame_tokens),
+                                             st->src_row, buf.resid, M, H, s), "embed/concat");
+  }
   PRUNK(mmd::launch_resid_add_rmsnorm_precise(buf.resid, nullptr, 0, 0, w->layers[0].ln1_w, xmain, nullptr, M, H, w->rms_eps, prec_of_row,
                                              nullptr, 0, 0, all_prec ? buf.xp2 : nullptr, s, 0, app_prec ? 1 : 0, P), "input_layernorm");
   const int s_qkv = choose_splits(c->num_sms, NQKV, H, Mt);
@@ -649,6 +657,16 @@ int mmd_decoder_step(mmd_ctx* c, const mmd_dec_weights* w, const mmd_kv_pool* po
                                                  w->rms_eps, prec_of_row, app_prec ? buf.planes + (int64_t)M * H : nullptr, eff,
                                                  (int64_t)Mt * H, all_prec ? buf.xp2 : nullptr, s, (int64_t)P * H, app_prec ? 1 : 0, P),
             "next_layernorm");
+  }
+  if (st->resid_out != nullptr) {
+    // not the last stage: fold the pending down_proj planes into the residual stream (precise rows: their hi + lo copies'
+    // outputs) and hand it on; model.norm, the heads and lm_head belong to the last stage
+    PRUNK(mmd::launch_resid_add_rmsnorm_precise(buf.resid, buf.planes, eff, (int64_t)Mt * H, nullptr, nullptr, nullptr, M, H, w->rms_eps,
+                                               prec_of_row, app_prec ? buf.planes + (int64_t)M * H : nullptr, eff, (int64_t)Mt * H, nullptr,
+                                               s, (int64_t)P * H, 0, P), "next_layernorm");
+    if (cudaMemcpyAsync(st->resid_out, buf.resid, (size_t)M * H * sizeof(float), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+      return fail(MMD_ERR_CUDA, "mmd_decoder_step: copy to resid_out failed");
+    return check_launch("mmd_decoder_step");
   }
   // final norm on the rows that are read only, with the informative/relevance heads as its epilogue (+ bf16 rows for lm_head)
   if (st->n_score_rows > 0 && (st->score_rows == nullptr || st->head_logits_out == nullptr || st->scores_out == nullptr || w->heads_w == nullptr))

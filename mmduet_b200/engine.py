@@ -317,7 +317,11 @@ class CacheView:
 class DecoderEngine:
     """Qwen2 decoder + informative/relevance heads over a paged KV pool (video_head_live_llava_qwen.py:121-205)."""
 
-    def __init__(self, cfg: ModelConfig, state_dict, device, n_pages=None, max_tokens=512, max_lm_rows=1, max_context=None):
+    def __init__(self, cfg: ModelConfig, state_dict, device, n_pages=None, max_tokens=512, max_lm_rows=1, max_context=None,
+                 layer_range=None):
+        """layer_range=(l0, l1): this engine is ONE STAGE of a layer pipeline (parallel.LayerPipeline): it holds decoder layers
+        l0 .. l1-1 and their KV pages only; the first stage also holds the embedding table, the last one model.norm, the
+        heads and lm_head.  step(..., resid_in=, resid_out=True) hands the fp32 residual stream from stage to stage."""
         cfg.validate()
         self.cfg, self.device = cfg, torch.device(device)
         self.lib = _lib.load()
@@ -325,8 +329,12 @@ class DecoderEngine:
         sd, dev = state_dict, self.device
         H = cfg.hidden
         keep = []
-        layers = (_lib.DecLayer * cfg.layers)()
-        for i in range(cfg.layers):
+        l0, l1 = layer_range if layer_range is not None else (0, cfg.layers)
+        if not (0 <= l0 < l1 <= cfg.layers):
+            raise _lib.MmdError(f"layer_range {layer_range} outside 0..{cfg.layers}")
+        self.layer_range, self.first_stage, self.last_stage = (l0, l1), l0 == 0, l1 == cfg.layers
+        layers = (_lib.DecLayer * (l1 - l0))()
+        for i in range(l0, l1):
             p = f"model.layers.{i}."
             t = dict(ln1_w=_f32(sd[p + "input_layernorm.weight"], dev),
                      qkv_w=_bf16(torch.cat([sd[p + f"self_attn.{n}_proj.weight"] for n in "qkv"], 0), dev),
@@ -338,28 +346,31 @@ class DecoderEngine:
                                      .reshape(2 * cfg.mlp, H), dev),
                      down_w=_bf16(sd[p + "mlp.down_proj.weight"], dev))
             for k, v in t.items():
-                setattr(layers[i], k, v.data_ptr())
+                setattr(layers[i - l0], k, v.data_ptr())
             keep.append(t)
         self.max_context = int(max_context or cfg.max_pos)
         # RoPE tables exactly as Qwen2RotaryEmbedding computes them in fp32 (TF:models/qwen2/modeling_qwen2.py:102-125)
         inv_freq = 1.0 / (cfg.rope_theta ** (torch.arange(0, cfg.head_dim, 2, dtype=torch.int64).float() / cfg.head_dim))
         freqs = torch.arange(self.max_context, dtype=torch.float32)[:, None] * inv_freq[None, :]
-        t = dict(final_norm_w=_f32(sd["model.norm.weight"], dev), embed=_bf16(sd["model.embed_tokens.weight"], dev),
-                 heads_w=_f32(torch.cat([sd["informative_head.weight"], sd["relevance_head.weight"]], 0), dev),
-                 rope_cos=_f32(freqs.cos(), dev), rope_sin=_f32(freqs.sin(), dev))
-        self.embed = t["embed"]
-        lm = sd.get("lm_head.weight")
+        t = dict(rope_cos=_f32(freqs.cos(), dev), rope_sin=_f32(freqs.sin(), dev))
+        if self.first_stage:
+            t["embed"] = _bf16(sd["model.embed_tokens.weight"], dev)
+        if self.last_stage:
+            t["final_norm_w"] = _f32(sd["model.norm.weight"], dev)
+            t["heads_w"] = _f32(torch.cat([sd["informative_head.weight"], sd["relevance_head.weight"]], 0), dev)
+        self.embed = t.get("embed")
+        lm = sd.get("lm_head.weight") if self.last_stage else None
         self.lm_head = _bf16(lm, dev) if lm is not None else None
         keep.append(t)
         self._layers, self._keep = layers, keep
-        self.w = _lib.DecWeights(hidden=H, n_layers=cfg.layers, q_heads=cfg.q_heads, kv_heads=cfg.kv_heads, head_dim=cfg.head_dim,
+        ptrs = {k: (t[k].data_ptr() if k in t else 0) for k in ("final_norm_w", "embed", "heads_w", "rope_cos", "rope_sin")}
+        self.w = _lib.DecWeights(hidden=H, n_layers=l1 - l0, q_heads=cfg.q_heads, kv_heads=cfg.kv_heads, head_dim=cfg.head_dim,
                                  mlp=cfg.mlp, vocab=cfg.vocab, max_pos=self.max_context, rms_eps=cfg.rms_eps, layers=layers,
-                                 lm_head=self.lm_head.data_ptr() if self.lm_head is not None else 0,
-                                 **{k: v.data_ptr() for k, v in t.items()})
+                                 lm_head=self.lm_head.data_ptr() if self.lm_head is not None else 0, **ptrs)
         if n_pages is None:
             n_pages = (self.max_context + PAGE - 1) // PAGE + 1
         self.n_pages = n_pages
-        self.pool = torch.empty(cfg.layers, n_pages, 2, cfg.kv_heads, PAGE, cfg.head_dim, dtype=torch.bfloat16, device=dev)
+        self.pool = torch.empty(l1 - l0, n_pages, 2, cfg.kv_heads, PAGE, cfg.head_dim, dtype=torch.bfloat16, device=dev)
         self.kv = _lib.KvPool(pool=self.pool.data_ptr(), layer_stride=self.pool.stride(0), n_pages=n_pages)
         self._free = list(range(n_pages - 1, -1, -1))
         self._lock = threading.Lock()
@@ -367,6 +378,40 @@ class DecoderEngine:
         self._ws = None
         self._ensure_ws(max_tokens, max_lm_rows)
         self._meta_ring, self._meta_next = [None] * 8, 0
+
+    def stage(self, layer_range, n_pages=None, max_tokens=None):
+        """A pipeline-stage view of this (whole) engine: decoder layers l0 .. l1-1 on the SAME packed weights, with its own KV
+        pages, workspace and lock (parallel.LayerPipeline runs one stage per GPU; tests chain stages on one GPU)."""
+        l0, l1 = layer_range
+        if self.layer_range != (0, self.cfg.layers) or not (0 <= l0 < l1 <= self.cfg.layers):
+            raise _lib.MmdError(f"stage({layer_range}) needs a whole engine and a range inside 0..{self.cfg.layers}")
+        st = object.__new__(DecoderEngine)
+        st.cfg, st.device, st.lib, st.ctx = self.cfg, self.device, self.lib, self.ctx
+        st.layer_range, st.first_stage, st.last_stage = (l0, l1), l0 == 0, l1 == self.cfg.layers
+        layers = (_lib.DecLayer * (l1 - l0))()
+        for i in range(l0, l1):
+            layers[i - l0] = self._layers[i]
+        st._layers, st._keep = layers, self._keep              # the weight tensors stay owned (and alive) through the parent's list
+        st.max_context = self.max_context
+        st.embed = self.embed if st.first_stage else None
+        st.lm_head = self.lm_head if st.last_stage else None
+        w = self.w
+        st.w = _lib.DecWeights(hidden=w.hidden, n_layers=l1 - l0, q_heads=w.q_heads, kv_heads=w.kv_heads, head_dim=w.head_dim, mlp=w.mlp,
+                               vocab=w.vocab, max_pos=w.max_pos, rms_eps=w.rms_eps, layers=layers,
+                               final_norm_w=w.final_norm_w if st.last_stage else 0, heads_w=w.heads_w if st.last_stage else 0,
+                               lm_head=w.lm_head if st.last_stage else 0, embed=w.embed if st.first_stage else 0,
+                               rope_cos=w.rope_cos, rope_sin=w.rope_sin)
+        st.n_pages = n_pages if n_pages is not None else self.n_pages
+        cfg = self.cfg
+        st.pool = torch.empty(l1 - l0, st.n_pages, 2, cfg.kv_heads, PAGE, cfg.head_dim, dtype=torch.bfloat16, device=self.device)
+        st.kv = _lib.KvPool(pool=st.pool.data_ptr(), layer_stride=st.pool.stride(0), n_pages=st.n_pages)
+        st._free = list(range(st.n_pages - 1, -1, -1))
+        st._lock = threading.Lock()
+        st.max_tokens, st.max_lm_rows = max_tokens or self.max_tokens, self.max_lm_rows
+        st._ws = None
+        st._ensure_ws(st.max_tokens, st.max_lm_rows)
+        st._meta_ring, st._meta_next = [None] * 8, 0
+        return st
 
     # ---- pages ----
     def _alloc_page(self):
@@ -387,16 +432,22 @@ class DecoderEngine:
             self._ws = torch.empty(n, dtype=torch.uint8, device=self.device)
 
     # ---- the step ----
-    def step(self, items, score="last", lm="none"):
+    def step(self, items, score="last", lm="none", resid_in=None, resid_out=False):
         """One decoder pass over several streams.
 
         items: list of dicts {storage: KVStorage, past: int (view length to append at), and either
                               embeds: bf16 [M,H] tensor  or  ids: list[int] (+ optional frames: bf16 [n,H] appended after)}
         score: 'last' (last row of each item), 'all', 'frame_ends' (item key 'score_rows': row offsets inside the item) or 'none'
         lm:    'none' or 'last' (lm_head logits for the last row of each item)
-        Returns dict(head_logits [n,4], scores [n,2], lm_logits [n_lm,V] or None, views [CacheView per item])."""
+        Returns dict(head_logits [n,4], scores [n,2], lm_logits [n_lm,V] or None, views [CacheView per item]).
+
+        Layer-pipeline stages (layer_range): a later stage passes resid_in = the fp32 residual stream [M,H] of the previous
+        stage, with items that carry 'n_rows' instead of ids / frames; every stage but the last passes resid_out=True and
+        gets dict(resid [M,H] fp32, views) back (score / lm still name the rows that are read: they select the precise rows)."""
+        if (resid_in is None) != self.first_stage or bool(resid_out) == self.last_stage:
+            raise _lib.MmdError(f"stage {self.layer_range}: resid_in is for later stages, resid_out for all but the last")
         with self._lock:
-            return self._step_locked(items, score, lm)
+            return self._step_locked(items, score, lm, resid_in, resid_out)
 
     def _plan(self, items, score, lm):
         """Phase 1 of a step: validates every item and works out rows, positions and page needs WITHOUT touching any stream
@@ -413,7 +464,9 @@ class DecoderEngine:
             if past < 0 or past > st.length:
                 raise _lib.MmdError("cache view is longer than the stream (stale view after a rollback)")
             chunk = None
-            if it.get("embeds") is not None:
+            if it.get("n_rows") is not None:               # a later pipeline stage: the rows arrive as a residual stream
+                rows = [0] * int(it["n_rows"])
+            elif it.get("embeds") is not None:
                 chunk = it["embeds"]
                 rows = []
             else:
@@ -467,7 +520,7 @@ class DecoderEngine:
         ev.record()
         return devbuf
 
-    def _step_locked(self, items, score, lm):
+    def _step_locked(self, items, score, lm, resid_in=None, resid_out=False):
         H, dev = self.cfg.hidden, self.device
         plan = self._plan(items, score, lm)
         src_row, tok_pos, tok_slot, desc, tables, score_rows, lm_rows = [], [], [], [], [], [], []
@@ -537,12 +590,19 @@ class DecoderEngine:
             n_s, n_l = len(score_rows), len(lm_rows)
             head_logits = torch.empty(max(n_s, 1), 4, dtype=torch.float32, device=dev)
             scores = torch.empty(max(n_s, 1), 2, dtype=torch.float32, device=dev)
-            lm_logits = torch.empty(n_l, self.cfg.vocab, dtype=torch.float32, device=dev) if n_l else None
+            lm_logits = torch.empty(n_l, self.cfg.vocab, dtype=torch.float32, device=dev) if n_l and not resid_out else None
+            if resid_in is not None and (resid_in.shape != (M, H) or resid_in.dtype != torch.float32 or not resid_in.is_contiguous()
+                                         or resid_in.device != dev):
+                raise _lib.MmdError(f"resid_in must be a contiguous fp32 [{M}, {H}] tensor on {dev}")
+            resid = torch.empty(M, H, dtype=torch.float32, device=dev) if resid_out else None
+            if resid_out:
+                n_l = 0
             step = _lib.Step(n_tokens=M, src_row=p_src, frame_tokens=_lib.ptr(frame_tokens), tok_pos=p_pos, tok_slot=p_slot,
                              n_streams=len(items), stream_desc=p_desc, block_tables=p_tab, max_n_q=max_n_q, max_kv_len=max_kv,
                              n_score_rows=n_s, score_rows=p_score, head_logits_out=head_logits.data_ptr(), scores_out=scores.data_ptr(),
                              n_lm_rows=n_l, lm_rows=p_lm, lm_logits_out=_lib.ptr(lm_logits),
-                             n_prec_rows=len(prec), prec_rows=p_prec if prec else 0, prec_of_row=p_prec_of if prec else 0)
+                             n_prec_rows=len(prec), prec_rows=p_prec if prec else 0, prec_of_row=p_prec_of if prec else 0,
+                             resid_in=_lib.ptr(resid_in), resid_out=_lib.ptr(resid))
             rc = self.lib.mmd_decoder_step(self.ctx, ctypes.byref(self.w), ctypes.byref(self.kv), ctypes.byref(step), self._ws.data_ptr(),
                                            self._ws.numel(), _lib.stream_ptr())
             _lib.check(rc, "mmd_decoder_step")
@@ -554,5 +614,7 @@ class DecoderEngine:
         for it, st, past, rows, chunk, n_q, new_len in plan:
             st.length = new_len
             views.append(CacheView(st, new_len))
-        self._last_meta = (meta_d, frame_tokens)  # keep alive until the kernels have consumed them
+        self._last_meta = (meta_d, frame_tokens, resid_in)  # keep alive until the kernels have consumed them
+        if resid_out:
+            return {"resid": resid, "views": views}
         return {"head_logits": head_logits[:n_s], "scores": scores[:n_s], "lm_logits": lm_logits, "views": views}

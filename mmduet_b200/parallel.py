@@ -172,6 +172,74 @@ class PeerStoreEncoder:
     wait_all = staticmethod(FrameParallelEncoder.wait_all)
 
 
+def layer_ranges(n_layers, n_stages):
+    """Contiguous decoder-layer ranges of a layer pipeline, sizes differing by at most one (earlier stages take the extra)."""
+    base, extra = divmod(n_layers, n_stages)
+    out, l0 = [], 0
+    for s in range(n_stages):
+        n = base + (1 if s < extra else 0)
+        out.append((l0, l0 + n))
+        l0 += n
+    return out
+
+
+class LayerPipeline:
+    """One video's decoder split BY LAYERS over `stage_ranks` (ascending pipeline order, one stage per GPU).
+
+    A video's decoder stream is sequential in time — pass p+1 attends over pass p's keys — but only layer by layer: layer l of
+    pass p+1 needs layer l's K/V of pass p, not pass p's final output (no token of the video depends on a generated one while
+    frames are being scored).  So stage s runs its layers for pass p while stage s-1 already runs pass p+1: the owner's serial
+    term is divided by the number of stages, at the price of one point-to-point hand-over of the fp32 residual
+    stream [rows, hidden] per pass and stage boundary (28 MB for a 40-frame pass: ~40 us over NVLink).
+
+    run(passes, stage_fn): `passes` is the same list on every stage rank (each entry a dict with 'rows' = tokens of the pass);
+    stage_fn(p, desc, resid_in) returns the residual stream to hand on (every stage but the last; resid_in is None on the
+    first) or the stage's result (last stage).  Returns the list of results on the last stage, None elsewhere."""
+
+    def __init__(self, stage_ranks, hidden, device, dtype=torch.float32, group=None):
+        self.stage_ranks = list(stage_ranks)
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.hidden, self.device, self.dtype = hidden, device, dtype
+        self.index = self.stage_ranks.index(self.rank) if self.rank in self.stage_ranks else None
+
+    @property
+    def n_stages(self):
+        return len(self.stage_ranks)
+
+    @property
+    def is_first(self):
+        return self.index == 0
+
+    @property
+    def is_last(self):
+        return self.index == len(self.stage_ranks) - 1
+
+    def run(self, passes, stage_fn):
+        if self.index is None:
+            return None
+        prev = self.stage_ranks[self.index - 1] if not self.is_first else None
+        nxt = self.stage_ranks[self.index + 1] if not self.is_last else None
+        results, inflight = [], []
+        for p, desc in enumerate(passes):
+            rin = None
+            if prev is not None:
+                rin = torch.empty(desc["rows"], self.hidden, dtype=self.dtype, device=self.device)
+                dist.irecv(rin, src=prev, group=self.group).wait()      # (NCCL: the current stream waits, not the host)
+            out = stage_fn(p, desc, rin)
+            if nxt is not None:
+                # asynchronous: this stage goes on to pass p + 1 while the hand-over of pass p is in flight; the tensors stay
+                # referenced until the send has been waited for
+                inflight.append((dist.isend(out, dst=nxt, group=self.group), out))
+                if len(inflight) > 2:
+                    inflight.pop(0)[0].wait()
+            else:
+                results.append(out)
+        for req, _ in inflight:
+            req.wait()
+        return results if self.is_last else None
+
+
 def gather_results(obj, dst=0, group=None):
     """Per-rank Python results (score traces of the rank's videos) -> list on `dst` (a few KB; config 4's only exchange)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)

@@ -190,3 +190,49 @@ def test_loop_on_a_one_frame_and_an_empty_video():
     infer.input_video_stream(frames[:0])
     assert infer.inference() == [] and infer.debug_data_list == []
     assert infer.session.context_len == 0
+
+
+@pytest.mark.parametrize("n_stages", [2, 3])
+def test_layer_pipeline_stages_equal_the_whole_engine(small, n_stages):
+    """The decoder split by layers into stages (parallel.LayerPipeline runs one per GPU; here chained on one GPU through the
+    same step(resid_in=, resid_out=) interface): scores BIT-IDENTICAL to the whole engine over a multi-pass stream with a
+    prefix, a big pass (appended precise rows), single-frame passes (every row hi+lo) and a rollback; lm logits too."""
+    arch, wd, vis, dec, dev = small
+    from mmduet_b200.parallel import layer_ranges
+    fe = _frames(arch, 8, 33, dev)
+    stages = [dec.stage(r) for r in layer_ranges(arch.layers, n_stages)]
+    assert stages[0].first_stage and stages[-1].last_stage and sum(b - a for a, b in layer_ranges(arch.layers, n_stages)) == arch.layers
+    passes = [(PREFIX, fe[:5 * 49], [32 + 49 * (j + 1) - 1 for j in range(5)]),      # 277 tokens: appended precise rows
+              ([], fe[5 * 49:6 * 49], [48]), ([], fe[6 * 49:7 * 49], [48]),            # single-frame passes
+              ([11, 12, 13], None, [2])]                                               # a text turn (lm logits)
+    whole, L = dec.new_stream(), 0
+    streams, Ls = [s.new_stream() for s in stages], 0
+    for ids, fr, rows in passes:
+        n_rows = len(ids) + (0 if fr is None else fr.shape[0])
+        ref = dec.step([dict(storage=whole, past=L, ids=ids, frames=fr, score_rows=rows)], score="frame_ends", lm="last")
+        L = ref["views"][0].length
+        resid = None
+        for k, (stg, sst) in enumerate(zip(stages, streams)):
+            item = dict(storage=sst, past=Ls, ids=ids, frames=fr, score_rows=rows) if k == 0 else \
+                dict(storage=sst, past=Ls, n_rows=n_rows, score_rows=rows)
+            out = stg.step([item], score="frame_ends", lm="last", resid_in=resid, resid_out=k + 1 < n_stages)
+            resid = out.get("resid")
+        Ls = out["views"][0].length
+        assert Ls == L
+        assert torch.equal(out["scores"], ref["scores"]) and torch.equal(out["head_logits"], ref["head_logits"])
+        assert torch.equal(out["lm_logits"], ref["lm_logits"])
+    # rollback on every stage: re-append the last single-frame pass on top of the view before it
+    ref = dec.step([dict(storage=whole, past=32 + 6 * 49, ids=[], frames=fe[7 * 49:], score_rows=[48])], score="frame_ends")
+    resid = None
+    for k, (stg, sst) in enumerate(zip(stages, streams)):
+        item = dict(storage=sst, past=32 + 6 * 49, ids=[], frames=fe[7 * 49:], score_rows=[48]) if k == 0 else \
+            dict(storage=sst, past=32 + 6 * 49, n_rows=49, score_rows=[48])
+        out = stg.step([item], score="frame_ends", resid_in=resid, resid_out=k + 1 < n_stages)
+        resid = out.get("resid")
+    assert torch.equal(out["scores"], ref["scores"])
+    from mmduet_b200 import _lib
+    with pytest.raises(_lib.MmdError, match="resid_in"):
+        stages[1].step([dict(storage=streams[1], past=0, n_rows=4)])          # a later stage needs the residual stream
+    whole.release()
+    for sst in streams:
+        sst.release()

@@ -170,3 +170,67 @@ def test_peer_store_encoder_world2_control_flow(n_frames, owner, owner_encodes):
     for p_ in procs:
         p_.join(timeout=60)
     assert res == {0: True, 1: True}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# LayerPipeline: hand-over schedule of a 3-stage decoder pipeline over gloo (the stages' arithmetic is a stand-in)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_layer_ranges():
+    from mmduet_b200.parallel import layer_ranges
+    assert layer_ranges(28, 4) == [(0, 7), (7, 14), (14, 21), (21, 28)]
+    assert layer_ranges(28, 3) == [(0, 10), (10, 19), (19, 28)]
+    assert layer_ranges(28, 1) == [(0, 28)]
+    for n in (1, 2, 5, 28):
+        r = layer_ranges(28, n)
+        assert r[0][0] == 0 and r[-1][1] == 28 and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+
+
+def _pipe_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mmduet_b200.parallel import LayerPipeline
+        stage_ranks = [0, 2, 1]                                        # pipeline order need not be rank order; rank 3 is no stage
+        pipe = LayerPipeline(stage_ranks, hidden=4, device="cpu", dtype=torch.float32)
+        passes = [{"rows": 3 + (p % 2), "p": p} for p in range(7)]
+        log = []
+
+        def stage_fn(p, desc, rin):
+            log.append(p)
+            if pipe.is_first:
+                x = torch.full((desc["rows"], 4), float(p))
+            else:
+                assert rin.shape == (desc["rows"], 4)
+                x = rin
+            y = x * 2 + pipe.index                                     # stage k: y = 2x + k
+            return y if not pipe.is_last else y.sum().item()
+
+        res = pipe.run(passes, stage_fn)
+        ok = True
+        if rank == 3:
+            ok = res is None and log == []
+        else:
+            ok = log == list(range(7))
+            if pipe.is_last:
+                # ((2p + 0) * 2 + 1) * 2 + 2 = 8p + 4 per element
+                want = [(8 * p + 4) * 4 * (3 + p % 2) for p in range(7)]
+                ok = ok and res == want
+            else:
+                ok = ok and res is None
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_layer_pipeline_hand_over_gloo():
+    world = 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pipe_worker, args=(r, world, port, q)) for r in range(world)]
+    for p_ in procs:
+        p_.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p_ in procs:
+        p_.join(timeout=60)
+    assert res == {0: True, 1: True, 2: True, 3: True}
