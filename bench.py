@@ -556,24 +556,38 @@ def configs2_frame_parallel(vis, dec, cfg, dev, world, rank, chunk):
     Timed on the device from before the first encode launch to the last score, max over ranks."""
     import torch
     import torch.distributed as dist
-    from mmduet_b200.parallel import FrameParallelEncoder, PeerStoreEncoder, encoder_frame_range
+    from mmduet_b200.parallel import (FrameParallelEncoder, LayerPipeline, PeerStoreEncoder, encoder_batches, encoder_frame_range,
+                                      layer_ranges)
     from mmduet_b200.random_init import synthetic_frames
     n, tpf, H = CONFIGS2_FRAMES, vis.tokens_per_frame, cfg.hidden
     k = max(chunk, 1)
     frames = synthetic_frames(n, seed=7, device=dev)              # the same video on every rank; each encodes its slice
-    # the decoder-owning rank does not encode when there are other ranks: its sequential decoder stream is the serial term,
-    # so it starts on the first batch as soon as that lands while ranks 1..N-1 keep encoding
-    encoders = list(range(1, world)) if world > 1 else [0]
+    # The video's decoder stream is the serial term.  Ranks 0..S-1 hold it as a LAYER PIPELINE (stage s runs its layers of pass p
+    # while stage s-1 runs pass p+1; parallel.LayerPipeline), ranks S..N-1 encode; the decoder ranks do not encode when there
+    # are other ranks.  One GPU's decode of this video costs ~1.2x its encode, hence S ~ 0.55 N.
+    S = 1 if world <= 2 else min(world - 1, max(1, int(round(0.55 * world))))
+    S = int(os.environ.get("MMD_CONFIGS2_STAGES", S))
+    encoders = list(range(S, world)) if world > 1 else [0]
     lo, hi = encoder_frame_range(n, encoders, rank)
+    pipe = LayerPipeline(list(range(S)), H, dev) if S > 1 else None
+    stage_ranges = layer_ranges(cfg.layers, S)
+    stage_eng = dec.stage(stage_ranges[rank], max_tokens=49 * k + 64) if S > 1 and rank < S else None
+    passes = [dict(rows=min(k, n - f0) * tpf, f0=f0, nf=min(k, n - f0)) for f0 in range(0, n, k)]
     exchange = "none (1 GPU)"
     enc = None
     if world > 1:
         try:
+            # batches of 40 frames dealt round-robin to the encoder ranks: the video becomes available front to back at the
+            # encoders' aggregate rate, which is the order the decoder consumes it in
             enc = PeerStoreEncoder(lambda fr, dst: vis.visual_embed(fr, normalize=True, out=dst), tpf, H, max_frames=n, device=dev,
-                                   owner=0, batch=40, encoders=encoders)
-            exchange = "peer stores into the owner's HBM (symmetric memory over NVLink), per-batch signals, no collective"
+                                   owner=0, batch=40, encoders=encoders, assignment="round_robin")
+            mine = encoder_batches(n, encoders, rank, 40, "round_robin")
+            local_frames = torch.cat([frames[b0:b1] for b0, b1 in mine]) if mine else frames[:0]
+            exchange = ("peer stores into the owner's HBM (symmetric memory over NVLink), 40-frame batches dealt round-robin to the "
+                        "encoder ranks, per-batch signals, no collective")
         except Exception as e:  # noqa: BLE001
             enc = FrameParallelEncoder(lambda fr: vis.visual_embed(fr, normalize=True), tpf, H, device=dev, owner=0, batch=40, encoders=encoders)
+            local_frames = frames[lo:hi]
             exchange = f"NCCL isend/irecv per 40-frame batch (symmetric memory unavailable: {type(e).__name__})"
     dec._ensure_ws(49 * k, 1)
     if dec.max_context < n * tpf:
@@ -592,15 +606,43 @@ def configs2_frame_parallel(vis, dec, cfg, dev, world, rank, chunk):
         st.release()
         return torch.cat(sc, 0), L
 
+    def pipelined_decode(tokens, ready):
+        """this rank's stage of the layer pipeline over all passes; the scores end up on rank 0 (the video's owner)"""
+        st, state = stage_eng.new_stream(), {"L": 0}
+
+        def stage_fn(p, d, rin):
+            f0, nf = d["f0"], d["nf"]
+            rows = [tpf * (j + 1) - 1 for j in range(nf)]
+            if pipe.is_first:
+                if ready is not None:
+                    ready[f0 + nf - 1]()
+                item = dict(storage=st, past=state["L"], ids=[], frames=tokens[f0 * tpf:(f0 + nf) * tpf], score_rows=rows)
+            else:
+                item = dict(storage=st, past=state["L"], n_rows=nf * tpf, score_rows=rows)
+            o = stage_eng.step([item], score="frame_ends", resid_in=rin, resid_out=not pipe.is_last)
+            state["L"] = o["views"][0].length
+            return o["scores"] if pipe.is_last else o["resid"]
+        res = pipe.run(passes, stage_fn)
+        st.release()
+        sc = None
+        if pipe.is_last:
+            sc = torch.cat(res, 0)
+            dist.send(sc, dst=0)
+        if rank == 0:
+            sc = torch.empty(n, 2, dtype=torch.float32, device=dev)
+            dist.recv(sc, src=S - 1)
+        return sc, state["L"]
+
     def one_pass():
         if world == 1:
             tokens = vis.visual_embed(frames, normalize=True)
             return owner_decode(tokens, None) + (tokens,)
-        tokens, ready = enc.encode(n, frames[lo:hi])
-        if rank != 0:
+        tokens, ready = enc.encode(n, local_frames)
+        if rank >= S:
             return None, None, None
-        sc, L = owner_decode(tokens, ready)
-        FrameParallelEncoder.wait_all(ready)
+        sc, L = pipelined_decode(tokens, ready) if S > 1 else owner_decode(tokens, ready)
+        if rank == 0:
+            FrameParallelEncoder.wait_all(ready)
         return sc, L, tokens
 
     def barrier():
@@ -627,7 +669,7 @@ def configs2_frame_parallel(vis, dec, cfg, dev, world, rank, chunk):
     if world == 1:
         tokens = vis.visual_embed(frames, normalize=True)
     else:
-        tokens, ready = enc.encode(n, frames[lo:hi])
+        tokens, ready = enc.encode(n, local_frames)
         FrameParallelEncoder.wait_all(ready)
     e_enc.record()
     barrier()
@@ -655,12 +697,18 @@ def configs2_frame_parallel(vis, dec, cfg, dev, world, rank, chunk):
                            "exchanged to rank 0, which decodes the whole stream (final context 29.4k tokens) and applies the running-sum rule "
                            "(threshold 2, informative head); responses not generated (remove_assistant_turns: context-neutral)",
                "frames": n, "n_ranks": world, "n_encoder_ranks": len(encoders), "decoder_rank_also_encodes": world == 1, "exchange": exchange,
+               "n_decoder_stages": S, "decoder_layers_per_stage": [b_ - a_ for a_, b_ in stage_ranges],
+               "decoder_exchange": "none (one decoder rank)" if S == 1 else
+                                   f"layer pipeline: fp32 residual stream [{k * tpf}, {H}] handed from stage to stage per pass (NCCL isend/irecv, "
+                                   f"{k * tpf * H * 4 / 1e6:.0f} MB), KV pages of a layer live on its stage only",
                "decoder_frames_per_pass": k,
                "ms": ms, "frames_per_s": n / (ms / 1e3), "encode_exchange_only_ms": enc_ms, "owner_decode_only_ms": dec_ms,
                "final_context_tokens": int(L), "responses": len(resp), "first_response_frames": resp[:8],
                "tokens_bit_identical_to_single_rank_encode": ident,
                "scores_equal_overlapped_vs_separate": bool(torch.equal(sc, sc2)),
-               "limiter": "the owner's decoder stream is sequential (KV dependency): Amdahl's serial term is owner_decode_only_ms"}
+               "limiter": "the owner's decoder stream is sequential (KV dependency): Amdahl's serial term is owner_decode_only_ms" if S == 1 else
+                          f"one GPU's decode of the video (owner_decode_only_ms) is divided over {S} layer stages (+ {S - 1} passes of pipeline "
+                          f"fill); {len(encoders)} encoder ranks run beside it"}
     del frames
     return res
 

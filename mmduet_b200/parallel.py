@@ -31,6 +31,20 @@ def encoder_frame_range(n_frames, encoders, rank):
     return frame_range(n_frames, len(encoders), encoders.index(rank))
 
 
+def encoder_batches(n_frames, encoders, rank, batch, assignment="contiguous"):
+    """[(b0, b1)] frame batches `rank` encodes, in its encoding order.  "contiguous": one frame range per encoder;
+    "round_robin": batch b of the video goes to encoder b mod E, so the frames become available IN ORDER at the encoders'
+    aggregate rate — what a decoder that consumes the video front to back needs (with contiguous ranges it is fed by the first
+    encoder alone until that one's range is finished)."""
+    if rank not in encoders:
+        return []
+    if assignment == "round_robin":
+        every = [(b0, min(b0 + batch, n_frames)) for b0 in range(0, n_frames, batch)]
+        return every[encoders.index(rank)::len(encoders)]
+    lo, hi = encoder_frame_range(n_frames, encoders, rank)
+    return [(b0, min(b0 + batch, hi)) for b0 in range(lo, hi, batch)]
+
+
 def videos_for_rank(n_videos, world, rank):
     return list(range(rank, n_videos, world))
 
@@ -104,7 +118,7 @@ class PeerStoreEncoder:
     embed_into(frames[b0:b1], dst[(b1-b0)*tokens_per_frame, hidden]) must write the tokens of those frames into dst."""
 
     def __init__(self, embed_into, tokens_per_frame, hidden, max_frames, device, owner=0, batch=32, group=None, symm=None,
-                 dtype=torch.bfloat16, encoders=None):
+                 dtype=torch.bfloat16, encoders=None, assignment="contiguous"):
         if symm is None:                   # injectable: the CPU tests drive the same control flow through a gloo-backed stand-in
             import torch.distributed._symmetric_memory as symm
         self.embed_into, self.tpf, self.hidden, self.device = embed_into, tokens_per_frame, hidden, device
@@ -112,6 +126,7 @@ class PeerStoreEncoder:
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         self.encoders = sorted(encoders) if encoders is not None else list(range(self.world))   # ranks that encode
+        self.assignment = assignment       # see encoder_batches
         self.buf = symm.empty(max_frames * tokens_per_frame, hidden, dtype=dtype, device=device)
         self.hdl = symm.rendezvous(self.buf, self.group)
         # the owner's buffer as seen from this rank (a peer mapping unless this rank is the owner)
@@ -129,8 +144,8 @@ class PeerStoreEncoder:
         """Returns (tokens, ready) on the owner (tokens is a view of the symmetric buffer, valid until the next encode;
         ready[i]() makes the current stream wait until frame i has landed) and (None, None) elsewhere."""
         assert n_frames <= self.max_frames
-        lo, hi = encoder_frame_range(n_frames, self.encoders, self.rank)
-        assert len(local_frames) == hi - lo, (len(local_frames), lo, hi)
+        mine = encoder_batches(n_frames, self.encoders, self.rank, self.batch, self.assignment)
+        assert len(local_frames) == sum(b1 - b0 for b0, b1 in mine), (len(local_frames), mine)   # this rank's batches, concatenated
         # Signals of the previous video that the owner never consumed (it stopped early, or never called its ready[i]) would
         # satisfy THIS video's waits before the data has landed, and a producer's put_signal blocks on a channel that is
         # still set: consume them first.  Every producer always posts all of its signals, so these waits terminate.
@@ -140,9 +155,10 @@ class PeerStoreEncoder:
         self._pending = {}
         # nobody may overwrite the owner's buffer while it is still decoding the previous video
         self.hdl.barrier(channel=0)
-        for n, b0 in enumerate(range(lo, hi, self.batch)):
-            b1 = min(b0 + self.batch, hi)
-            self.embed_into(local_frames[b0 - lo:b1 - lo], self.dst[b0 * self.tpf:b1 * self.tpf])
+        off = 0
+        for n, (b0, b1) in enumerate(mine):
+            self.embed_into(local_frames[off:off + b1 - b0], self.dst[b0 * self.tpf:b1 * self.tpf])
+            off += b1 - b0
             if self.rank != self.owner:
                 # stream-ordered after the kernel that stored the batch.  One channel per batch: a signal is a binary
                 # semaphore, and reusing one channel would block this rank's stream until the owner had consumed the
@@ -153,8 +169,8 @@ class PeerStoreEncoder:
         pending = {}                                           # src rank -> list of its batches, in sending order
         for src in self.encoders:
             if src != self.owner:
-                s_lo, s_hi = encoder_frame_range(n_frames, self.encoders, src)
-                pending[src] = [(b0, min(b0 + self.batch, s_hi), self._channel(n)) for n, b0 in enumerate(range(s_lo, s_hi, self.batch))]
+                pending[src] = [(b0, b1, self._channel(n))
+                                for n, (b0, b1) in enumerate(encoder_batches(n_frames, self.encoders, src, self.batch, self.assignment))]
         self._pending = pending
 
         def ready_fn(i):

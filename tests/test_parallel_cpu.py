@@ -122,6 +122,16 @@ class _GlooSymm:
         return _GlooSymm.Handle(tensor, group)
 
 
+def test_encoder_batches_assignments():
+    from mmduet_b200.parallel import encoder_batches
+    enc = [1, 2, 3]
+    rr = [encoder_batches(10, enc, r, 2, "round_robin") for r in range(4)]
+    assert rr[0] == [] and rr[1] == [(0, 2), (6, 8)] and rr[2] == [(2, 4), (8, 10)] and rr[3] == [(4, 6)]
+    cont = [encoder_batches(10, enc, r, 2) for r in range(4)]
+    assert cont[0] == [] and sorted(b for c in cont for b in c) == sorted(set(b for c in cont for b in c))
+    assert sum(b1 - b0 for c in cont for b0, b1 in c) == 10 and sum(b1 - b0 for c in rr for b0, b1 in c) == 10
+
+
 def _peer_worker(rank, world, port, n_frames, owner, q, owner_encodes=True):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -234,3 +244,46 @@ def test_layer_pipeline_hand_over_gloo():
     for p_ in procs:
         p_.join(timeout=60)
     assert res == {0: True, 1: True, 2: True, 3: True}
+
+
+def _peer_rr_worker(rank, world, port, n_frames, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mmduet_b200.parallel import encoder_batches
+        tpf, hidden, owner, encoders = 3, 4, 0, [1, 2]
+        mine = encoder_batches(n_frames, encoders, rank, 2, "round_robin")
+        frames = torch.tensor([float(f) for b0, b1 in mine for f in range(b0, b1)])
+
+        def embed_into(fr, dst):
+            dst.copy_((fr[:, None] * 10 + torch.arange(tpf)[None, :]).reshape(-1, 1).expand(-1, hidden))
+
+        enc = PeerStoreEncoder(embed_into, tpf, hidden, max_frames=n_frames, device="cpu", owner=owner, batch=2, symm=_GlooSymm,
+                               dtype=torch.float32, encoders=encoders, assignment="round_robin")
+        ok = True
+        for _ in range(2):
+            out, ready = enc.encode(n_frames, frames)
+            if rank == owner:
+                want = (torch.arange(n_frames)[:, None] * 10 + torch.arange(tpf)[None, :]).reshape(-1, 1).expand(-1, hidden).float()
+                for i in range(n_frames):                              # front to back, as a decoder consumes the video
+                    ready[i]()
+                    ok = ok and torch.equal(out[i * tpf:(i + 1) * tpf], want[i * tpf:(i + 1) * tpf])
+            else:
+                ok = ok and out is None
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_store_round_robin_batches_world3():
+    """Owner 0 only receives; encoders 1 and 2 take the 2-frame batches alternately; the owner reads the video front to back."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_rr_worker, args=(r, 3, port, 11, q)) for r in range(3)]
+    for p_ in procs:
+        p_.start()
+    res = dict(q.get(timeout=120) for _ in range(3))
+    for p_ in procs:
+        p_.join(timeout=60)
+    assert res == {0: True, 1: True, 2: True}
