@@ -39,8 +39,17 @@ def encoder_batches(n_frames, encoders, rank, batch, assignment="contiguous"):
     if rank not in encoders:
         return []
     if assignment == "round_robin":
-        every = [(b0, min(b0 + batch, n_frames)) for b0 in range(0, n_frames, batch)]
+        # `batch` may be a list of batch sizes (a schedule, e.g. small batches first so that the first frames land early);
+        # the last size repeats until the video is covered
+        sizes = list(batch) if isinstance(batch, (list, tuple)) else [batch]
+        every, b0, i = [], 0, 0
+        while b0 < n_frames:
+            b1 = min(b0 + sizes[min(i, len(sizes) - 1)], n_frames)
+            every.append((b0, b1))
+            b0, i = b1, i + 1
         return every[encoders.index(rank)::len(encoders)]
+    if isinstance(batch, (list, tuple)):
+        raise ValueError("a batch-size schedule needs assignment='round_robin'")
     lo, hi = encoder_frame_range(n_frames, encoders, rank)
     return [(b0, min(b0 + batch, hi)) for b0 in range(lo, hi, batch)]
 

@@ -127,6 +127,8 @@ def test_encoder_batches_assignments():
     enc = [1, 2, 3]
     rr = [encoder_batches(10, enc, r, 2, "round_robin") for r in range(4)]
     assert rr[0] == [] and rr[1] == [(0, 2), (6, 8)] and rr[2] == [(2, 4), (8, 10)] and rr[3] == [(4, 6)]
+    sched = [encoder_batches(23, [2, 3], r, [2, 2, 4, 8], "round_robin") for r in range(4)]   # sizes 2 2 4 8 then 8s (7 left)
+    assert sched[0] == sched[1] == [] and sched[2] == [(0, 2), (4, 8), (16, 23)] and sched[3] == [(2, 4), (8, 16)]
     cont = [encoder_batches(10, enc, r, 2) for r in range(4)]
     assert cont[0] == [] and sorted(b for c in cont for b in c) == sorted(set(b for c in cont for b in c))
     assert sum(b1 - b0 for c in cont for b0, b1 in c) == 10 and sum(b1 - b0 for c in rr for b0, b1 in c) == 10
