@@ -63,17 +63,6 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
-// smem descriptor, MN-major operand (V as [key][d], d contiguous), 128-B swizzle: LBO = distance between the 64-element
-// blocks along N (d), SBO = distance between 8-row groups along K (keys) = 1024 B.
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
 // A format: 1 = bf16, 0 = f16 (the P operand when it is produced by packed half-precision exponentials); B = V is bf16
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_mn_b(uint32_t M, uint32_t N, uint32_t a_bf16 = 1u) {
   return (1u << 4) | (a_bf16 << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
@@ -86,6 +75,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_mn_b(uint32_t M, uint32_t
 #ifndef MMD_EXP_F16X2
 #define MMD_EXP_F16X2 0
 #endif
+#if MMD_EXP_F16X2
 __device__ __forceinline__ uint32_t ex2_f16x2(float lo, float hi) {
   uint32_t h, r;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(hi), "f"(lo));
@@ -102,6 +92,7 @@ __device__ __forceinline__ float h2_sum_f32(uint32_t h) {
   asm("{ .reg .b16 l, u; mov.b32 {l, u}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, u; }" : "=f"(lo), "=f"(hi) : "r"(h));
   return lo + hi;
 }
+#endif
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
