@@ -7,13 +7,23 @@ lib, ctx = _lib.load(), _lib.context(0)
 s = lambda: torch.cuda.current_stream().cuda_stream
 torch.manual_seed(0)
 
+from bench import ClockSampler
+LAST_CLOCKS = {}
+
 def timeit(fn, iters=20):
+    """us per call; the timed loop runs >= 0.5 s so that nvidia-smi (100 ms ticks) samples the clocks under this load"""
     for _ in range(3): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters): fn()
     e1.record(); torch.cuda.synchronize()
+    iters = max(iters, int(500.0 / max(e0.elapsed_time(e1) / iters, 1e-3)))
+    clk = ClockSampler(0); clk.start()
+    e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    LAST_CLOCKS.clear(); LAST_CLOCKS.update(clk.stop())
     return e0.elapsed_time(e1) / iters * 1e3
 
 res = []
@@ -24,7 +34,7 @@ flops = 4.0 * T * H * S * S * dh
 for impl in (0, 1):
     lib.mmd_set_attention_impl(impl)
     us = timeit(lambda: lib.mmd_vit_attention(qkv.data_ptr(), out.data_ptr(), T, S, H, dh, 1, s()))
-    res.append({"kernel": "vit_attention", "impl": impl, "us": us, "tflops": flops / us / 1e6}); print(res[-1], flush=True)
+    res.append({"kernel": "vit_attention", "impl": impl, "us": us, "tflops": flops / us / 1e6, "clocks": dict(LAST_CLOCKS)}); print(res[-1], flush=True)
 
 Hq, Hkv, dh, PAGE = 28, 4, 128, 64
 for n_q, L in ((49, 3000), (49, 30000), (392, 3000), (392, 6000), (1, 6000)):
@@ -42,6 +52,6 @@ for n_q, L in ((49, 3000), (49, 30000), (392, 3000), (392, 6000), (1, 6000)):
         us = timeit(lambda: lib.mmd_kv_attention(ctx, q.data_ptr(), pool.data_ptr(), desc.data_ptr(), tab.data_ptr(), 1, n_q, n_q, L,
                                                  o_part.data_ptr(), ml.data_ptr(), outd.data_ptr(), Hq, Hkv, dh, ns, s()))
         res.append({"kernel": "kv_attention", "n_q": n_q, "L": L, "impl": impl, "splits": ns, "us": us, "tflops": fl / us / 1e6,
-                    "kv_GBs": L * Hkv * dh * 2 * 2 / us / 1e3}); print(res[-1], flush=True)
+                    "kv_GBs": L * Hkv * dh * 2 * 2 / us / 1e3, "clocks": dict(LAST_CLOCKS)}); print(res[-1], flush=True)
 lib.mmd_set_attention_impl(2)
 json.dump(res, open("gpurun_out/bench_attention.json", "w"), indent=1)

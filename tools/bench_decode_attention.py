@@ -11,6 +11,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mmduet_b200 import _lib  # noqa: E402
+from bench import ClockSampler  # noqa: E402
 
 dev = torch.device("cuda:0")
 lib, ctx = _lib.load(), _lib.context(0)
@@ -49,17 +50,24 @@ for L in (5912, 29400, 58800):
         graph.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10
+        e0.record()
+        graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        reps = max(10, int(600.0 / max(e0.elapsed_time(e1), 1e-3)))       # >= 0.6 s under load: the clock sampler ticks every 100 ms
+        clk = ClockSampler(0)
+        clk.start()
         e0.record()
         for _ in range(reps):
             graph.replay()
         e1.record()
         torch.cuda.synchronize()
+        clocks = clk.stop()
         us = e0.elapsed_time(e1) * 1e3 / (reps * LAYERS)
         nbytes = 2 * L * Hkv * dh * 2 + 2 * n_q * Hq * dh * 2
         flops = 4.0 * n_q * L * Hq * dh
         r = {"context": L, "n_q": n_q, "splits": ns, "us_per_layer": round(us, 2), "GBps": round(nbytes / us / 1e3, 1), "hbm_frac": round(nbytes / us / 1e3 / peak, 3),
-             "TFLOPs": round(flops / us / 1e6, 1), "ms_per_step_28_layers": round(us * LAYERS / 1e3, 3)}
+             "TFLOPs": round(flops / us / 1e6, 1), "ms_per_step_28_layers": round(us * LAYERS / 1e3, 3), "clocks": clocks}
         res.append(r)
         print(r, flush=True)
     del pools
