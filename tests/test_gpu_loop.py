@@ -412,11 +412,14 @@ def test_many_videos_leave_no_pages_or_memory_behind():
             if v % 2:
                 infer.input_query_stream([{"role": "user", "time": 1.0, "content": "what is happening"}])
             turns = infer.inference()
+            infer.last_turns = turns
             n_resp += sum(t["role"] == "assistant" for t in turns)
             assert len(infer.debug_data_list) == len(frames)
             torch.cuda.synchronize()
+            del turns
+            torch.empty(1, device="cuda:0")                 # an allocation makes the caching allocator retire completed frees
             mem.append(torch.cuda.memory_allocated())
-            results.append((turns, [d["informative_score"] for d in infer.debug_data_list]))
+            results.append(([(t["role"], t["time"], t["content"]) for t in infer.last_turns], [d["informative_score"] for d in infer.debug_data_list]))
     infer.reset()
     assert len(dec._free) == n_free
     assert n_resp > 0                                     # the soak did generate and roll back
