@@ -565,13 +565,26 @@ def configs2_frame_parallel(vis, dec, cfg, dev, world, rank, chunk):
     # The video's decoder stream is the serial term.  Ranks 0..S-1 hold it as a LAYER PIPELINE (stage s runs its layers of pass p
     # while stage s-1 runs pass p+1; parallel.LayerPipeline), ranks S..N-1 encode; the decoder ranks do not encode when there
     # are other ranks.  One GPU's decode of this video costs ~1.2x its encode, hence S ~ 0.55 N.
-    S = 1 if world <= 2 else min(world - 1, max(1, int(round(0.55 * world))))
+    S = 1 if world < 2 else min(world - 1, max(1, int(round(0.55 * world))))
+    # Two GPUs: both are decoder stages AND both encode (on a side stream, batches dealt round-robin), so each carries half of
+    # the video's encode and half of its decode instead of one GPU idling behind the other.
+    both = world == 2 and os.environ.get("MMD_CONFIGS2_N2_SPLIT", "1") != "0"
+    if both:
+        S = 2
     S = int(os.environ.get("MMD_CONFIGS2_STAGES", S))
-    encoders = list(range(S, world)) if world > 1 else [0]
+    encoders = ([0, 1] if both else list(range(S, world))) if world > 1 else [0]
+    enc_stream = torch.cuda.Stream(device=dev) if both else None
     lo, hi = encoder_frame_range(n, encoders, rank)
     pipe = LayerPipeline(list(range(S)), H, dev) if S > 1 else None
     stage_ranges = layer_ranges(cfg.layers, S)
     stage_eng = dec.stage(stage_ranges[rank], max_tokens=49 * k + 64) if S > 1 and rank < S else None
+
+    def encode_video():
+        if enc_stream is None:
+            return enc.encode(n, local_frames)
+        enc_stream.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(enc_stream):          # the encode launches run beside this rank's decoder stage
+            return enc.encode(n, local_frames)
     passes = [dict(rows=min(k, n - f0) * tpf, f0=f0, nf=min(k, n - f0)) for f0 in range(0, n, k)]
     exchange = "none (1 GPU)"
     enc = None
@@ -637,12 +650,14 @@ def configs2_frame_parallel(vis, dec, cfg, dev, world, rank, chunk):
         if world == 1:
             tokens = vis.visual_embed(frames, normalize=True)
             return owner_decode(tokens, None) + (tokens,)
-        tokens, ready = enc.encode(n, local_frames)
+        tokens, ready = encode_video()
         if rank >= S:
             return None, None, None
         sc, L = pipelined_decode(tokens, ready) if S > 1 else owner_decode(tokens, ready)
         if rank == 0:
             FrameParallelEncoder.wait_all(ready)
+        if enc_stream is not None:
+            torch.cuda.current_stream(dev).wait_stream(enc_stream)
         return sc, L, tokens
 
     def barrier():
@@ -669,7 +684,7 @@ def configs2_frame_parallel(vis, dec, cfg, dev, world, rank, chunk):
     if world == 1:
         tokens = vis.visual_embed(frames, normalize=True)
     else:
-        tokens, ready = enc.encode(n, local_frames)
+        tokens, ready = encode_video()
         FrameParallelEncoder.wait_all(ready)
     e_enc.record()
     barrier()
@@ -696,7 +711,8 @@ def configs2_frame_parallel(vis, dec, cfg, dev, world, rank, chunk):
         res = {"workload": "BASELINE.json configs[2]: one 600-frame video (5 min @ 2 fps), encoder sharded over the ranks, frame tokens "
                            "exchanged to rank 0, which decodes the whole stream (final context 29.4k tokens) and applies the running-sum rule "
                            "(threshold 2, informative head); responses not generated (remove_assistant_turns: context-neutral)",
-               "frames": n, "n_ranks": world, "n_encoder_ranks": len(encoders), "decoder_rank_also_encodes": world == 1, "exchange": exchange,
+               "frames": n, "n_ranks": world, "n_encoder_ranks": len(encoders), "decoder_rank_also_encodes": world == 1 or both,
+               "exchange": exchange,
                "n_decoder_stages": S, "decoder_layers_per_stage": [b_ - a_ for a_, b_ in stage_ranges],
                "decoder_exchange": "none (one decoder rank)" if S == 1 else
                                    f"layer pipeline: fp32 residual stream [{k * tpf}, {H}] handed from stage to stage per pass (NCCL isend/irecv, "

@@ -165,9 +165,14 @@ class PeerStoreEncoder:
         # nobody may overwrite the owner's buffer while it is still decoding the previous video
         self.hdl.barrier(channel=0)
         off = 0
+        own_events = []                     # owner that also encodes: one event per own batch (it may encode on a side stream)
         for n, (b0, b1) in enumerate(mine):
             self.embed_into(local_frames[off:off + b1 - b0], self.dst[b0 * self.tpf:b1 * self.tpf])
             off += b1 - b0
+            if self.rank == self.owner and torch.device(self.device).type == "cuda":
+                ev = torch.cuda.Event()
+                ev.record()
+                own_events.append((b0, b1, ev))
             if self.rank != self.owner:
                 # stream-ordered after the kernel that stored the batch.  One channel per batch: a signal is a binary
                 # semaphore, and reusing one channel would block this rank's stream until the owner had consumed the
@@ -184,6 +189,9 @@ class PeerStoreEncoder:
 
         def ready_fn(i):
             def wait():
+                for b0, b1, ev in own_events:
+                    if b0 <= i < b1:
+                        torch.cuda.current_stream().wait_event(ev)
                 for src, batches in pending.items():
                     if batches and any(b0 <= i < b1 for b0, b1, _ in batches):
                         while batches:                        # consume this source's signals up to the batch holding frame i
