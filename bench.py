@@ -566,13 +566,15 @@ def configs2_frame_parallel(vis, dec, cfg, dev, world, rank, chunk):
     # while stage s-1 runs pass p+1; parallel.LayerPipeline), ranks S..N-1 encode; the decoder ranks do not encode when there
     # are other ranks.  One GPU's decode of this video costs ~1.2x its encode, hence S ~ 0.55 N.
     S = 1 if world < 2 else min(world - 1, max(1, int(round(0.55 * world))))
-    # Two GPUs: both are decoder stages AND both encode (on a side stream, batches dealt round-robin), so each carries half of
-    # the video's encode and half of its decode instead of one GPU idling behind the other.
-    both = world == 2 and os.environ.get("MMD_CONFIGS2_N2_SPLIT", "1") != "0"
+    # Opt-in (MMD_CONFIGS2_ALL_BOTH=1, NOT the default): every rank is a decoder stage AND encodes its round-robin batches on a
+    # side stream.  Measured 561 ms at N = 2 (default split: 602) and 303 ms at N = 4 (341), bit-identical scores, but the same
+    # run HUNG at N = 8 (side-stream signal waits + NCCL point-to-point on 8 ranks; not diagnosed), so the default keeps
+    # dedicated decoder and encoder ranks.
+    both = world >= 2 and os.environ.get("MMD_CONFIGS2_ALL_BOTH") == "1"
     if both:
-        S = 2
+        S = world
     S = int(os.environ.get("MMD_CONFIGS2_STAGES", S))
-    encoders = ([0, 1] if both else list(range(S, world))) if world > 1 else [0]
+    encoders = (list(range(world)) if both else list(range(S, world))) if world > 1 else [0]
     enc_stream = torch.cuda.Stream(device=dev) if both else None
     lo, hi = encoder_frame_range(n, encoders, rank)
     pipe = LayerPipeline(list(range(S)), H, dev) if S > 1 else None
